@@ -183,6 +183,17 @@ pgemb_status pgemb_bind_point(pgemb_index *idx, idx_t id);
  * (embedding.c:606-701).  All n binds run on the device without host round trips. */
 pgemb_status pgemb_insert_batch(pgemb_index *idx, size_t n, const coord_t *coords, const label_t *labels);
 
+/* Bulk build (the GPU counterpart of ambuild's row-by-row hnsw_add_point loop, embedding.c:504-548):
+ * bind nodes [first, first+n) -- already appended, unbound -- in id order, in BATCHES: every node of a
+ * batch runs bindPoint's search (hnswalg.cpp:229) against the graph as it was when the batch started;
+ * own lists are then written and back-links (hnswalg.cpp:182-222) applied per target in source-id order.
+ * Batch size grows with the graph (<= 1/32 of the bound nodes, capped by batch_max), starting with exact
+ * one-by-one binds, so a batch of 1 is exactly one reference insert.  The result is a valid graph in the
+ * reference's format built with the reference's heuristics, but NOT bit-identical to a sequential
+ * build when batch_max > 1 (nodes of one batch do not see each other) -- see DESIGN.md section 8.
+ * seconds_out (optional) receives the wall time including the final synchronisation. */
+pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t n, size_t batch_max, double *seconds_out);
+
 /* Shard top-k merge: for each of nq queries merge n_shards lists of
  * (dist,label) ascending lists of length k (n valid per list in n_in) into the k best by
  * (dist,label) lexicographic order (hnswalg.cpp:236-247 pair order). Device pointers. */

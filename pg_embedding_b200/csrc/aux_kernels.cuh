@@ -1,0 +1,174 @@
+// aux_kernels.cuh -- small kernels around the traversal: cached norms, stand-alone distance batches
+// (the reference's hnsw_dist_func / SQL distance operators, distfunc.c:171-174, embedding.c:1022-1062),
+// reference-record (AoS) ingest/export, shard top-k merge.
+#pragma once
+#include "common.cuh"
+#include "dist_exact.cuh"
+
+namespace pgemb {
+
+// ---- squared norms of stored rows, cosine lane order (4 threads per row) -----------------------
+__global__ void norms_kernel(const float *__restrict__ vectors, uint32_t row_f, uint32_t dim, uint32_t first, uint32_t n,
+							 float *__restrict__ norms)
+{
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t row = t >> 2;
+	const int	   sub = t & 3;
+	// all 32 lanes of a warp must reach the shuffles: clamp the row instead of returning early
+	const uint32_t rr = row < n ? row : (n ? n - 1 : 0);
+	if (n == 0) return;
+	const float *v = vectors + (size_t) (first + rr) * row_f;
+	const float	 s = sqnorm_exact<4>(v, (int) dim, sub);
+	if (row < n && sub == 0) norms[first + row] = s;
+}
+
+// ---- pair distances: out[i] = dist(a[i] | a[0], b[i]); LANES threads per pair, scalar loads --------
+template <int METRIC>
+__global__ void dist_pairs_kernel(const float *__restrict__ a, const float *__restrict__ b, uint32_t dim, uint32_t a_stride,
+								  uint32_t b_stride, uint32_t n, int broadcast_a, float *__restrict__ out)
+{
+	constexpr int  TPR = MetricLanes<METRIC>::LANES;
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t pair = t / TPR;
+	const int	   sub = t % TPR;
+	if (n == 0) return;
+	const uint32_t pp = pair < n ? pair : n - 1;
+	const float	  *av = a + (broadcast_a ? 0 : (size_t) pp * a_stride);
+	const float	  *bv = b + (size_t) pp * b_stride;
+	float		   qn = 0.f, vn = 0.f;
+	if (METRIC == M_COS)
+	{
+		qn = sqnorm_exact<4>(av, (int) dim, sub & 3);
+		vn = sqnorm_exact<4>(bv, (int) dim, sub & 3);
+	}
+	const float d = distance_exact<METRIC, TPR>(av, bv, (int) dim, qn, vn, sub);
+	if (pair < n && sub == 0) out[pair] = d;
+}
+
+// ---- gather distances: out[q][j] = dist(query q, stored node ids[q][j]) with cached norms ---------
+template <int METRIC>
+__global__ void dist_gather_kernel(const float *__restrict__ vectors, const float *__restrict__ norms, uint32_t row_f,
+								   uint32_t dim, uint32_t n_items, const float *__restrict__ queries, uint32_t q_stride,
+								   uint32_t nq, uint32_t k, const uint32_t *__restrict__ ids, float *__restrict__ out)
+{
+	constexpr int  TPR = MetricLanes<METRIC>::LANES;
+	const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t pair = t / TPR;
+	const int	   sub = (int) (t % TPR);
+	const uint64_t total = (uint64_t) nq * k;
+	if (total == 0) return;
+	const uint64_t pp = pair < total ? pair : total - 1;
+	const uint32_t q = (uint32_t) (pp / k);
+	uint32_t	   id = ids[pp];
+	const bool	   ok = id < n_items;
+	if (!ok) id = 0;
+	const float *av = queries + (size_t) q * q_stride;
+	const float *bv = vectors + (size_t) id * row_f;
+	float		 qn = 0.f, vn = 0.f;
+	if (METRIC == M_COS)
+	{
+		qn = sqnorm_exact<4>(av, (int) dim, sub & 3);
+		vn = norms[id];
+	}
+	const float d = distance_exact<METRIC, TPR>(av, bv, (int) dim, qn, vn, sub);
+	if (pair < total && sub == 0) out[pair] = ok ? d : __int_as_float(0x7fc00000);
+}
+
+// ---- reference record layout (embedding.c:224-228, :619-621) <-> SoA --------------------------------
+// record = [u32 count | u32 links[maxM] | f32 coords[dim] | u64 label], records `stride` bytes apart.
+// One warp per record; byte-granular because the 8-byte label is only 4-byte aligned in general.
+__global__ void records_unpack_kernel(const unsigned char *__restrict__ recs, size_t stride, uint32_t n, uint32_t first,
+									  uint32_t dim, uint32_t maxM, uint32_t row_f, uint32_t link_stride,
+									  float *__restrict__ vectors, uint32_t *__restrict__ links, uint64_t *__restrict__ labels)
+{
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (w >= n) return;
+	const unsigned char *rec = recs + (size_t) w * stride;
+	const uint32_t		*rl = reinterpret_cast<const uint32_t *>(rec);
+	const float			*rc = reinterpret_cast<const float *>(rec + (size_t) (maxM + 1) * 4);
+	const uint32_t		*rlab = reinterpret_cast<const uint32_t *>(rec + (size_t) (maxM + 1) * 4 + (size_t) dim * 4);
+	const size_t		 id = (size_t) first + w;
+	for (uint32_t i = lane; i < link_stride; i += 32) links[id * link_stride + i] = (i <= maxM) ? rl[i] : 0u;
+	for (uint32_t i = lane; i < row_f; i += 32) vectors[id * row_f + i] = (i < dim) ? rc[i] : 0.0f;
+	if (lane == 0) labels[id] = (uint64_t) rlab[0] | ((uint64_t) rlab[1] << 32);
+}
+
+__global__ void records_pack_kernel(unsigned char *__restrict__ recs, size_t stride, uint32_t n, uint32_t first, uint32_t dim,
+									uint32_t maxM, uint32_t row_f, uint32_t link_stride, const float *__restrict__ vectors,
+									const uint32_t *__restrict__ links, const uint64_t *__restrict__ labels)
+{
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (w >= n) return;
+	unsigned char *rec = recs + (size_t) w * stride;
+	uint32_t	  *rl = reinterpret_cast<uint32_t *>(rec);
+	float		  *rc = reinterpret_cast<float *>(rec + (size_t) (maxM + 1) * 4);
+	uint32_t	  *rlab = reinterpret_cast<uint32_t *>(rec + (size_t) (maxM + 1) * 4 + (size_t) dim * 4);
+	const size_t   id = (size_t) first + w;
+	for (uint32_t i = lane; i <= maxM; i += 32) rl[i] = links[id * link_stride + i];
+	for (uint32_t i = lane; i < dim; i += 32) rc[i] = vectors[id * row_f + i];
+	if (lane == 0)
+	{
+		const uint64_t l = labels[id];
+		rlab[0] = (uint32_t) l;
+		rlab[1] = (uint32_t) (l >> 32);
+	}
+}
+
+// ---- K5: per-query merge of n_shards ascending (dist,label) lists of length k -------------------------
+// Order = (dist,label) lexicographic, the pair order of searchKnn's result queue (hnswalg.cpp:236-247).
+// One warp per query; rank of an element = its index in its own list + sum over the other lists of the
+// number of smaller elements (binary search), so no sort is needed.
+__global__ void merge_topk_kernel(uint32_t nq, uint32_t n_shards, uint32_t k, const float *__restrict__ din,
+								  const uint64_t *__restrict__ lin, const int32_t *__restrict__ nin, float *__restrict__ dout,
+								  uint64_t *__restrict__ lout, int32_t *__restrict__ nout)
+{
+	const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (q >= nq) return;
+	// input layout: [shard][query][k]
+	uint32_t total = 0;
+	for (uint32_t s = 0; s < n_shards; s++) total += (uint32_t) max(0, min((int32_t) k, nin[(size_t) s * nq + q]));
+	const uint32_t keep = min(total, k);
+	for (uint32_t e = lane; e < n_shards * k; e += 32)
+	{
+		const uint32_t s = e / k, i = e % k;
+		const uint32_t ns = (uint32_t) max(0, min((int32_t) k, nin[(size_t) s * nq + q]));
+		if (i >= ns) continue;
+		const size_t   base = ((size_t) s * nq + q) * k;
+		const uint32_t od = f2o(din[base + i]);
+		const uint64_t ol = lin[base + i];
+		uint32_t	   rank = i;
+		for (uint32_t s2 = 0; s2 < n_shards; s2++)
+		{
+			if (s2 == s) continue;
+			const uint32_t n2 = (uint32_t) max(0, min((int32_t) k, nin[(size_t) s2 * nq + q]));
+			const size_t   b2 = ((size_t) s2 * nq + q) * k;
+			uint32_t	   lo = 0, hi = n2;
+			while (lo < hi)
+			{
+				const uint32_t mid = (lo + hi) >> 1;
+				const uint32_t d2 = f2o(din[b2 + mid]);
+				const uint64_t l2 = lin[b2 + mid];
+				// element of another shard sorts first if smaller, or equal with the lower shard index
+				const bool less = d2 < od || (d2 == od && (l2 < ol || (l2 == ol && s2 < s)));
+				if (less) lo = mid + 1; else hi = mid;
+			}
+			rank += lo;
+		}
+		if (rank < keep)
+		{
+			dout[(size_t) q * k + rank] = din[base + i];
+			lout[(size_t) q * k + rank] = ol;
+		}
+	}
+	for (uint32_t i = keep + lane; i < k; i += 32)
+	{
+		dout[(size_t) q * k + i] = __int_as_float(0x7f800000);
+		lout[(size_t) q * k + i] = ~0ull;
+	}
+	if (lane == 0) nout[q] = (int32_t) keep;
+}
+
+}  // namespace pgemb

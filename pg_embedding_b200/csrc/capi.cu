@@ -1,0 +1,1026 @@
+// capi.cu -- host side of the C ABI declared in include/pgemb_b200.h.
+//
+// Mirrors the reference's host-facing contract for the hot path (embedding.h:44-56): hnsw_search,
+// hnsw_bind_point, hnsw_dist_func, hnsw_init_dist_func keep their names, argument meaning, ownership
+// (malloc'd results freed by the caller, embedding.c:327) and error behaviour (bool false, no C++
+// exception crosses -- hnswalg.cpp:258-276), and adds the bulk/device entry points a GPU needs.
+// There is no CPU implementation of any of it in this library: without a usable CUDA device every
+// entry point fails with PGEMB_ERR_CUDA.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "bind_kernel.cuh"
+#include "common.cuh"
+#include "search_kernel.cuh"
+
+using namespace pgemb;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t>	g_launches{0};
+
+static pgemb_status fail(pgemb_status st, const std::string &msg)
+{
+	g_last_error = msg;
+	return st;
+}
+
+#define CU_TRY(expr)                                                                                             \
+	do {                                                                                                         \
+		cudaError_t _e = (expr);                                                                                 \
+		if (_e != cudaSuccess)                                                                                   \
+			return fail(PGEMB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+	} while (0)
+
+extern "C" const char *pgemb_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *pgemb_version(void) { return "pg_embedding_b200 0.1 (sm_100a)"; }
+extern "C" uint64_t	   pgemb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int pgemb_device_count(void)
+{
+	int			n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// metadata (embedding.c:222-235)
+// ------------------------------------------------------------------------------------------------
+extern "C" pgemb_status pgemb_meta_init(HnswMetadata *meta, size_t dims, size_t m, size_t efConstruction, size_t efSearch,
+										dist_func_t dist)
+{
+	if (!meta || dims == 0) return fail(PGEMB_ERR_ARG, "HNSW index requires 'dims' to be specified");  // embedding.c:219-221
+	if (efConstruction < 1 || efSearch < 1) return fail(PGEMB_ERR_ARG, "efconstruction/efsearch must be >= 1");
+	if ((int) dist < 0 || (int) dist > 2) return fail(PGEMB_ERR_ARG, "unknown distance function");
+	memset(meta, 0, sizeof(*meta));
+	meta->dim = dims;
+	meta->M = m;
+	meta->maxM = m * 2;
+	meta->data_size = dims * sizeof(coord_t);
+	meta->offset_data = (meta->maxM + 1) * sizeof(idx_t);
+	meta->offset_label = meta->offset_data + meta->data_size;
+	meta->size_data_per_element = meta->offset_label + sizeof(label_t);
+	// BLCKSZ 8192, MAXALIGN(SizeOfPageHeaderData) 24, sizeof(HnswPageOpaque) 4, sizeof(ItemIdData) 4
+	meta->elems_per_page = (8192 - 24 - 4) / (meta->size_data_per_element + 4);
+	meta->efConstruction = efConstruction;
+	meta->efSearch = efSearch;
+	meta->dist_func = dist;
+	meta->enterpoint_node = 0;
+	if (meta->elems_per_page == 0) return fail(PGEMB_ERR_ARG, "Element doesn't fit in Postgres page");  // embedding.c:229-231
+	return PGEMB_OK;
+}
+
+extern "C" bool hnsw_is_deleted(label_t label) { return ((label >> 48) & 1u) != 0; }
+
+// ------------------------------------------------------------------------------------------------
+// the device index
+// ------------------------------------------------------------------------------------------------
+struct SearchConfig
+{
+	int		 tpr = 0;
+	uint32_t stages = 0, row_smem = 0, smem = 0, slots = 0;
+	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_hopnorm, off_mbar;
+	uint32_t ef = 0;
+};
+
+struct pgemb_index
+{
+	HnswMetadata meta;
+	int			 device = 0;
+	int			 sm_count = 0;
+	size_t		 capacity = 0, n = 0;
+	uint32_t	 row_f = 0, link_stride = 0;
+	float		*d_vectors = nullptr;
+	uint32_t	*d_links = nullptr;
+	uint64_t	*d_labels = nullptr;
+	float		*d_norms = nullptr;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t	 ev0 = nullptr, ev1 = nullptr;
+	bool		 ev_valid = false;
+	// search workspace
+	uint32_t	  ws_slots = 0, ws_ef = 0, vis_words = 0, vlog_cap = 0;
+	uint32_t	 *d_visited = nullptr, *d_vlog = nullptr;
+	uint64_t	 *d_ovf = nullptr;
+	unsigned int *d_counter = nullptr;
+	int			 *d_error = nullptr;
+	// staging for the host-pointer API
+	void  *d_stage = nullptr;
+	size_t stage_bytes = 0;
+	// bind workspace
+	BindWorkspace bind_ws;
+};
+
+static pgemb_status set_device(const pgemb_index *idx)
+{
+	CU_TRY(cudaSetDevice(idx->device));
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_create(const HnswMetadata *meta, size_t capacity, int device, pgemb_index **out)
+{
+	if (!meta || !out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (meta->dim == 0 || meta->dim > 65535) return fail(PGEMB_ERR_ARG, "dims out of range (1..65535; stored as uint16 on pages, embedding.c:494)");
+	if (meta->maxM != meta->M * 2) return fail(PGEMB_ERR_ARG, "maxM must be 2*M (embedding.c:224)");
+	if (meta->maxM > 4096) return fail(PGEMB_ERR_ARG, "maxM > 4096 unsupported");
+	if (capacity == 0 || capacity >= (1ull << 31)) return fail(PGEMB_ERR_ARG, "capacity must be in [1, 2^31)");
+	int ndev = 0;
+	CU_TRY(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return fail(PGEMB_ERR_CUDA, "no such CUDA device");
+	CU_TRY(cudaSetDevice(device));
+	pgemb_index *idx = new (std::nothrow) pgemb_index();
+	if (!idx) return fail(PGEMB_ERR_NOMEM, "out of host memory");
+	idx->meta = *meta;
+	idx->device = device;
+	idx->capacity = capacity;
+	idx->row_f = (uint32_t) ((meta->dim + 3) & ~(size_t) 3);
+	idx->link_stride = (uint32_t) ((meta->maxM + 1 + 3) & ~(size_t) 3);
+	cudaDeviceProp prop;
+	CU_TRY(cudaGetDeviceProperties(&prop, device));
+	idx->sm_count = prop.multiProcessorCount;
+	cudaError_t e;
+#define ALLOC(ptr, bytes)                                                                                 \
+	if ((e = cudaMalloc((void **) &(ptr), (bytes))) != cudaSuccess)                                       \
+	{                                                                                                     \
+		pgemb_index_destroy(idx);                                                                         \
+		return fail(PGEMB_ERR_NOMEM, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e));       \
+	}
+	ALLOC(idx->d_vectors, capacity * idx->row_f * sizeof(float));
+	ALLOC(idx->d_links, capacity * idx->link_stride * sizeof(uint32_t));
+	ALLOC(idx->d_labels, capacity * sizeof(uint64_t));
+	ALLOC(idx->d_norms, capacity * sizeof(float));
+	ALLOC(idx->d_counter, sizeof(unsigned int) * 4);
+	ALLOC(idx->d_error, sizeof(int));
+#undef ALLOC
+	CU_TRY(cudaMemset(idx->d_error, 0, sizeof(int)));
+	CU_TRY(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+	CU_TRY(cudaEventCreate(&idx->ev0));
+	CU_TRY(cudaEventCreate(&idx->ev1));
+	*out = idx;
+	return PGEMB_OK;
+}
+
+extern "C" void pgemb_index_destroy(pgemb_index *idx)
+{
+	if (!idx) return;
+	cudaSetDevice(idx->device);
+	cudaDeviceSynchronize();
+	cudaFree(idx->d_vectors);
+	cudaFree(idx->d_links);
+	cudaFree(idx->d_labels);
+	cudaFree(idx->d_norms);
+	cudaFree(idx->d_visited);
+	cudaFree(idx->d_vlog);
+	cudaFree(idx->d_ovf);
+	cudaFree(idx->d_counter);
+	cudaFree(idx->d_error);
+	cudaFree(idx->d_stage);
+	bind_ws_free(idx->bind_ws);
+	if (idx->stream) cudaStreamDestroy(idx->stream);
+	if (idx->ev0) cudaEventDestroy(idx->ev0);
+	if (idx->ev1) cudaEventDestroy(idx->ev1);
+	delete idx;
+}
+
+extern "C" size_t pgemb_index_size(const pgemb_index *idx) { return idx ? idx->n : 0; }
+extern "C" size_t pgemb_index_capacity(const pgemb_index *idx) { return idx ? idx->capacity : 0; }
+extern "C" int	  pgemb_index_device(const pgemb_index *idx) { return idx ? idx->device : -1; }
+
+static pgemb_status ensure_stage(pgemb_index *idx, size_t bytes)
+{
+	if (idx->stage_bytes >= bytes) return PGEMB_OK;
+	if (idx->d_stage) cudaFree(idx->d_stage);
+	idx->d_stage = nullptr;
+	idx->stage_bytes = 0;
+	size_t want = bytes + bytes / 4 + 4096;
+	CU_TRY(cudaMalloc(&idx->d_stage, want));
+	idx->stage_bytes = want;
+	return PGEMB_OK;
+}
+
+static pgemb_status compute_norms(pgemb_index *idx, size_t first, size_t n, cudaStream_t s)
+{
+	if (idx->meta.dist_func != DIST_COSINE || n == 0) return PGEMB_OK;
+	const uint32_t threads = 128;
+	const uint32_t blocks = (uint32_t) ((n * 4 + threads - 1) / threads);
+	norms_kernel<<<blocks, threads, 0, s>>>(idx->d_vectors, idx->row_f, (uint32_t) idx->meta.dim, (uint32_t) first, (uint32_t) n,
+											idx->d_norms);
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	return PGEMB_OK;
+}
+
+static pgemb_status append_common(pgemb_index *idx, size_t n, const coord_t *coords, const label_t *labels, const idx_t *links,
+								  cudaMemcpyKind kind, cudaStream_t s)
+{
+	if (!idx || (!coords && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (idx->n + n > idx->capacity) return fail(PGEMB_ERR_CAPACITY, "index capacity exceeded");
+	if (n == 0) return PGEMB_OK;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t first = idx->n;
+	const size_t dim = idx->meta.dim, maxM1 = idx->meta.maxM + 1;
+	// rows: zero the padding, then a pitched copy dim -> row_f
+	if (idx->row_f != dim) CU_TRY(cudaMemsetAsync(idx->d_vectors + first * idx->row_f, 0, n * idx->row_f * sizeof(float), s));
+	CU_TRY(cudaMemcpy2DAsync(idx->d_vectors + first * idx->row_f, idx->row_f * sizeof(float), coords, dim * sizeof(float),
+							 dim * sizeof(float), n, kind, s));
+	CU_TRY(cudaMemsetAsync(idx->d_links + first * idx->link_stride, 0, n * idx->link_stride * sizeof(uint32_t), s));
+	if (links)
+		CU_TRY(cudaMemcpy2DAsync(idx->d_links + first * idx->link_stride, idx->link_stride * sizeof(uint32_t), links,
+								 maxM1 * sizeof(uint32_t), maxM1 * sizeof(uint32_t), n, kind, s));
+	if (labels)
+		CU_TRY(cudaMemcpyAsync(idx->d_labels + first, labels, n * sizeof(uint64_t), kind, s));
+	else
+	{
+		std::vector<uint64_t> tmp(n);
+		for (size_t i = 0; i < n; i++) tmp[i] = first + i;
+		CU_TRY(cudaMemcpyAsync(idx->d_labels + first, tmp.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+		CU_TRY(cudaStreamSynchronize(s));
+	}
+	st = compute_norms(idx, first, n, s);
+	if (st) return st;
+	idx->n += n;
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_append(pgemb_index *idx, size_t n, const coord_t *coords, const label_t *labels,
+										   const idx_t *links)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	pgemb_status st = append_common(idx, n, coords, labels, links, cudaMemcpyHostToDevice, idx->stream);
+	if (st) return st;
+	CU_TRY(cudaStreamSynchronize(idx->stream));
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_append_device(pgemb_index *idx, size_t n, const coord_t *d_coords, const label_t *d_labels,
+												  const idx_t *d_links, void *stream)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	return append_common(idx, n, d_coords, d_labels, d_links, cudaMemcpyDeviceToDevice, (cudaStream_t) stream);
+}
+
+extern "C" pgemb_status pgemb_index_append_records(pgemb_index *idx, size_t n, const void *records, size_t record_stride)
+{
+	if (!idx || (!records && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (record_stride < idx->meta.size_data_per_element || (record_stride & 3)) return fail(PGEMB_ERR_ARG, "bad record stride");
+	if (idx->n + n > idx->capacity) return fail(PGEMB_ERR_CAPACITY, "index capacity exceeded");
+	if (n == 0) return PGEMB_OK;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t chunk = 1u << 16;
+	for (size_t done = 0; done < n; done += chunk)
+	{
+		const size_t m = (n - done < chunk) ? (n - done) : chunk;
+		st = ensure_stage(idx, m * record_stride);
+		if (st) return st;
+		CU_TRY(cudaMemcpyAsync(idx->d_stage, (const char *) records + done * record_stride, m * record_stride, cudaMemcpyHostToDevice,
+							   idx->stream));
+		const uint32_t threads = 128, blocks = (uint32_t) ((m * 32 + threads - 1) / threads);
+		records_unpack_kernel<<<blocks, threads, 0, idx->stream>>>((const unsigned char *) idx->d_stage, record_stride, (uint32_t) m,
+																   (uint32_t) (idx->n + done), (uint32_t) idx->meta.dim,
+																   (uint32_t) idx->meta.maxM, idx->row_f, idx->link_stride,
+																   idx->d_vectors, idx->d_links, idx->d_labels);
+		g_launches++;
+		CU_TRY(cudaGetLastError());
+		CU_TRY(cudaStreamSynchronize(idx->stream));
+	}
+	st = compute_norms(idx, idx->n, n, idx->stream);
+	if (st) return st;
+	CU_TRY(cudaStreamSynchronize(idx->stream));
+	idx->n += n;
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_export_records(const pgemb_index *cidx, size_t first, size_t n, void *records, size_t record_stride)
+{
+	pgemb_index *idx = const_cast<pgemb_index *>(cidx);
+	if (!idx || (!records && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (record_stride < idx->meta.size_data_per_element || (record_stride & 3)) return fail(PGEMB_ERR_ARG, "bad record stride");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "range beyond index size");
+	if (n == 0) return PGEMB_OK;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t chunk = 1u << 16;
+	for (size_t done = 0; done < n; done += chunk)
+	{
+		const size_t m = (n - done < chunk) ? (n - done) : chunk;
+		st = ensure_stage(idx, m * record_stride);
+		if (st) return st;
+		CU_TRY(cudaMemsetAsync(idx->d_stage, 0, m * record_stride, idx->stream));
+		const uint32_t threads = 128, blocks = (uint32_t) ((m * 32 + threads - 1) / threads);
+		records_pack_kernel<<<blocks, threads, 0, idx->stream>>>((unsigned char *) idx->d_stage, record_stride, (uint32_t) m,
+																 (uint32_t) (first + done), (uint32_t) idx->meta.dim,
+																 (uint32_t) idx->meta.maxM, idx->row_f, idx->link_stride, idx->d_vectors,
+																 idx->d_links, idx->d_labels);
+		g_launches++;
+		CU_TRY(cudaGetLastError());
+		CU_TRY(cudaMemcpyAsync((char *) records + done * record_stride, idx->d_stage, m * record_stride, cudaMemcpyDeviceToHost,
+							   idx->stream));
+		CU_TRY(cudaStreamSynchronize(idx->stream));
+	}
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_get_links(const pgemb_index *idx, size_t first, size_t n, idx_t *links_out)
+{
+	if (!idx || (!links_out && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "range beyond index size");
+	if (n == 0) return PGEMB_OK;
+	CU_TRY(cudaSetDevice(idx->device));
+	const size_t maxM1 = idx->meta.maxM + 1;
+	CU_TRY(cudaMemcpy2DAsync(links_out, maxM1 * sizeof(uint32_t), idx->d_links + first * idx->link_stride,
+							 idx->link_stride * sizeof(uint32_t), maxM1 * sizeof(uint32_t), n, cudaMemcpyDeviceToHost, idx->stream));
+	CU_TRY(cudaStreamSynchronize(idx->stream));
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_set_links(pgemb_index *idx, size_t first, size_t n, const idx_t *links)
+{
+	if (!idx || (!links && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "range beyond index size");
+	if (n == 0) return PGEMB_OK;
+	CU_TRY(cudaSetDevice(idx->device));
+	const size_t maxM1 = idx->meta.maxM + 1;
+	CU_TRY(cudaMemcpy2DAsync(idx->d_links + first * idx->link_stride, idx->link_stride * sizeof(uint32_t), links,
+							 maxM1 * sizeof(uint32_t), maxM1 * sizeof(uint32_t), n, cudaMemcpyHostToDevice, idx->stream));
+	CU_TRY(cudaStreamSynchronize(idx->stream));
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_get_labels(const pgemb_index *idx, size_t first, size_t n, label_t *labels_out)
+{
+	if (!idx || (!labels_out && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "range beyond index size");
+	if (n == 0) return PGEMB_OK;
+	CU_TRY(cudaSetDevice(idx->device));
+	CU_TRY(cudaMemcpyAsync(labels_out, idx->d_labels + first, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, idx->stream));
+	CU_TRY(cudaStreamSynchronize(idx->stream));
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_set_labels(pgemb_index *idx, size_t first, size_t n, const label_t *labels)
+{
+	if (!idx || (!labels && n)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "range beyond index size");
+	if (n == 0) return PGEMB_OK;
+	CU_TRY(cudaSetDevice(idx->device));
+	CU_TRY(cudaMemcpyAsync(idx->d_labels + first, labels, n * sizeof(uint64_t), cudaMemcpyHostToDevice, idx->stream));
+	CU_TRY(cudaStreamSynchronize(idx->stream));
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_index_truncate(pgemb_index *idx)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	idx->n = 0;
+	return PGEMB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// search launch configuration
+// ------------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+	const char *v = getenv(name);
+	return (v && *v) ? atoi(v) : dflt;
+}
+
+static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c)
+{
+	const int  metric = (int) idx->meta.dist_func;
+	const int  lanes = (metric == DIST_L2) ? 8 : 4;
+	int		   tpr = env_int("PGEMB_TPR", 4);
+	if (tpr != 1 && tpr != 2 && tpr != 4 && tpr != 8) tpr = 4;
+	if (tpr > lanes) tpr = lanes;
+	if (metric == DIST_L2 && tpr == 1) tpr = 2;
+	const uint32_t R = 32u / (uint32_t) tpr;
+	const uint32_t row_bytes = idx->row_f * 4u;
+	// bank-conflict-free row pitch in shared memory: 16 (mod 128) for the 4-lane metrics, 32 (mod 128) for L2
+	const uint32_t resid = (metric == DIST_L2) ? 32u : 16u;
+	uint32_t	   row_smem = row_bytes / 128u * 128u + resid;
+	if (row_smem < row_bytes) row_smem += 128u;
+	const uint32_t maxM = (uint32_t) idx->meta.maxM;
+	const uint32_t hopcap = maxM > 1 ? maxM : 1;
+	const uint32_t groups_per_hop = (hopcap + R - 1) / R;
+	const uint32_t smem_sm = 233472u;  // 228 KB per SM on sm_100
+	const uint32_t max_cta = 232448u;  // 227 KB per CTA
+
+	auto layout = [&](uint32_t stages, SearchConfig *o) {
+		uint32_t off = 0;
+		o->off_q = off;			off = align_up(off + row_bytes, 128);
+		o->off_ring = off;		off = align_up(off + stages * R * row_smem, 16);
+		o->off_res = off;		off += 2u * ef * 8u;
+		o->off_hopkey = off;	off += hopcap * 8u;
+		o->off_acckey = off;	off += hopcap * 8u;
+		o->off_evict = off;		off += hopcap * 8u;
+		o->off_hopid = off;		off += hopcap * 4u;
+		o->off_hopnorm = off;	off += hopcap * 4u;
+		off = align_up(off, 8);
+		o->off_mbar = off;		off += stages * 8u;
+		o->smem = align_up(off, 128);
+		o->stages = stages;
+	};
+
+	int		 want_slots = env_int("PGEMB_SLOTS_PER_SM", 0);
+	int		 want_stages = env_int("PGEMB_STAGES", 0);
+	uint32_t stages;
+	if (want_stages > 0)
+		stages = (uint32_t) want_stages;
+	else
+	{
+		// default: a ring of ~48 KB (or one whole hop if that is smaller), at least 2 stages when they fit
+		const uint32_t target = 51200u;
+		stages = target / (R * row_smem);
+		if (stages < 1) stages = 1;
+	}
+	if (stages > groups_per_hop) stages = groups_per_hop;
+	if (stages > 32) stages = 32;
+	if (stages < 1) stages = 1;
+	SearchConfig t;
+	for (;;)
+	{
+		layout(stages, &t);
+		if (t.smem <= max_cta || stages == 1) break;
+		stages -= 1;
+	}
+	if (t.smem > max_cta) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
+	*c = t;
+	c->tpr = tpr;
+	c->row_smem = row_smem;
+	c->ef = ef;
+	uint32_t slots_sm = smem_sm / (c->smem + 1024u);
+	if (slots_sm < 1) slots_sm = 1;
+	if (slots_sm > 16) slots_sm = 16;
+	if (want_slots > 0 && (uint32_t) want_slots < slots_sm) slots_sm = (uint32_t) want_slots;
+	c->slots = slots_sm * (uint32_t) idx->sm_count;
+	return PGEMB_OK;
+}
+
+typedef void (*search_fn_t)(const SearchParams);
+
+static search_fn_t pick_search_kernel(int metric, int tpr)
+{
+	switch (metric)
+	{
+		case DIST_L2:
+			if (tpr == 2) return search_kernel<M_L2, 2>;
+			if (tpr == 4) return search_kernel<M_L2, 4>;
+			if (tpr == 8) return search_kernel<M_L2, 8>;
+			break;
+		case DIST_COSINE:
+			if (tpr == 1) return search_kernel<M_COS, 1>;
+			if (tpr == 2) return search_kernel<M_COS, 2>;
+			if (tpr == 4) return search_kernel<M_COS, 4>;
+			break;
+		case DIST_MANHATTAN:
+			if (tpr == 1) return search_kernel<M_MAN, 1>;
+			if (tpr == 2) return search_kernel<M_MAN, 2>;
+			if (tpr == 4) return search_kernel<M_MAN, 4>;
+			break;
+	}
+	return nullptr;
+}
+
+static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t ef)
+{
+	const uint32_t vis_words = (uint32_t) ((idx->capacity + 31) / 32);
+	if (idx->ws_slots < slots || idx->vis_words != vis_words)
+	{
+		cudaFree(idx->d_visited);
+		cudaFree(idx->d_vlog);
+		idx->d_visited = nullptr;
+		idx->d_vlog = nullptr;
+		idx->ws_slots = 0;
+		idx->vlog_cap = (uint32_t) (idx->capacity < 32768 ? idx->capacity : 32768);
+		CU_TRY(cudaMalloc((void **) &idx->d_visited, (size_t) slots * vis_words * 4));
+		CU_TRY(cudaMemset(idx->d_visited, 0, (size_t) slots * vis_words * 4));
+		CU_TRY(cudaMalloc((void **) &idx->d_vlog, (size_t) slots * idx->vlog_cap * 4));
+		idx->ws_slots = slots;
+		idx->vis_words = vis_words;
+		cudaFree(idx->d_ovf);
+		idx->d_ovf = nullptr;
+		idx->ws_ef = 0;
+	}
+	if (idx->ws_ef < ef || !idx->d_ovf)
+	{
+		cudaFree(idx->d_ovf);
+		idx->d_ovf = nullptr;
+		CU_TRY(cudaMalloc((void **) &idx->d_ovf, (size_t) idx->ws_slots * ef * 8));
+		idx->ws_ef = ef;
+	}
+	return PGEMB_OK;
+}
+
+// Launch the traversal for nq queries.  All pointers are device pointers.
+pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, uint32_t q_stride, const uint32_t *d_query_ids,
+						   uint32_t n_items, size_t ef, int raw_mode, label_t *d_labels_out, dist_t *d_dists_out, idx_t *d_ids_out,
+						   int32_t *d_n_out, uint32_t *d_stats_out, cudaStream_t s, bool time_it)
+{
+	if (!idx || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (ef < 1 || ef > (1u << 20)) return fail(PGEMB_ERR_ARG, "ef out of range");
+	if (nq == 0) return PGEMB_OK;
+	if (nq >= (1ull << 31)) return fail(PGEMB_ERR_ARG, "too many queries in one batch");
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	SearchConfig cfg;
+	st = make_config(idx, (uint32_t) ef, &cfg);
+	if (st) return st;
+	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, cfg.tpr);
+	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for metric/TPR");
+	CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.smem));
+	int occ = 0;
+	CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, cfg.smem));
+	if (occ < 1) return fail(PGEMB_ERR_CAPACITY, "search kernel cannot be resident (shared memory)");
+	uint32_t slots = cfg.slots;
+	if ((uint32_t) occ * (uint32_t) idx->sm_count < slots) slots = (uint32_t) occ * (uint32_t) idx->sm_count;
+	st = ensure_workspace(idx, slots, (uint32_t) ef);
+	if (st) return st;
+
+	SearchParams p;
+	memset(&p, 0, sizeof(p));
+	p.vectors = idx->d_vectors;
+	p.links = idx->d_links;
+	p.labels = idx->d_labels;
+	p.norms = idx->d_norms;
+	p.n_items = n_items;
+	p.dim = (uint32_t) idx->meta.dim;
+	p.row_f = idx->row_f;
+	p.link_stride = idx->link_stride;
+	p.maxM = (uint32_t) idx->meta.maxM;
+	p.entry = idx->meta.enterpoint_node;
+	p.queries = d_queries;
+	p.query_ids = d_query_ids;
+	p.nq = (uint32_t) nq;
+	p.q_stride = q_stride;
+	p.ef = (uint32_t) ef;
+	p.raw_mode = raw_mode ? 1u : 0u;
+	p.labels_out = d_labels_out;
+	p.dists_out = d_dists_out;
+	p.ids_out = d_ids_out;
+	p.n_out = d_n_out;
+	p.stats_out = d_stats_out;
+	p.visited = idx->d_visited;
+	p.vlog = idx->d_vlog;
+	p.ovf = idx->d_ovf;
+	p.vis_words = idx->vis_words;
+	p.vlog_cap = idx->vlog_cap;
+	p.counter = idx->d_counter;
+	p.error_flag = idx->d_error;
+	p.stages = cfg.stages;
+	p.row_smem = cfg.row_smem;
+	p.row_bytes = idx->row_f * 4u;
+	p.off_q = cfg.off_q;
+	p.off_ring = cfg.off_ring;
+	p.off_res = cfg.off_res;
+	p.off_hopkey = cfg.off_hopkey;
+	p.off_acckey = cfg.off_acckey;
+	p.off_evict = cfg.off_evict;
+	p.off_hopid = cfg.off_hopid;
+	p.off_hopnorm = cfg.off_hopnorm;
+	p.off_mbar = cfg.off_mbar;
+
+	CU_TRY(cudaMemsetAsync(idx->d_counter, 0, sizeof(unsigned int), s));
+	const uint32_t grid = (uint32_t) (nq < slots ? nq : slots);
+	if (time_it) CU_TRY(cudaEventRecord(idx->ev0, s));
+	fn<<<grid, 32, cfg.smem, s>>>(p);
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	if (time_it)
+	{
+		CU_TRY(cudaEventRecord(idx->ev1, s));
+		idx->ev_valid = true;
+	}
+	return PGEMB_OK;
+}
+
+static pgemb_status check_device_error(pgemb_index *idx, cudaStream_t s)
+{
+	int err = 0;
+	CU_TRY(cudaMemcpyAsync(&err, idx->d_error, sizeof(int), cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaStreamSynchronize(s));
+	if (err != 0)
+	{
+		CU_TRY(cudaMemsetAsync(idx->d_error, 0, sizeof(int), s));
+		return fail(PGEMB_ERR_STATE, err == 1 ? "corrupt graph: link id / count out of range"
+											  : (err == 2 ? "tie-overflow buffer exceeded" : "bind failed (reference would throw)"));
+	}
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_search_batch_device(pgemb_index *idx, size_t nq, const coord_t *d_queries, size_t ef,
+												  label_t *d_labels_out, dist_t *d_dists_out, idx_t *d_ids_out, int32_t *d_n_out,
+												  uint32_t *d_stats_out, void *stream)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	return launch_search(idx, nq, d_queries, (uint32_t) idx->meta.dim, nullptr, (uint32_t) idx->n, ef, 0, d_labels_out, d_dists_out,
+						 d_ids_out, d_n_out, d_stats_out, (cudaStream_t) stream, true);
+}
+
+extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const coord_t *queries, size_t ef, label_t *labels_out,
+										   dist_t *dists_out, idx_t *ids_out, int32_t *n_out, uint32_t *stats_out)
+{
+	if (!idx || !queries || !n_out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (nq == 0) return PGEMB_OK;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t dim = idx->meta.dim;
+	const size_t qb = align_up((uint32_t) 0, 1) + nq * dim * sizeof(float);
+	const size_t lb = nq * ef * sizeof(uint64_t), db = nq * ef * sizeof(float), ib = nq * ef * sizeof(uint32_t);
+	const size_t nb = nq * sizeof(int32_t), sb = nq * 4 * sizeof(uint32_t);
+	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+	const size_t total = up(qb) + up(lb) + up(db) + up(ib) + up(nb) + up(sb);
+	st = ensure_stage(idx, total);
+	if (st) return st;
+	char	 *base = (char *) idx->d_stage;
+	float	 *d_q = (float *) base;				base += up(qb);
+	uint64_t *d_l = (uint64_t *) base;			base += up(lb);
+	float	 *d_d = (float *) base;				base += up(db);
+	uint32_t *d_i = (uint32_t *) base;			base += up(ib);
+	int32_t	 *d_n = (int32_t *) base;			base += up(nb);
+	uint32_t *d_s = (uint32_t *) base;
+	cudaStream_t s = idx->stream;
+	CU_TRY(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, s));
+	st = launch_search(idx, nq, d_q, (uint32_t) dim, nullptr, (uint32_t) idx->n, ef, 0, labels_out ? d_l : nullptr,
+					   dists_out ? d_d : nullptr, ids_out ? d_i : nullptr, d_n, stats_out ? d_s : nullptr, s, true);
+	if (st) return st;
+	if (labels_out) CU_TRY(cudaMemcpyAsync(labels_out, d_l, lb, cudaMemcpyDeviceToHost, s));
+	if (dists_out) CU_TRY(cudaMemcpyAsync(dists_out, d_d, db, cudaMemcpyDeviceToHost, s));
+	if (ids_out) CU_TRY(cudaMemcpyAsync(ids_out, d_i, ib, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaMemcpyAsync(n_out, d_n, nb, cudaMemcpyDeviceToHost, s));
+	if (stats_out) CU_TRY(cudaMemcpyAsync(stats_out, d_s, sb, cudaMemcpyDeviceToHost, s));
+	return check_device_error(idx, s);
+}
+
+extern "C" float pgemb_last_kernel_ms(const pgemb_index *idx)
+{
+	if (!idx || !idx->ev_valid) return -1.0f;
+	float ms = -1.0f;
+	if (cudaSetDevice(idx->device) != cudaSuccess) return -1.0f;
+	if (cudaEventSynchronize(idx->ev1) != cudaSuccess) return -1.0f;
+	if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) != cudaSuccess) return -1.0f;
+	return ms;
+}
+
+// ------------------------------------------------------------------------------------------------
+// distances (distfunc.c:157-174; embedding.c:1022-1062)
+// ------------------------------------------------------------------------------------------------
+static pgemb_status launch_pairs(int metric, const float *d_a, const float *d_b, uint32_t dim, uint32_t n, int broadcast_a, float *d_out,
+								 cudaStream_t s)
+{
+	const uint32_t threads = 128;
+	const uint32_t lanes = (metric == DIST_L2) ? 8 : 4;
+	const uint32_t blocks = (uint32_t) (((size_t) n * lanes + threads - 1) / threads);
+	switch (metric)
+	{
+		case DIST_L2: dist_pairs_kernel<M_L2><<<blocks, threads, 0, s>>>(d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
+		case DIST_COSINE: dist_pairs_kernel<M_COS><<<blocks, threads, 0, s>>>(d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
+		case DIST_MANHATTAN: dist_pairs_kernel<M_MAN><<<blocks, threads, 0, s>>>(d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
+		default: return fail(PGEMB_ERR_ARG, "unknown distance function");
+	}
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_dist_batch(dist_func_t dist, size_t dim, size_t n, const coord_t *a, int broadcast_a, const coord_t *b,
+										 dist_t *out)
+{
+	if ((!a || !b || !out) && n) return fail(PGEMB_ERR_ARG, "null argument");
+	if (dim == 0 || dim > 65535) return fail(PGEMB_ERR_ARG, "dims out of range");
+	if (n == 0) return PGEMB_OK;
+	if (n >= (1ull << 28)) return fail(PGEMB_ERR_ARG, "batch too large");
+	float		*d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
+	const size_t ab = (broadcast_a ? 1 : n) * dim * sizeof(float), bb = n * dim * sizeof(float);
+	cudaError_t	 e = cudaMalloc((void **) &d_a, ab);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_b, bb);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_o, n * sizeof(float));
+	if (e == cudaSuccess) e = cudaMemcpy(d_a, a, ab, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(d_b, b, bb, cudaMemcpyHostToDevice);
+	pgemb_status st = PGEMB_OK;
+	if (e == cudaSuccess)
+	{
+		st = launch_pairs((int) dist, d_a, d_b, (uint32_t) dim, (uint32_t) n, broadcast_a, d_o, 0);
+		if (st == PGEMB_OK) e = cudaMemcpy(out, d_o, n * sizeof(float), cudaMemcpyDeviceToHost);
+	}
+	cudaFree(d_a);
+	cudaFree(d_b);
+	cudaFree(d_o);
+	if (e != cudaSuccess) return fail(PGEMB_ERR_CUDA, std::string("pgemb_dist_batch: ") + cudaGetErrorString(e));
+	return st;
+}
+
+extern "C" pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, const idx_t *ids, dist_t *out)
+{
+	if (!idx || ((!queries || !ids || !out) && nq && k)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (nq == 0 || k == 0) return PGEMB_OK;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t dim = idx->meta.dim;
+	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+	const size_t qb = nq * dim * 4, ib = nq * k * 4, ob = nq * k * 4;
+	st = ensure_stage(idx, up(qb) + up(ib) + up(ob));
+	if (st) return st;
+	char		*base = (char *) idx->d_stage;
+	float		*d_q = (float *) base;		base += up(qb);
+	uint32_t	*d_i = (uint32_t *) base;	base += up(ib);
+	float		*d_o = (float *) base;
+	cudaStream_t s = idx->stream;
+	CU_TRY(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, s));
+	CU_TRY(cudaMemcpyAsync(d_i, ids, ib, cudaMemcpyHostToDevice, s));
+	const int	   metric = (int) idx->meta.dist_func;
+	const uint32_t threads = 128, lanes = (metric == DIST_L2) ? 8 : 4;
+	const uint32_t blocks = (uint32_t) ((nq * k * lanes + threads - 1) / threads);
+#define GATHER(MM)                                                                                                              \
+	dist_gather_kernel<MM><<<blocks, threads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, (uint32_t) idx->n, d_q, \
+													  (uint32_t) dim, (uint32_t) nq, (uint32_t) k, d_i, d_o)
+	if (metric == DIST_L2) GATHER(M_L2);
+	else if (metric == DIST_COSINE) GATHER(M_COS);
+	else GATHER(M_MAN);
+#undef GATHER
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	CU_TRY(cudaMemcpyAsync(out, d_o, ob, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaStreamSynchronize(s));
+	return PGEMB_OK;
+}
+
+extern "C" void hnsw_init_dist_func(void)
+{
+	// distfunc.c:159-169 picks the CPU SIMD variant here; the CUDA path has a single variant per metric
+	// (the AVX2 summation order).  Touch the runtime so that later calls do not pay context creation.
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) cudaGetLastError();
+}
+
+extern "C" dist_t hnsw_dist_func(dist_func_t dist, coord_t const *ax, coord_t const *bx, size_t dim)
+{
+	float		 out = NAN;
+	pgemb_status st = pgemb_dist_batch(dist, dim, 1, ax, 0, bx, &out);
+	if (st != PGEMB_OK) return NAN;
+	return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference-shaped search / bind
+// ------------------------------------------------------------------------------------------------
+extern "C" bool hnsw_search(HnswMetadata *meta, const coord_t *point, size_t *n_results, label_t **results)
+{
+	if (!meta || !point || !n_results || !results) return false;
+	PgembHostIndex *h = reinterpret_cast<PgembHostIndex *>(meta);
+	if (!h->dev) { g_last_error = "hnsw_search: no device index attached to this HnswMetadata"; return false; }
+	const size_t ef = meta->efSearch;  // re-read every call: the caller doubles it (embedding.c:334)
+	if (ef < 1) return false;
+	label_t *buf = (label_t *) malloc(ef * sizeof(label_t));
+	if (!buf) return false;
+	int32_t		 n = 0;
+	pgemb_status st = pgemb_search_batch(h->dev, 1, point, ef, buf, nullptr, nullptr, &n, nullptr);
+	if (st != PGEMB_OK)
+	{
+		free(buf);
+		return false;
+	}
+	*results = buf;
+	*n_results = (size_t) n;
+	return true;
+}
+
+extern "C" pgemb_status pgemb_bind_point(pgemb_index *idx, idx_t id)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	if ((size_t) id >= idx->n) return fail(PGEMB_ERR_ARG, "bind: node not stored");
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	st = bind_points(idx, id, 1);
+	if (st) return st;
+	return check_device_error(idx, idx->stream);
+}
+
+extern "C" pgemb_status pgemb_insert_batch(pgemb_index *idx, size_t n, const coord_t *coords, const label_t *labels)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	const size_t first = idx->n;
+	pgemb_status st = pgemb_index_append(idx, n, coords, labels, nullptr);
+	if (st) return st;
+	st = bind_points(idx, (idx_t) first, n);
+	if (st) return st;
+	return check_device_error(idx, idx->stream);
+}
+
+extern "C" bool hnsw_bind_point(HnswMetadata *meta, const coord_t *point, idx_t cur)
+{
+	(void) point;  // the node's coordinates were stored by the caller before this call (embedding.c:619-621)
+	if (!meta) return false;
+	PgembHostIndex *h = reinterpret_cast<PgembHostIndex *>(meta);
+	if (!h->dev) { g_last_error = "hnsw_bind_point: no device index attached"; return false; }
+	h->dev->meta.efConstruction = meta->efConstruction;
+	pgemb_status st = pgemb_bind_point(h->dev, cur);
+	if (st != PGEMB_OK)
+	{
+		fprintf(stderr, "Catch %s\n", pgemb_last_error());  // hnswalg.cpp:288
+		return false;
+	}
+	return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 driver: sequential binds (hnsw_bind_point semantics, hnswalg.cpp:225-232) without host round trips
+// ------------------------------------------------------------------------------------------------
+static pgemb_status ensure_bind_ws(pgemb_index *idx, size_t points, size_t ef)
+{
+	BindWorkspace &w = idx->bind_ws;
+	const size_t   M = idx->meta.M ? idx->meta.M : 1;
+	if (w.cap_points >= points && w.cap_ef >= ef && w.cap_m >= M) return PGEMB_OK;
+	bind_ws_free(w);
+	CU_TRY(cudaMalloc((void **) &w.d_qids, points * sizeof(uint32_t)));
+	CU_TRY(cudaMalloc((void **) &w.d_cand_ids, points * ef * sizeof(uint32_t)));
+	CU_TRY(cudaMalloc((void **) &w.d_cand_d, points * ef * sizeof(float)));
+	CU_TRY(cudaMalloc((void **) &w.d_cand_n, points * sizeof(int32_t)));
+	CU_TRY(cudaMalloc((void **) &w.d_pairs, points * M * sizeof(uint64_t)));
+	CU_TRY(cudaMalloc((void **) &w.d_pairs_sorted, points * M * sizeof(uint64_t)));
+	w.cub_bytes = 0;
+	cub::DeviceRadixSort::SortKeys(nullptr, w.cub_bytes, w.d_pairs, w.d_pairs_sorted, (int) (points * M));
+	CU_TRY(cudaMalloc(&w.d_cub, w.cub_bytes + 256));
+	w.cap_points = points;
+	w.cap_ef = ef;
+	w.cap_m = M;
+	return PGEMB_OK;
+}
+
+static GraphView graph_view(pgemb_index *idx)
+{
+	GraphView g;
+	g.vectors = idx->d_vectors;
+	g.norms = idx->d_norms;
+	g.links = idx->d_links;
+	g.row_f = idx->row_f;
+	g.link_stride = idx->link_stride;
+	g.dim = (uint32_t) idx->meta.dim;
+	g.M = (uint32_t) idx->meta.M;
+	g.maxM = (uint32_t) idx->meta.maxM;
+	g.error_flag = idx->d_error;
+	return g;
+}
+
+// Connect `count` new nodes whose candidate lists sit in bind_ws slots [0,count): select + back-links.
+static pgemb_status launch_connect(pgemb_index *idx, const uint32_t *d_new_ids, size_t count, size_t ef, cudaStream_t s)
+{
+	BindWorkspace &w = idx->bind_ws;
+	GraphView	   g = graph_view(idx);
+	const size_t   M = idx->meta.M ? idx->meta.M : 1;
+	const size_t   maxM1 = idx->meta.maxM + 1;
+	const size_t   sel_smem = ef * 8 + M * 8 + ef * 4;
+	const size_t   bl_smem = maxM1 * 8 * 2 + (idx->meta.maxM ? idx->meta.maxM : 1) * 8 + maxM1 * 4;
+	const int	   metric = (int) idx->meta.dist_func;
+#define LAUNCH_SELECT(MM)                                                                                                        \
+	do {                                                                                                                         \
+		if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
+		select_kernel<MM><<<(uint32_t) count, kBindThreads, sel_smem, s>>>(g, d_new_ids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) ef, w.d_pairs); \
+	} while (0)
+	if (metric == DIST_L2) LAUNCH_SELECT(M_L2);
+	else if (metric == DIST_COSINE) LAUNCH_SELECT(M_COS);
+	else LAUNCH_SELECT(M_MAN);
+#undef LAUNCH_SELECT
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	const size_t   n_pairs = count * M;
+	const uint64_t *sorted = w.d_pairs;
+	if (count > 1)
+	{
+		size_t bytes = w.cub_bytes;
+		CU_TRY(cub::DeviceRadixSort::SortKeys(w.d_cub, bytes, w.d_pairs, w.d_pairs_sorted, (int) n_pairs, 0, 64, s));
+		g_launches++;
+		sorted = w.d_pairs_sorted;
+	}
+#define LAUNCH_BACK(MM)                                                                                                          \
+	do {                                                                                                                         \
+		if (bl_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(backlink_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bl_smem)); \
+		backlink_kernel<MM><<<(uint32_t) n_pairs, kBindThreads, bl_smem, s>>>(g, sorted, (uint32_t) n_pairs);                      \
+	} while (0)
+	if (metric == DIST_L2) LAUNCH_BACK(M_L2);
+	else if (metric == DIST_COSINE) LAUNCH_BACK(M_COS);
+	else LAUNCH_BACK(M_MAN);
+#undef LAUNCH_BACK
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	return PGEMB_OK;
+}
+
+pgemb_status bind_points(pgemb_index *idx, idx_t first, size_t n)
+{
+	if (n == 0) return PGEMB_OK;
+	if ((size_t) first + n > idx->n) return fail(PGEMB_ERR_ARG, "bind: nodes not stored");
+	const size_t efc = idx->meta.efConstruction;
+	if (efc < 1) return fail(PGEMB_ERR_ARG, "efConstruction must be >= 1");
+	cudaStream_t s = idx->stream;
+	pgemb_status st = ensure_bind_ws(idx, n > 1 ? n : 1, efc);
+	if (st) return st;
+	BindWorkspace &w = idx->bind_ws;
+	{
+		std::vector<uint32_t> ids(n);
+		for (size_t i = 0; i < n; i++) ids[i] = first + (uint32_t) i;
+		CU_TRY(cudaMemcpyAsync(w.d_qids, ids.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+		CU_TRY(cudaStreamSynchronize(s));
+	}
+	// strictly sequential: node i sees the links written for nodes < i (embedding.c:624-629 serialises writers)
+	for (size_t i = 0; i < n; i++)
+	{
+		if (first + i == 0) continue;  // hnswalg.cpp:227-228
+		st = launch_search(idx, 1, nullptr, 0, w.d_qids + i, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n,
+						   nullptr, s, false);
+		if (st) return st;
+		st = launch_connect(idx, w.d_qids + i, 1, efc, s);
+		if (st) return st;
+	}
+	return PGEMB_OK;
+}
+
+__global__ void iota_kernel(uint32_t *out, uint32_t start, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = start + i;
+}
+
+extern "C" pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t n, size_t batch_max, double *seconds_out)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "build: nodes not stored");
+	if (batch_max < 1) batch_max = 1;
+	if (batch_max > (1u << 16)) batch_max = 1u << 16;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t efc = idx->meta.efConstruction;
+	if (efc < 1) return fail(PGEMB_ERR_ARG, "efConstruction must be >= 1");
+	cudaStream_t s = idx->stream;
+	st = ensure_bind_ws(idx, batch_max, efc);
+	if (st) return st;
+	BindWorkspace &w = idx->bind_ws;
+	cudaEvent_t	   e0, e1;
+	CU_TRY(cudaEventCreate(&e0));
+	CU_TRY(cudaEventCreate(&e1));
+	CU_TRY(cudaEventRecord(e0, s));
+	size_t pos = first;
+	const size_t end = first + n;
+	while (pos < end)
+	{
+		size_t B = pos / 32;  // nodes bound so far = pos
+		if (B < 1) B = 1;
+		if (B > batch_max) B = batch_max;
+		if (B > end - pos) B = end - pos;
+		if (pos == 0)
+		{
+			pos = 1;  // node 0 has nothing to connect to (hnswalg.cpp:227-228)
+			continue;
+		}
+		iota_kernel<<<(uint32_t) ((B + 255) / 256), 256, 0, s>>>(w.d_qids, (uint32_t) pos, (uint32_t) B);
+		g_launches++;
+		st = launch_search(idx, B, nullptr, 0, w.d_qids, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n, nullptr, s,
+						   false);
+		if (st) return st;
+		st = launch_connect(idx, w.d_qids, B, efc, s);
+		if (st) return st;
+		pos += B;
+	}
+	CU_TRY(cudaEventRecord(e1, s));
+	st = check_device_error(idx, s);
+	float ms = 0.f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (seconds_out) *seconds_out = ms * 1e-3;
+	return st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shard merge
+// ------------------------------------------------------------------------------------------------
+extern "C" pgemb_status pgemb_merge_topk_device(size_t nq, size_t n_shards, size_t k, const dist_t *d_dists_in, const label_t *d_labels_in,
+												const int32_t *d_n_in, dist_t *d_dists_out, label_t *d_labels_out, int32_t *d_n_out,
+												void *stream)
+{
+	if (nq == 0) return PGEMB_OK;
+	if (!d_dists_in || !d_labels_in || !d_n_in || !d_dists_out || !d_labels_out || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (n_shards == 0 || k == 0) return fail(PGEMB_ERR_ARG, "n_shards and k must be > 0");
+	const uint32_t threads = 128;
+	const uint32_t blocks = (uint32_t) ((nq * 32 + threads - 1) / threads);
+	merge_topk_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>>((uint32_t) nq, (uint32_t) n_shards, (uint32_t) k, d_dists_in,
+																	 d_labels_in, d_n_in, d_dists_out, d_labels_out, d_n_out);
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	return PGEMB_OK;
+}

@@ -1,0 +1,463 @@
+// search_kernel.cuh -- K3: persistent best-first traversal, one WARP per query slot.
+//
+// Replaces, per query, the reference's  hnsw_search -> searchKnn -> searchBaseLayer  chain
+// (hnswalg.cpp:256-277, :234-252, :42-114) including its innermost loop
+// begin_read -> hnsw_dist_func -> end_read (hnswalg.cpp:95-97) with results identical to the
+// reference (same ids, same order, same distances bit for bit).
+//
+// Structure per hop (one iteration of `while (!candidateSet.empty())`, hnswalg.cpp:67-112):
+//   pop      nearest unexpanded candidate; ties: larger id first (pair(-dist,id) max-heap, :53,:69)
+//   expand   read its link list [count, ids...] (:76-77), test-and-set the visited bitmap (:92-93)
+//   gather   K1: the unvisited neighbours' vectors are pulled HBM -> shared memory with 1-D bulk TMA
+//            (cp.async.bulk + mbarrier, S-stage ring of R rows) and scored with the reference's exact
+//            fp32 summation order (dist_exact.cuh)
+//   update   K2: warp-level top-ef queue update that is EQUIVALENT to the reference's sequential
+//            push/pop loop (:99-108), exact distance ties included -- see "sequential equivalence".
+//
+// Sequential equivalence (proved in DESIGN.md section 5, model-checked in tests/test_batch_semantics.py).
+// The reference scores the unvisited neighbours x_1..x_n in list order and accepts x_k iff
+// `topResults.size() < ef || topResults.top().first > d_k`.  With R = current results:
+//     accept(x_k)  <=>  #{ y in R u {x_1..x_{k-1}} : dist(y) <= d_k } < ef
+// (rejected earlier items may be counted: they never change the ef-th smallest distance).  The new
+// result set is the ef smallest (dist,id) pairs of R u accepted.  candidateSet = unexpanded members
+// of the result set, plus ("overflow") accepted-but-evicted entries whose distance still EQUALS the
+// current worst result distance -- only those can ever be popped before the `> lowerBound` break
+// (:70).  Overflow entries exist only under exact distance ties; they are bounded by ef-1 and kept
+// in a per-slot global buffer.
+//
+// One warp = one slot: no CTA-wide barriers anywhere; smem per slot ~56 KB at dim=768 so 4 slots
+// share an SM and overlap each other's dependent-latency phases (pop -> links -> bitmap -> rows).
+#pragma once
+#include "common.cuh"
+#include "dist_exact.cuh"
+
+namespace pgemb {
+
+struct SearchParams
+{
+	// index (HBM, SoA)
+	const float	   *vectors;	 // [n][row_f] f32, rows 16-B aligned, zero padded
+	const uint32_t *links;		 // [n][link_stride] u32: [count, ids...]
+	const uint64_t *labels;		 // [n]
+	const float	   *norms;		 // [n] squared norms in cosine lane order (cosine only)
+	uint32_t		n_items, dim, row_f, link_stride, maxM, entry;
+	// queries
+	const float	   *queries;	 // [nq][q_stride] or NULL
+	const uint32_t *query_ids;	 // [nq] stored nodes used as queries (bind path) or NULL
+	uint32_t		nq, q_stride, ef;
+	uint32_t		raw_mode;	 // 1: emit searchBaseLayer's (dist,id) list (no label lookup / deleted filter)
+	// outputs (any may be NULL except n_out)
+	uint64_t *labels_out;		 // [nq][ef]
+	float	 *dists_out;		 // [nq][ef]
+	uint32_t *ids_out;			 // [nq][ef]
+	int32_t	 *n_out;			 // [nq]
+	uint32_t *stats_out;		 // [nq][4]: distance evals, expansions, link words, overflow high-water
+	// per-slot workspace
+	uint32_t	 *visited;		 // [slots][vis_words]
+	uint32_t	 *vlog;			 // [slots][vlog_cap] ids whose bit was set (for O(visited) cleanup)
+	uint64_t	 *ovf;			 // [slots][ef]
+	uint32_t	  vis_words, vlog_cap;
+	unsigned int *counter;		 // work-stealing query counter
+	int			 *error_flag;	 // sticky: 1 = bad link id, 2 = overflow buffer exceeded
+	// shared-memory layout (bytes from the dynamic smem base)
+	uint32_t stages, row_smem, row_bytes;
+	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_hopnorm, off_mbar;
+};
+
+constexpr uint32_t kNone = 0xffffffffu;
+
+template <int METRIC, int TPR>
+__global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	constexpr int R = 32 / TPR;	 // rows scored per stage
+	float		  *q_s = reinterpret_cast<float *>(smem + p.off_q);
+	unsigned char *ring = smem + p.off_ring;
+	uint64_t	  *res = reinterpret_cast<uint64_t *>(smem + p.off_res);	// two buffers of ef keys
+	uint64_t	  *hop_key = reinterpret_cast<uint64_t *>(smem + p.off_hopkey);
+	uint64_t	  *acc_key = reinterpret_cast<uint64_t *>(smem + p.off_acckey);
+	uint64_t	  *evict_key = reinterpret_cast<uint64_t *>(smem + p.off_evict);
+	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(smem + p.off_hopid);
+	float		  *hop_norm = reinterpret_cast<float *>(smem + p.off_hopnorm);
+	uint64_t	  *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
+
+	const uint32_t lane = threadIdx.x;
+	const uint32_t lt = lanemask_lt();
+	const int	   row_in_stage = lane / TPR;
+	const int	   sub = lane % TPR;
+	const uint32_t ef = p.ef;
+	const int	   dim = (int) p.dim;
+	const uint32_t S = p.stages;
+	uint32_t	  *vis = p.visited + (size_t) blockIdx.x * p.vis_words;
+	uint32_t	  *vlog = p.vlog + (size_t) blockIdx.x * p.vlog_cap;
+	uint64_t	  *ovf = p.ovf + (size_t) blockIdx.x * ef;
+	const uint64_t pol = l2_policy_evict_first();
+
+	if (lane == 0)
+	{
+		for (uint32_t s = 0; s < S; s++) mbar_init(&mbar[s], 1);
+		fence_mbar_init();
+	}
+	__syncwarp();
+	uint32_t parity = 0;  // bit s: phase parity the next wait on stage s must observe
+
+	for (;;)
+	{
+		uint32_t qi = 0;
+		if (lane == 0) qi = atomicAdd(p.counter, 1u);
+		qi = __shfl_sync(kFull, qi, 0);
+		if (qi >= p.nq) break;
+
+		// ---- stage the query in shared memory -------------------------------------------------
+		{
+			const float *qsrc = p.query_ids ? p.vectors + (size_t) p.query_ids[qi] * p.row_f
+											: p.queries + (size_t) qi * p.q_stride;
+			for (uint32_t i = lane; i < p.row_f; i += 32) q_s[i] = (i < p.dim) ? qsrc[i] : 0.0f;
+		}
+		__syncwarp();
+		float qn = 0.0f;
+		if (METRIC == M_COS) qn = sqnorm_exact<4>(q_s, dim, lane & 3);	// distfunc.c:141 once per query
+
+		int		 cur = 0;		// which res buffer is live
+		uint32_t r = 0;			// results held (<= ef), ascending (dist,id)
+		uint32_t ovf_n = 0, ovf_hw = 0;
+		uint32_t logn = 0;
+		uint32_t st_dist = 0, st_hops = 0, st_words = 0;
+
+		// ---- entry point (hnswalg.cpp:55-65): scored like a one-element hop ---------------------
+		uint32_t n = 0;
+		if (p.n_items > 0 && p.entry < p.n_items)
+		{
+			if (lane == 0)
+			{
+				hop_id[0] = p.entry;
+				atomicOr(&vis[p.entry >> 5], 1u << (p.entry & 31));
+				if (p.vlog_cap > 0) vlog[0] = p.entry;
+			}
+			n = 1;
+			logn = 1;
+		}
+		__syncwarp();
+
+		for (;;)
+		{
+			if (n > 0)
+			{
+				// ================= K1: gather + score the n rows in hop_id[] ======================
+				const uint32_t G = (n + R - 1) / R;
+				st_dist += n;
+				auto issue = [&](uint32_t g) {
+					const uint32_t st = g % S;
+					const uint32_t rows = min((uint32_t) R, n - g * R);
+					if (lane == 0) mbar_arrive_expect_tx(&mbar[st], rows * p.row_bytes);
+					__syncwarp();
+					if (lane < rows)
+					{
+						const uint32_t id = hop_id[g * R + lane];
+						tma_load_1d(ring + (size_t) (st * R + lane) * p.row_smem, p.vectors + (size_t) id * p.row_f,
+									p.row_bytes, &mbar[st], pol);
+					}
+				};
+				for (uint32_t g = 0; g < G && g < S; g++) issue(g);
+				if (METRIC == M_COS)
+				{
+					for (uint32_t k = lane; k < n; k += 32) hop_norm[k] = p.norms[hop_id[k]];
+					__syncwarp();
+				}
+				for (uint32_t g = 0; g < G; g++)
+				{
+					const uint32_t st = g % S;
+					mbar_wait(&mbar[st], (parity >> st) & 1u);
+					parity ^= 1u << st;
+					const uint32_t k = g * R + row_in_stage;
+					const float	  *rowp = reinterpret_cast<const float *>(ring + (size_t) (st * R + row_in_stage) * p.row_smem);
+					const float	   vn = (METRIC == M_COS && k < n) ? hop_norm[k] : 1.0f;
+					const float	   d = distance_exact<METRIC, TPR>(q_s, rowp, dim, qn, vn, sub);
+					if (sub == 0 && k < n) hop_key[k] = make_key(d, hop_id[k]);
+					__syncwarp();
+					if (g + S < G) issue(g + S);
+				}
+
+				// ================= K2: sequential-equivalent queue update ==========================
+				const uint64_t *Rb = res + (size_t) cur * ef;
+				uint64_t	   *Ob = res + (size_t) (cur ^ 1) * ef;
+				const bool		all_accept = (r + n <= ef);
+				const uint32_t	W = (r == ef) ? key_dist(Rb[ef - 1]) : 0xffffffffu;
+				uint32_t		a = 0;
+				for (uint32_t base = 0; base < n; base += 32)
+				{
+					const uint32_t k = base + lane;
+					bool		   acc = false;
+					uint64_t	   key = 0;
+					if (k < n)
+					{
+						key = hop_key[k];
+						const uint32_t od = key_dist(key);
+						if (all_accept)
+							acc = true;
+						else if (r == ef && od >= W)
+							acc = false;
+						else
+						{
+							uint32_t lo = 0, hi = r;  // cR = #{R : dist <= od}
+							while (lo < hi)
+							{
+								const uint32_t mid = (lo + hi) >> 1;
+								if (key_dist(Rb[mid]) <= od) lo = mid + 1; else hi = mid;
+							}
+							if (lo < ef)
+							{
+								uint32_t c = lo;
+								for (uint32_t j = 0; j < k; j++) c += (key_dist(hop_key[j]) <= od) ? 1u : 0u;
+								acc = c < ef;
+							}
+						}
+					}
+					const uint32_t m = __ballot_sync(kFull, acc);
+					if (acc) acc_key[a + __popc(m & lt)] = key;
+					a += __popc(m);
+				}
+				__syncwarp();
+				if (a > 0)
+				{
+					const uint32_t total = r + a;
+					for (uint32_t t = lane; t < a; t += 32)
+					{
+						const uint64_t key = acc_key[t];
+						const uint64_t ko = key_order(key);
+						uint32_t	   lo = 0, hi = r;
+						while (lo < hi)
+						{
+							const uint32_t mid = (lo + hi) >> 1;
+							if (key_order(Rb[mid]) < ko) lo = mid + 1; else hi = mid;
+						}
+						uint32_t pos = lo;
+						for (uint32_t j = 0; j < a; j++) pos += (key_order(acc_key[j]) < ko) ? 1u : 0u;
+						if (pos < ef) Ob[pos] = key; else evict_key[pos - ef] = key;
+					}
+					for (uint32_t i = lane; i < r; i += 32)
+					{
+						const uint64_t key = Rb[i];
+						const uint64_t ko = key_order(key);
+						uint32_t	   pos = i;
+						for (uint32_t j = 0; j < a; j++) pos += (key_order(acc_key[j]) < ko) ? 1u : 0u;
+						if (pos < ef) Ob[pos] = key; else evict_key[pos - ef] = key;
+					}
+					__syncwarp();
+					cur ^= 1;
+					r = min(total, ef);
+					if (total > ef)
+					{
+						const uint32_t Wn = key_dist(Ob[ef - 1]);
+						if (ovf_n > 0 && Wn != W) ovf_n = 0;  // worst distance dropped: old ties are dead
+						const uint32_t ne = total - ef;
+						for (uint32_t base = 0; base < ne; base += 32)
+						{
+							const uint32_t e = base + lane;
+							uint64_t	   ek = 0;
+							bool		   keep = false;
+							if (e < ne)
+							{
+								ek = evict_key[e];
+								keep = !key_expanded(ek) && key_dist(ek) == Wn;
+							}
+							const uint32_t m = __ballot_sync(kFull, keep);
+							const uint32_t at = ovf_n + __popc(m & lt);
+							if (keep)
+							{
+								if (at < ef) ovf[at] = ek; else *p.error_flag = 2;
+							}
+							ovf_n = min(ovf_n + (uint32_t) __popc(m), ef);
+						}
+						ovf_hw = max(ovf_hw, ovf_n);
+						__syncwarp();
+					}
+				}
+			}
+
+			// ================= pop the next candidate (hnswalg.cpp:69-74) =========================
+			const uint64_t *Rb = res + (size_t) cur * ef;
+			int				best = -1;
+			for (uint32_t base = 0; base < r; base += 32)
+			{
+				const uint32_t i = base + lane;
+				const bool	   un = (i < r) && !key_expanded(Rb[i]);
+				const uint32_t m = __ballot_sync(kFull, un);
+				if (m)
+				{
+					best = (int) base + __ffs(m) - 1;
+					break;
+				}
+			}
+			if (best >= 0)
+			{
+				// equal-distance group: the reference pops the LARGEST id first (pair(-d,id) order)
+				const uint32_t D = key_dist(Rb[best]);
+				for (uint32_t base = (uint32_t) best + 1; base < r; base += 32)
+				{
+					const uint32_t i = base + lane;
+					const bool	   ing = (i < r) && key_dist(Rb[i]) == D;
+					const bool	   un = ing && !key_expanded(Rb[i]);
+					const uint32_t mg = __ballot_sync(kFull, ing);
+					const uint32_t mu = __ballot_sync(kFull, un);
+					if (mu) best = (int) base + 31 - __clz(mu);
+					if (mg != kFull) break;
+				}
+			}
+			uint32_t c = kNone;
+			bool	 from_ovf = false;
+			if (ovf_n > 0)
+			{
+				// candidates evicted from the result set that still tie with its worst distance
+				uint64_t bp = ~0ull;  // (dist << 32 | (0x7fffffff - id)) : smaller is better
+				uint32_t bi = 0;
+				for (uint32_t i = lane; i < ovf_n; i += 32)
+				{
+					const uint64_t k = ovf[i];
+					const uint64_t pr = ((uint64_t) key_dist(k) << 32) | (uint64_t) (0x7fffffffu - key_id(k));
+					if (pr < bp) { bp = pr; bi = i; }
+				}
+				for (int off = 16; off > 0; off >>= 1)
+				{
+					const uint64_t op = __shfl_xor_sync(kFull, bp, off);
+					const uint32_t oi = __shfl_xor_sync(kFull, bi, off);
+					if (op < bp) { bp = op; bi = oi; }
+				}
+				uint64_t rp = ~0ull;
+				if (best >= 0)
+					rp = ((uint64_t) key_dist(Rb[best]) << 32) | (uint64_t) (0x7fffffffu - key_id(Rb[best]));
+				if (bp < rp)
+				{
+					from_ovf = true;
+					c = 0x7fffffffu - (uint32_t) (bp & 0xffffffffu);
+					__syncwarp();
+					if (lane == 0) ovf[bi] = ovf[ovf_n - 1];
+					ovf_n -= 1;
+					__syncwarp();
+				}
+			}
+			if (!from_ovf)
+			{
+				if (best < 0) break;  // candidateSet exhausted (or only entries beyond lowerBound)
+				c = key_id(Rb[best]);
+				if (lane == 0) res[(size_t) cur * ef + best] |= 1ull;
+				__syncwarp();
+			}
+
+			// ================= expand c: link list + visited bitmap (hnswalg.cpp:76-93) ===========
+			const uint32_t *L = p.links + (size_t) c * p.link_stride;
+			uint32_t		cnt = L[0];
+			if (cnt > p.maxM)
+			{
+				cnt = p.maxM;
+				*p.error_flag = 1;
+			}
+			st_hops += 1;
+			st_words += 1 + cnt;
+			n = 0;
+			for (uint32_t base = 0; base < cnt; base += 32)
+			{
+				const uint32_t k = base + lane;
+				bool		   valid = k < cnt;
+				uint32_t	   id = valid ? L[1 + k] : 0u;
+				if (valid && id >= p.n_items)
+				{
+					valid = false;
+					*p.error_flag = 1;
+				}
+				const uint32_t mm = __match_any_sync(kFull, valid ? id : (0x80000000u | lane));
+				const bool	   first = valid && ((uint32_t) (__ffs(mm) - 1) == lane);
+				const uint32_t bit = 1u << (id & 31);
+				uint32_t	   old = 0xffffffffu;
+				if (first) old = atomicOr(&vis[id >> 5], bit);
+				const bool	   unv = first && !(old & bit);
+				const uint32_t m = __ballot_sync(kFull, unv);
+				const uint32_t off = __popc(m & lt);
+				if (unv)
+				{
+					hop_id[n + off] = id;
+					if (logn + off < p.vlog_cap) vlog[logn + off] = id;
+				}
+				n += __popc(m);
+				logn += __popc(m);
+			}
+			__syncwarp();
+		}
+
+		// ---- emit (hnswalg.cpp:238-249, :262-270) ---------------------------------------------------
+		const uint64_t *Rb = res + (size_t) cur * ef;
+		uint64_t	   *lab = res + (size_t) (cur ^ 1) * ef;  // scratch: labels of the results
+		const size_t	ob = (size_t) qi * ef;
+		uint32_t		count = r;
+		if (p.raw_mode)
+		{
+			for (uint32_t i = lane; i < ef; i += 32)
+			{
+				const bool ok = i < r;
+				if (p.ids_out) p.ids_out[ob + i] = ok ? key_id(Rb[i]) : kNone;
+				if (p.dists_out) p.dists_out[ob + i] = ok ? o2f(key_dist(Rb[i])) : __int_as_float(0x7f800000);
+				if (p.labels_out) p.labels_out[ob + i] = ok ? (uint64_t) key_id(Rb[i]) : ~0ull;
+			}
+		}
+		else
+		{
+			for (uint32_t i = lane; i < r; i += 32) lab[i] = p.labels[key_id(Rb[i])];
+			__syncwarp();
+			// order by (dist, label) among non-deleted entries (searchKnn builds pair<dist,label>)
+			uint32_t cnt_live = 0;
+			for (uint32_t base = 0; base < r; base += 32)
+			{
+				const uint32_t i = base + lane;
+				bool		   live = false;
+				uint32_t	   pos = 0;
+				if (i < r)
+				{
+					const uint64_t li = lab[i];
+					live = ((li >> 48) & 1ull) == 0;  // !hnsw_is_deleted, embedding.c:948-953
+					if (live)
+					{
+						const uint32_t di = key_dist(Rb[i]);
+						for (uint32_t j = 0; j < r; j++)
+						{
+							const uint64_t lj = lab[j];
+							if ((lj >> 48) & 1ull) continue;
+							const uint32_t dj = key_dist(Rb[j]);
+							pos += (dj < di || (dj == di && (lj < li || (lj == li && j < i)))) ? 1u : 0u;
+						}
+						if (p.labels_out) p.labels_out[ob + pos] = li;
+						if (p.dists_out) p.dists_out[ob + pos] = o2f(di);
+						if (p.ids_out) p.ids_out[ob + pos] = key_id(Rb[i]);
+					}
+				}
+				cnt_live += __popc(__ballot_sync(kFull, live));
+			}
+			count = cnt_live;
+			for (uint32_t i = count + lane; i < ef; i += 32)
+			{
+				if (p.labels_out) p.labels_out[ob + i] = ~0ull;
+				if (p.dists_out) p.dists_out[ob + i] = __int_as_float(0x7f800000);
+				if (p.ids_out) p.ids_out[ob + i] = kNone;
+			}
+		}
+		if (lane == 0)
+		{
+			p.n_out[qi] = (int32_t) count;
+			if (p.stats_out)
+			{
+				p.stats_out[(size_t) qi * 4 + 0] = st_dist;
+				p.stats_out[(size_t) qi * 4 + 1] = st_hops;
+				p.stats_out[(size_t) qi * 4 + 2] = st_words;
+				p.stats_out[(size_t) qi * 4 + 3] = ovf_hw;
+			}
+		}
+
+		// ---- reset the visited bitmap: O(visited) via the log, full clear if the log overflowed ----
+		if (logn <= p.vlog_cap)
+			for (uint32_t i = lane; i < logn; i += 32) vis[vlog[i] >> 5] = 0u;
+		else
+			for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
+		__syncwarp();
+	}
+}
+
+}  // namespace pgemb

@@ -1,0 +1,87 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/pgemb_b200.h declares, HnswMetadata has the reference's layout, and the product path fails
+loudly (no fallback) when no CUDA device is usable."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pg_embedding_b200 import build
+    build.build()
+    from pg_embedding_b200 import _lib
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from pg_embedding_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pgemb_b200.h")).read()
+    declared = set(re.findall(r"\b((?:pgemb|hnsw)_[a-z_0-9]+)\s*\(", header))
+    declared -= {"pgemb_status", "pgemb_index"}
+    assert declared, "no prototypes parsed"
+    assert declared == set(_lib.ABI_SYMBOLS), declared ^ set(_lib.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by libpgemb_b200.so"
+
+
+def test_metadata_layout_matches_reference(lib):
+    from pg_embedding_b200._lib import HnswMetadata
+    # embedding.h:28-42: 10 size_t + idx_t + enum
+    assert C.sizeof(HnswMetadata) == 10 * 8 + 4 + 4
+    assert HnswMetadata.enterpoint_node.offset == 80 and HnswMetadata.dist_func.offset == 84
+    ref_h = "/root/reference/embedding.h"
+    if os.path.isfile(ref_h):
+        ref_fields = re.findall(r"^\s*(?:size_t|idx_t|dist_func_t)\s+(\w+);", open(ref_h).read(), re.M)
+        assert ref_fields == [f[0] for f in HnswMetadata._fields_]
+
+
+def test_meta_init_follows_hnsw_get_index(lib):
+    from pg_embedding_b200._lib import HnswMetadata
+    m = HnswMetadata()
+    assert lib.pgemb_meta_init(C.byref(m), 768, 32, 200, 64, 1) == 0
+    assert (m.dim, m.M, m.maxM, m.efConstruction, m.efSearch, m.dist_func) == (768, 32, 64, 200, 64, 1)
+    assert m.offset_data == 65 * 4 and m.offset_label == 260 + 3072 and m.size_data_per_element == 3340
+    assert m.elems_per_page == 2  # d=768/m=32 -> 3340 B, 2 per page
+    assert lib.pgemb_meta_init(C.byref(m), 3, 3, 16, 64, 0) == 0
+    assert m.size_data_per_element == 48 and m.elems_per_page == 157
+    assert lib.pgemb_meta_init(C.byref(m), 0, 3, 16, 64, 0) != 0          # dims required (embedding.c:219)
+    assert b"dims" in lib.pgemb_last_error()
+    assert lib.pgemb_meta_init(C.byref(m), 4000, 32, 16, 64, 0) != 0      # record does not fit a page (:229)
+
+
+def test_is_deleted_flag(lib):
+    assert lib.hnsw_is_deleted(1 << 48) and not lib.hnsw_is_deleted((1 << 48) - 1)
+    assert not lib.hnsw_is_deleted(2 << 48)
+
+
+def test_no_silent_cpu_fallback(lib):
+    """Without a CUDA device every compute entry point must FAIL, never compute on the CPU."""
+    if lib.pgemb_device_count() > 0:
+        pytest.skip("CUDA device present")
+    from pg_embedding_b200._lib import HnswMetadata
+    m = HnswMetadata()
+    assert lib.pgemb_meta_init(C.byref(m), 3, 3, 16, 64, 0) == 0
+    h = C.c_void_p()
+    assert lib.pgemb_index_create(C.byref(m), 16, 0, C.byref(h)) != 0
+    a = np.ones(3, np.float32)
+    out = np.zeros(1, np.float32)
+    fp = C.POINTER(C.c_float)
+    assert lib.pgemb_dist_batch(0, 3, 1, a.ctypes.data_as(fp), 0, a.ctypes.data_as(fp), out.ctypes.data_as(fp)) != 0
+    assert np.isnan(lib.hnsw_dist_func(0, a.ctypes.data_as(fp), a.ctypes.data_as(fp), 3))
+
+
+def test_product_does_not_import_oracle():
+    """The product package must not reference oracle/ (rule: oracle is test infrastructure only)."""
+    pkg = os.path.join(ROOT, "pg_embedding_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src and "libpgemb_port" not in src \
+                    and "libpgemb_ref" not in src, f

@@ -1,0 +1,339 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bar: bit-exact ids / labels / link lists AND bit-exact fp32 distances (tolerance 0 --
+north_star allows 1e-5 relative, the kernels reproduce the reference's summation order exactly).
+
+The checker is the C restatement (`port`, buildable on the GPU box) and, when the prebuilt
+oracle/_ref/libpgemb_ref.so travelled with the tree, the compiled reference itself (`ref`)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+METRICS = ["l2", "cosine", "manhattan"]
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import pg_embedding_b200 as pg
+    from pg_embedding_b200 import build
+    build.build()
+    if pg.device_count() < 1:
+        pytest.fail("no CUDA device: the product path has no CPU fallback")
+    return pg
+
+
+def checkers(oracle_mod):
+    return ["port"] + (["ref"] if oracle_mod.available("ref") else [])
+
+
+def _data(rng, n, dim, clustered=True, dup_frac=0.0, levels=0):
+    if levels:
+        x = rng.integers(0, levels, size=(n, dim)).astype(np.float32)
+    elif clustered:
+        c = rng.standard_normal((max(4, int(np.sqrt(n))), dim)).astype(np.float32)
+        x = c[rng.integers(0, len(c), n)] + 0.3 * rng.standard_normal((n, dim)).astype(np.float32)
+    else:
+        x = rng.standard_normal((n, dim)).astype(np.float32)
+    if dup_frac > 0:
+        k = int(n * dup_frac)
+        x[rng.integers(0, n, k)] = x[rng.integers(0, n, k)]
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# a1-a4: distances
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", METRICS)
+def test_distance_bits(pg, oracle_mod, metric):
+    rng = np.random.default_rng(11)
+    dims = list(range(1, 40)) + [63, 64, 65, 100, 127, 128, 129, 300, 768, 769, 1536, 2000]
+    for dim in dims:
+        a = rng.standard_normal((48, dim)).astype(np.float32) * rng.choice([1e-3, 1.0, 37.0], size=(48, 1)).astype(np.float32)
+        b = rng.standard_normal((48, dim)).astype(np.float32)
+        got = pg.dist_batch(metric, a, b)
+        for which in checkers(oracle_mod):
+            want = oracle_mod.dist_many(which, metric, a, b)
+            assert got.tobytes() == want.tobytes(), (metric, dim, which, np.flatnonzero(got != want)[:4])
+        got = pg.dist_batch(metric, a[0], b)
+        want = oracle_mod.dist_many("port", metric, a[0], b)
+        assert got.tobytes() == want.tobytes(), (metric, dim, "broadcast")
+
+
+def test_sql_distance_functions(pg, oracle_mod):
+    a, b = np.array([0, 1, 2], np.float32), np.array([3, 3, 3], np.float32)
+    assert pg.l2_distance(a, b) == oracle_mod.dist("port", "l2", a, b)
+    assert pg.cosine_distance(a, b) == oracle_mod.dist("port", "cosine", a, b)
+    assert pg.manhattan_distance(a, b) == np.float32(6.0)
+    with pytest.raises(ValueError, match="different array dimensions 3 and 2"):  # embedding.c:1031-1035
+        pg.l2_distance(a, b[:2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden KATs (reference pg_regress expected outputs) through the reference-shaped entry points
+# ---------------------------------------------------------------------------------------------------
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat_regress.json")))["cases"]
+
+
+def tid_label(blk, pos, flags=0):
+    return (blk >> 16) | ((blk & 0xFFFF) << 16) | (pos << 32) | (flags << 48)
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_kat_regress(pg, case):
+    o = case["options"]
+    for metric in case.get("expected", case.get("expected_tids")).keys():
+        idx = pg.HnswIndex(o["dims"], o["m"], o["efconstruction"], o["efsearch"], metric, capacity=64)
+        by_label = {}
+        for r in case.get("rows_before_truncate", []):
+            idx.insert(np.array(r["val"], np.float32), tid_label(*r["tid"]))
+        if "rows_before_truncate" in case:
+            idx.truncate()
+        for r in case["rows"]:
+            lab = tid_label(*r["tid"])
+            idx.insert(np.array(r["val"], np.float32), lab)
+            by_label[lab] = r
+        if "delete_all_then_insert" in case:
+            idx.mark_deleted(np.arange(len(idx)))
+            by_label = {}
+            for r in case["delete_all_then_insert"]:
+                lab = tid_label(*r["tid"])
+                idx.insert(np.array(r["val"], np.float32), lab)
+                by_label[lab] = r
+        labels = idx.search(np.array(case["query"], np.float32))  # hnsw_search
+        rows = [by_label[int(l)] for l in labels]
+        if "expected" in case:
+            assert [r["val"] for r in rows] == case["expected"][metric], metric
+        if "expected_tids" in case:
+            assert [r["tid"] for r in rows] == case["expected_tids"][metric], metric
+        if "expected_distances" in case:
+            out = idx.search_batch(np.array([case["query"]], np.float32))
+            np.testing.assert_allclose(out["dists"][0, : out["n"][0]], case["expected_distances"][metric], rtol=0, atol=5e-7)
+        idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# a6-a8: search on an identical graph
+# ---------------------------------------------------------------------------------------------------
+SEARCH_CFGS = [
+    # dims, m, efC, n, kwargs for _data, efs
+    (3, 3, 16, 300, dict(levels=3), (1, 2, 5, 64)),                 # tie-heavy: overflow machinery
+    (2, 3, 8, 400, dict(levels=2), (1, 3, 16)),                     # massive duplicates
+    (16, 8, 40, 2000, dict(), (1, 10, 64, 100)),
+    (33, 5, 20, 1000, dict(dup_frac=0.1), (7, 64)),                 # dims % 4 != 0 (row padding, scalar tails)
+    (128, 16, 64, 3000, dict(), (64, 200)),                         # BASELINE configs[1] shape (small N)
+    (100, 20, 32, 1500, dict(), (64,)),                             # maxM = 40 > one warp chunk
+    (24, 100, 16, 700, dict(), (64,)),                              # reference defaults m=100 -> maxM=200
+    (768, 32, 48, 600, dict(), (64,)),                              # north-star row shape
+]
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("cfg", SEARCH_CFGS, ids=[f"d{c[0]}m{c[1]}n{c[3]}" for c in SEARCH_CFGS])
+def test_search_identical_to_oracle(pg, oracle_mod, metric, cfg):
+    dims, m, efc, n, kw, efs = cfg
+    rng = np.random.default_rng(1000 + dims + m)
+    x = _data(rng, n, dims, **kw)
+    q = _data(rng, 64, dims, **{k: v for k, v in kw.items() if k == "levels"})
+    if metric == "cosine":
+        x, q = x + 1.0, q + 1.0
+    q[:8] = x[:8]
+    labels = (rng.permutation(n).astype(np.uint64) << np.uint64(32)) | np.uint64(7)  # labels != ids
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+    orc.build(x, labels)
+    for i in range(0, n, 5):
+        orc.mark_deleted(i)
+    links, labs = orc.links(), orc.labels()
+    ref = None
+    if oracle_mod.available("ref"):
+        ref = oracle_mod.FlatIndex("ref", dims, m, efc, 64, metric, capacity=n)
+        ref.load_graph(x, links, labs)
+
+    idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+    idx.append(x, labs, links)
+    assert idx.links().tobytes() == links.tobytes()
+    for ef in efs:
+        out = idx.search_batch(q, ef, want_stats=True)
+        want = orc.search_many(q, ef, want_counters=True)
+        assert out["n"].tolist() == want["n"].tolist(), (metric, ef)
+        assert out["labels"].tobytes() == want["labels"].tobytes(), (metric, ef)
+        if ref is not None:
+            w2 = ref.search_many(q, ef, nthreads=2)
+            assert out["labels"].tobytes() == w2["labels"].tobytes(), (metric, ef, "compiled reference")
+        # identical traversal: same number of distance evals / expansions / link words as the oracle host saw
+        assert out["stats"][:, 0].tolist() == want["counters"][:, 0].tolist()
+        assert out["stats"][:, 1].tolist() == want["counters"][:, 1].tolist()
+        assert out["stats"][:, 2].tolist() == want["counters"][:, 2].tolist()
+        # distances of the returned nodes: bit-exact vs hnsw_dist_func on the same pairs
+        for qi in range(0, q.shape[0], 7):
+            k = int(out["n"][qi])
+            ids = out["ids"][qi, :k]
+            dd = oracle_mod.dist_many("port", metric, q[qi], x[ids]) if k else np.zeros(0, np.float32)
+            assert out["dists"][qi, :k].tobytes() == dd.tobytes()
+            assert (labs[ids] == out["labels"][qi, :k]).all()
+    # the reference-shaped single-query entry point agrees with the batch
+    one = idx.search(q[3], efs[-1])
+    assert one.tolist() == orc.search(q[3], efs[-1]).tolist()
+    idx.close()
+
+
+def test_search_empty_and_tiny(pg, oracle_mod):
+    idx = pg.HnswIndex(4, 3, 8, 8, "l2", capacity=8)
+    out = idx.search_batch(np.zeros((3, 4), np.float32), 8)
+    assert out["n"].tolist() == [0, 0, 0]                    # gh-2: empty index -> no rows
+    assert idx.search(np.zeros(4, np.float32)).size == 0
+    idx.insert(np.ones(4, np.float32), 42)
+    assert idx.search(np.zeros(4, np.float32)).tolist() == [42]
+    with pytest.raises(ValueError, match="Wrong number of dimensions"):   # embedding.c:311-315
+        idx.search(np.zeros(5, np.float32))
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# a9-a11: bind (insert) -- link lists bit-for-bit
+# ---------------------------------------------------------------------------------------------------
+BIND_CFGS = [
+    (3, 3, 16, 250, dict(levels=3)),
+    (8, 4, 10, 500, dict(dup_frac=0.2)),
+    (16, 8, 40, 1200, dict()),
+    (33, 5, 20, 600, dict()),
+    (128, 16, 64, 800, dict()),
+    (24, 100, 16, 300, dict()),       # default m: lists never fill (append path only)
+    (768, 4, 20, 300, dict()),
+]
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("cfg", BIND_CFGS, ids=[f"d{c[0]}m{c[1]}n{c[3]}" for c in BIND_CFGS])
+def test_bind_links_identical_to_oracle(pg, oracle_mod, metric, cfg):
+    dims, m, efc, n, kw = cfg
+    rng = np.random.default_rng(77 + dims * 3 + m)
+    x = _data(rng, n, dims, **kw)
+    if metric == "cosine":
+        x = x + 1.0
+    which = "ref" if oracle_mod.available("ref") else "port"
+    orc = oracle_mod.FlatIndex(which, dims, m, efc, 64, metric, capacity=n)
+    orc.build(x)
+    idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+    half = n // 2
+    idx.insert_many(x[:half])                   # n sequential hnsw_add_point calls on the device
+    for i in range(half, half + 5):
+        idx.insert(x[i])                        # reference-shaped hnsw_bind_point, one at a time
+    idx.insert_many(x[half + 5:])
+    got, want = idx.links(), orc.links()
+    bad = np.flatnonzero((got != want).any(1))
+    assert bad.size == 0, f"{metric}: link lists differ at nodes {bad[:10]} (first: {got[bad[0]][:8]} vs {want[bad[0]][:8]})"
+    # bulk build with batch_max=1 is the same sequence of exact binds
+    idx2 = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+    idx2.build(x, batch_max=1)
+    assert idx2.links().tobytes() == want.tobytes()
+    idx.close()
+    idx2.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# f1: reference record layout ingest / export
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims,m", [(3, 3), (33, 5), (128, 16)])
+def test_record_layout_roundtrip(pg, oracle_mod, dims, m):
+    rng = np.random.default_rng(5)
+    n = 300
+    x = _data(rng, n, dims)
+    labels = rng.integers(0, 2**47, n).astype(np.uint64)
+    orc = oracle_mod.FlatIndex("port", dims, m, 16, 64, "l2", capacity=n)
+    orc.build(x, labels)
+    recs = orc.records()
+    idx = pg.HnswIndex(dims, m, 16, 64, "l2", capacity=n)
+    idx.load_records(recs)
+    assert idx.links().tobytes() == orc.links().tobytes()
+    assert idx.labels().tobytes() == labels.tobytes()
+    assert idx.export_records().tobytes() == recs.tobytes()
+    q = _data(rng, 16, dims)
+    assert idx.search_batch(q, 32)["labels"].tobytes() == orc.search_many(q, 32)["labels"].tobytes()
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# bulk build: structural validity + quality
+# ---------------------------------------------------------------------------------------------------
+def test_bulk_build_valid_graph_and_recall(pg, oracle_mod):
+    rng = np.random.default_rng(9)
+    n, dims, m, efc = 6000, 32, 8, 64
+    x = _data(rng, n, dims)
+    q = _data(rng, 200, dims)
+    idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    idx.build(x, batch_max=256)
+    links = idx.links()
+    cnt = links[:, 0]
+    assert (cnt <= 2 * m).all() and (cnt[1:] > 0).all()
+    for i in range(0, n, 37):
+        l = links[i, 1:1 + cnt[i]]
+        assert (l < n).all() and (l != i).all() and len(set(l.tolist())) == len(l)
+    # the CPU reference algorithm searching the GPU-built graph returns exactly what the GPU returns
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.load_graph(x, links)
+    out = idx.search_batch(q, 64)
+    assert out["labels"].tobytes() == orc.search_many(q, 64)["labels"].tobytes()
+    # recall@10 vs exact brute force, compared with the reference's own sequential build
+    d2 = ((q[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    truth = np.argsort(d2, axis=1)[:, :10]
+    def recall(labels):
+        return np.mean([len(set(truth[i].tolist()) & set(labels[i, :10].tolist())) / 10 for i in range(len(q))])
+    seq = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    seq.build(x)
+    r_gpu, r_seq = recall(out["labels"]), recall(seq.search_many(q, 64)["labels"])
+    assert r_gpu > r_seq - 0.05, (r_gpu, r_seq)
+
+
+# ---------------------------------------------------------------------------------------------------
+# f2: scan iteration semantics (efSearch doubling, embedding.c:322-366)
+# ---------------------------------------------------------------------------------------------------
+def test_scan_doubles_efsearch(pg, oracle_mod):
+    rng = np.random.default_rng(2)
+    n, dims = 500, 8
+    x = _data(rng, n, dims)
+    idx = pg.HnswIndex(dims, 6, 24, 4, "l2", capacity=n)
+    idx.insert_many(x)
+    q = x[17] + 0.01
+    got = []
+    for lab in idx.scan(q, limit=40):
+        got.append(int(lab))
+    assert len(got) == 40 and len(set(got)) == 40
+    assert got[:4] == idx.search(q, 4).tolist()
+    assert idx.efsearch == 4  # restored
+    idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# K5: shard top-k merge
+# ---------------------------------------------------------------------------------------------------
+def test_merge_topk(pg):
+    import ctypes as C
+    import torch
+    from pg_embedding_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    nq, S, k = 50, 4, 16
+    d = np.sort(rng.integers(0, 20, size=(S, nq, k)).astype(np.float32), axis=2)  # many ties across shards
+    l = rng.permutation(S * nq * k).astype(np.int64).reshape(S, nq, k)
+    # within a shard list, equal distances must be in ascending label order (that is what search emits)
+    for s in range(S):
+        for qi in range(nq):
+            order = np.lexsort((l[s, qi], d[s, qi]))
+            d[s, qi], l[s, qi] = d[s, qi][order], l[s, qi][order]
+    nin = rng.integers(0, k + 1, size=(S, nq)).astype(np.int32)
+    td, tl, tn = torch.from_numpy(d).cuda(), torch.from_numpy(l).cuda(), torch.from_numpy(nin).cuda()
+    od = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    ol = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    on = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    st = lib.pgemb_merge_topk_device(nq, S, k, td.data_ptr(), tl.data_ptr(), tn.data_ptr(), od.data_ptr(), ol.data_ptr(),
+                                     on.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert st == 0
+    torch.cuda.synchronize()
+    od, ol, on = od.cpu().numpy(), ol.cpu().numpy(), on.cpu().numpy()
+    for qi in range(nq):
+        pairs = sorted((float(d[s, qi, i]), int(l[s, qi, i])) for s in range(S) for i in range(nin[s, qi]))[:k]
+        assert on[qi] == len(pairs)
+        assert [(float(a), int(b)) for a, b in zip(od[qi, :on[qi]], ol[qi, :on[qi]])] == pairs
