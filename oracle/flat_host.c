@@ -245,6 +245,22 @@ flat_append_raw(FlatIndex *fi, size_t n, const coord_t *coords, const label_t *l
 	return 0;
 }
 
+/* Append n records already in the reference's AoS layout (e.g. exported from the GPU index). */
+int
+flat_append_records(FlatIndex *fi, size_t n, const char *recs, size_t stride)
+{
+	if (fi->n_items + n > fi->capacity || stride < fi->meta.size_data_per_element)
+		return -1;
+	if (stride == fi->meta.size_data_per_element)
+		memcpy(fi->records + fi->n_items * stride, recs, n * stride);
+	else
+		for (size_t i = 0; i < n; i++)
+			memcpy(fi->records + (fi->n_items + i) * fi->meta.size_data_per_element, recs + i * stride,
+				   fi->meta.size_data_per_element);
+	fi->n_items += n;
+	return 0;
+}
+
 /* Bind an already stored record (used when records were appended raw with zero links). */
 int
 flat_bind(FlatIndex *fi, idx_t idx)

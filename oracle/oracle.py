@@ -80,6 +80,8 @@ def load(which: str) -> C.CDLL:
     lib.flat_add.argtypes = [vp, f32p, C.c_uint64]
     lib.flat_append_raw.restype = C.c_int
     lib.flat_append_raw.argtypes = [vp, sz, f32p, u64p, u32p]
+    lib.flat_append_records.restype = C.c_int
+    lib.flat_append_records.argtypes = [vp, sz, vp, sz]
     lib.flat_bind.restype = C.c_int
     lib.flat_bind.argtypes = [vp, C.c_uint32]
     lib.flat_get_links.argtypes = [vp, sz, sz, u32p]
@@ -196,6 +198,13 @@ class FlatIndex:
         rc = self.lib.flat_append_raw(self.h, v.shape[0], _f32p(v), lp, l.ctypes.data_as(C.POINTER(C.c_uint32)))
         if rc != 0:
             raise RuntimeError("flat_append_raw failed (capacity?)")
+
+    def load_records(self, records) -> None:
+        """Append nodes given in the reference record layout [n, record_size] uint8."""
+        r = np.ascontiguousarray(records, dtype=np.uint8)
+        rc = self.lib.flat_append_records(self.h, r.shape[0], r.ctypes.data_as(C.c_void_p), r.shape[1])
+        if rc != 0:
+            raise RuntimeError("flat_append_records failed (capacity / stride?)")
 
     def append_unbound(self, vecs, labels=None) -> None:
         v = np.ascontiguousarray(vecs, dtype=np.float32)
