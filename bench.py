@@ -53,12 +53,12 @@ def log(*a):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=int(os.environ.get("PGEMB_BENCH_N", 1_000_000)),
                     help="index size (default 1M = the BASELINE config; smaller values are for development only)")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PGEMB_BENCH_BATCH", 16384)), help="queries per step per GPU")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PGEMB_BENCH_BATCH", 32768)), help="queries per step per GPU")
     ap.add_argument("--build-batch", type=int, default=int(os.environ.get("PGEMB_BENCH_BUILD_BATCH", 4096)))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
@@ -200,6 +200,8 @@ def main():
     for s in range(W):
         step_device(s)
     barrier()
+    if os.environ.get("PGEMB_PROFILE"):   # ncu --profile-from-start off: capture exactly the timed region
+        torch.cuda.profiler.start()
     launches0 = int(lib.pgemb_launch_count())
     sampler = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -208,6 +210,8 @@ def main():
         step_device(s)
     ev1.record()
     torch.cuda.synchronize()
+    if os.environ.get("PGEMB_PROFILE"):
+        torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = int(lib.pgemb_launch_count()) - launches0
     clocks = sampler.stop()

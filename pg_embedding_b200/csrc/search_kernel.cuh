@@ -345,8 +345,14 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			}
 
 			// ================= expand c: link list + visited bitmap (hnswalg.cpp:76-93) ===========
+			// The whole link row is fetched in one round of loads (count and ids together: a dependent
+			// second DRAM round trip for the ids would sit on the critical path of every hop).
 			const uint32_t *L = p.links + (size_t) c * p.link_stride;
-			uint32_t		cnt = L[0];
+			uint32_t		w0 = 0, w1 = 0, w2 = 0;
+			if (lane < p.link_stride) w0 = L[lane];
+			if (lane + 32 < p.link_stride) w1 = L[lane + 32];
+			if (lane + 64 < p.link_stride) w2 = L[lane + 64];
+			uint32_t cnt = __shfl_sync(kFull, w0, 0);
 			if (cnt > p.maxM)
 			{
 				cnt = p.maxM;
@@ -357,9 +363,21 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			n = 0;
 			for (uint32_t base = 0; base < cnt; base += 32)
 			{
+				// list position k = base + lane lives in word k + 1
 				const uint32_t k = base + lane;
 				bool		   valid = k < cnt;
-				uint32_t	   id = valid ? L[1 + k] : 0u;
+				uint32_t	   id;
+				if (base < 64)
+				{
+					// word k+1 is held by lane (k+1)&31 in register (k+1)>>5
+					const uint32_t src = (lane + 1) & 31;
+					const uint32_t a = __shfl_sync(kFull, base == 0 ? w0 : w1, src);
+					const uint32_t b = __shfl_sync(kFull, base == 0 ? w1 : w2, src);
+					id = (lane == 31) ? b : a;
+				}
+				else
+					id = valid ? L[1 + k] : 0u;
+				if (!valid) id = 0u;
 				if (valid && id >= p.n_items)
 				{
 					valid = false;
