@@ -91,9 +91,8 @@ extern "C" bool hnsw_is_deleted(label_t label) { return ((label >> 48) & 1u) != 
 // ------------------------------------------------------------------------------------------------
 struct SearchConfig
 {
-	int		 tpr = 0;
-	uint32_t stages = 0, row_smem = 0, smem = 0, slots = 0;
-	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_hopnorm, off_mbar;
+	uint32_t stages = 0, stage_bytes = 0, row_smem = 0, smem = 0, slots = 0;
+	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_mbar;
 	uint32_t ef = 0;
 };
 
@@ -113,7 +112,9 @@ struct pgemb_index
 	bool		 ev_valid = false;
 	// search workspace
 	uint32_t	  ws_slots = 0, ws_ef = 0, vis_words = 0, vlog_cap = 0;
-	uint32_t	 *d_visited = nullptr, *d_vlog = nullptr;
+	uint32_t	 *d_visited = nullptr, *d_vlog = nullptr, *d_vhash = nullptr;
+	uint32_t	  ws_vh = 0;  // allocated hash entries per slot
+	size_t		  l2_persist_max = 0, l2_window_max = 0;
 	uint64_t	 *d_ovf = nullptr;
 	unsigned int *d_counter = nullptr;
 	int			 *d_error = nullptr;
@@ -151,6 +152,8 @@ extern "C" pgemb_status pgemb_index_create(const HnswMetadata *meta, size_t capa
 	cudaDeviceProp prop;
 	CU_TRY(cudaGetDeviceProperties(&prop, device));
 	idx->sm_count = prop.multiProcessorCount;
+	idx->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+	idx->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
 	cudaError_t e;
 #define ALLOC(ptr, bytes)                                                                                 \
 	if ((e = cudaMalloc((void **) &(ptr), (bytes))) != cudaSuccess)                                       \
@@ -184,6 +187,7 @@ extern "C" void pgemb_index_destroy(pgemb_index *idx)
 	cudaFree(idx->d_norms);
 	cudaFree(idx->d_visited);
 	cudaFree(idx->d_vlog);
+	cudaFree(idx->d_vhash);
 	cudaFree(idx->d_ovf);
 	cudaFree(idx->d_counter);
 	cudaFree(idx->d_error);
@@ -403,55 +407,40 @@ static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c)
 {
-	const int  metric = (int) idx->meta.dist_func;
-	const int  lanes = (metric == DIST_L2) ? 8 : 4;
-	int		   tpr = env_int("PGEMB_TPR", 4);
-	if (tpr != 1 && tpr != 2 && tpr != 4 && tpr != 8) tpr = 4;
-	if (tpr > lanes) tpr = lanes;
-	if (metric == DIST_L2 && tpr == 1) tpr = 2;
-	const uint32_t R = 32u / (uint32_t) tpr;
 	const uint32_t row_bytes = idx->row_f * 4u;
-	// bank-conflict-free row pitch in shared memory: 16 (mod 128) for the 4-lane metrics, 32 (mod 128) for L2
-	const uint32_t resid = (metric == DIST_L2) ? 32u : 16u;
-	uint32_t	   row_smem = row_bytes / 128u * 128u + resid;
+	// bank-conflict-free pitch of a WHOLE row in shared memory: == 16 (mod 128) so that the LDS.128 of 8
+	// consecutive lanes (8 different rows, same column) hit 8 distinct 16-byte bank groups
+	uint32_t row_smem = row_bytes / 128u * 128u + 16u;
 	if (row_smem < row_bytes) row_smem += 128u;
 	const uint32_t maxM = (uint32_t) idx->meta.maxM;
 	const uint32_t hopcap = maxM > 1 ? maxM : 1;
-	const uint32_t groups_per_hop = (hopcap + R - 1) / R;
 	const uint32_t smem_sm = 233472u;  // 228 KB per SM on sm_100
 	const uint32_t max_cta = 232448u;  // 227 KB per CTA
 
-	auto layout = [&](uint32_t stages, SearchConfig *o) {
+	// one stage must hold a 32-float slice of 32 rows at least (32 * (128 + 16) bytes)
+	uint32_t stage_bytes = (uint32_t) env_int("PGEMB_STAGE_KB", 12) * 1024u;
+	if (stage_bytes < 4608u) stage_bytes = 4608u;
+	// no point in a stage larger than the widest hop at full row width
+	const uint32_t widest = (hopcap < 32u ? hopcap : 32u) * row_smem;
+	if (stage_bytes > widest) stage_bytes = align_up(widest, 128);
+	uint32_t stages = (uint32_t) env_int("PGEMB_STAGES", 2);
+	if (stages < 1) stages = 1;
+	if (stages > 8) stages = 8;
+
+	auto layout = [&](uint32_t nst, SearchConfig *o) {
 		uint32_t off = 0;
 		o->off_q = off;			off = align_up(off + row_bytes, 128);
-		o->off_ring = off;		off = align_up(off + stages * R * row_smem, 16);
+		o->off_ring = off;		off = align_up(off + nst * stage_bytes, 16);
 		o->off_res = off;		off += 2u * ef * 8u;
 		o->off_hopkey = off;	off += hopcap * 8u;
 		o->off_acckey = off;	off += hopcap * 8u;
 		o->off_evict = off;		off += hopcap * 8u;
 		o->off_hopid = off;		off += hopcap * 4u;
-		o->off_hopnorm = off;	off += hopcap * 4u;
 		off = align_up(off, 8);
-		o->off_mbar = off;		off += stages * 8u;
+		o->off_mbar = off;		off += nst * 8u;
 		o->smem = align_up(off, 128);
-		o->stages = stages;
+		o->stages = nst;
 	};
-
-	int		 want_slots = env_int("PGEMB_SLOTS_PER_SM", 0);
-	int		 want_stages = env_int("PGEMB_STAGES", 0);
-	uint32_t stages;
-	if (want_stages > 0)
-		stages = (uint32_t) want_stages;
-	else
-	{
-		// default: a ring of ~48 KB (or one whole hop if that is smaller), at least 2 stages when they fit
-		const uint32_t target = 51200u;
-		stages = target / (R * row_smem);
-		if (stages < 1) stages = 1;
-	}
-	if (stages > groups_per_hop) stages = groups_per_hop;
-	if (stages > 32) stages = 32;
-	if (stages < 1) stages = 1;
 	SearchConfig t;
 	for (;;)
 	{
@@ -461,12 +450,13 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	}
 	if (t.smem > max_cta) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
 	*c = t;
-	c->tpr = tpr;
+	c->stage_bytes = stage_bytes;
 	c->row_smem = row_smem;
 	c->ef = ef;
 	uint32_t slots_sm = smem_sm / (c->smem + 1024u);
 	if (slots_sm < 1) slots_sm = 1;
 	if (slots_sm > 16) slots_sm = 16;
+	const int want_slots = env_int("PGEMB_SLOTS_PER_SM", 0);
 	if (want_slots > 0 && (uint32_t) want_slots < slots_sm) slots_sm = (uint32_t) want_slots;
 	c->slots = slots_sm * (uint32_t) idx->sm_count;
 	return PGEMB_OK;
@@ -474,48 +464,59 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 
 typedef void (*search_fn_t)(const SearchParams);
 
-static search_fn_t pick_search_kernel(int metric, int tpr)
+static search_fn_t pick_search_kernel(int metric)
 {
 	switch (metric)
 	{
-		case DIST_L2:
-			if (tpr == 2) return search_kernel<M_L2, 2>;
-			if (tpr == 4) return search_kernel<M_L2, 4>;
-			if (tpr == 8) return search_kernel<M_L2, 8>;
-			break;
-		case DIST_COSINE:
-			if (tpr == 1) return search_kernel<M_COS, 1>;
-			if (tpr == 2) return search_kernel<M_COS, 2>;
-			if (tpr == 4) return search_kernel<M_COS, 4>;
-			break;
-		case DIST_MANHATTAN:
-			if (tpr == 1) return search_kernel<M_MAN, 1>;
-			if (tpr == 2) return search_kernel<M_MAN, 2>;
-			if (tpr == 4) return search_kernel<M_MAN, 4>;
-			break;
+		case DIST_L2: return search_kernel<M_L2>;
+		case DIST_COSINE: return search_kernel<M_COS>;
+		case DIST_MANHATTAN: return search_kernel<M_MAN>;
 	}
 	return nullptr;
 }
 
-static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t ef)
+// Visited-set sizing: an open-addressing table of vh entries per slot (kept at most half full by the
+// kernel, which then migrates to the exact bitmap).  A search touches ~20*ef nodes on typical data.
+static uint32_t visited_hash_entries(const pgemb_index *idx, uint32_t ef)
+{
+	uint64_t want = (uint64_t) ef * 64u;
+	if (want < 4096) want = 4096;
+	uint32_t h = 4096;
+	while (h < want && h < (1u << 20)) h <<= 1;
+	const uint64_t bitmap_bytes = ((uint64_t) idx->capacity + 31) / 32 * 4;
+	if (env_int("PGEMB_VISITED_HASH", 1) == 0 || bitmap_bytes <= (uint64_t) h * 4) return 0;  // the bitmap is the smaller structure
+	return h;
+}
+
+static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t ef, uint32_t vh)
 {
 	const uint32_t vis_words = (uint32_t) ((idx->capacity + 31) / 32);
-	if (idx->ws_slots < slots || idx->vis_words != vis_words)
+	if (idx->ws_slots < slots || idx->vis_words != vis_words || idx->ws_vh < vh)
 	{
 		cudaFree(idx->d_visited);
 		cudaFree(idx->d_vlog);
+		cudaFree(idx->d_vhash);
 		idx->d_visited = nullptr;
 		idx->d_vlog = nullptr;
+		idx->d_vhash = nullptr;
+		if (slots < idx->ws_slots) slots = idx->ws_slots;
+		if (vh < idx->ws_vh) vh = idx->ws_vh;
 		idx->ws_slots = 0;
 		idx->vlog_cap = (uint32_t) (idx->capacity < 32768 ? idx->capacity : 32768);
+		if (idx->vlog_cap < vh / 2) idx->vlog_cap = vh / 2;
 		CU_TRY(cudaMalloc((void **) &idx->d_visited, (size_t) slots * vis_words * 4));
 		CU_TRY(cudaMemset(idx->d_visited, 0, (size_t) slots * vis_words * 4));
 		CU_TRY(cudaMalloc((void **) &idx->d_vlog, (size_t) slots * idx->vlog_cap * 4));
+		CU_TRY(cudaMalloc((void **) &idx->d_vhash, (size_t) slots * (vh ? vh : 1) * 4));
+		CU_TRY(cudaMemset(idx->d_vhash, 0xff, (size_t) slots * (vh ? vh : 1) * 4));
 		idx->ws_slots = slots;
+		idx->ws_vh = vh;
 		idx->vis_words = vis_words;
 		cudaFree(idx->d_ovf);
 		idx->d_ovf = nullptr;
 		idx->ws_ef = 0;
+		if (idx->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, idx->l2_persist_max * 3 / 4);
+		cudaGetLastError();
 	}
 	if (idx->ws_ef < ef || !idx->d_ovf)
 	{
@@ -541,15 +542,16 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	SearchConfig cfg;
 	st = make_config(idx, (uint32_t) ef, &cfg);
 	if (st) return st;
-	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, cfg.tpr);
-	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for metric/TPR");
+	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func);
+	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for this metric");
 	CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.smem));
 	int occ = 0;
 	CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, cfg.smem));
 	if (occ < 1) return fail(PGEMB_ERR_CAPACITY, "search kernel cannot be resident (shared memory)");
 	uint32_t slots = cfg.slots;
 	if ((uint32_t) occ * (uint32_t) idx->sm_count < slots) slots = (uint32_t) occ * (uint32_t) idx->sm_count;
-	st = ensure_workspace(idx, slots, (uint32_t) ef);
+	const uint32_t vh = visited_hash_entries(idx, (uint32_t) ef);
+	st = ensure_workspace(idx, slots, (uint32_t) ef, vh);
 	if (st) return st;
 
 	SearchParams p;
@@ -580,9 +582,18 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.ovf = idx->d_ovf;
 	p.vis_words = idx->vis_words;
 	p.vlog_cap = idx->vlog_cap;
+	p.vhash = idx->d_vhash;
+	p.vh_size = vh;
+	{
+		uint32_t lg = 0;
+		while ((1u << lg) < vh) lg++;
+		p.vh_shift = 32u - lg;
+	}
+	p.copy_mode = (uint32_t) env_int("PGEMB_COPY", 0);
 	p.counter = idx->d_counter;
 	p.error_flag = idx->d_error;
 	p.stages = cfg.stages;
+	p.stage_bytes = cfg.stage_bytes;
 	p.row_smem = cfg.row_smem;
 	p.row_bytes = idx->row_f * 4u;
 	p.off_q = cfg.off_q;
@@ -592,9 +603,22 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.off_acckey = cfg.off_acckey;
 	p.off_evict = cfg.off_evict;
 	p.off_hopid = cfg.off_hopid;
-	p.off_hopnorm = cfg.off_hopnorm;
 	p.off_mbar = cfg.off_mbar;
 
+	if (vh && idx->l2_window_max > 0 && env_int("PGEMB_L2_PERSIST", 1))
+	{
+		// keep the per-slot visited sets (hit on every hop by L2 atomics) resident while rows stream through L2
+		cudaStreamAttrValue av;
+		memset(&av, 0, sizeof(av));
+		size_t bytes = (size_t) slots * vh * 4;
+		if (bytes > idx->l2_window_max) bytes = idx->l2_window_max;
+		av.accessPolicyWindow.base_ptr = idx->d_vhash;
+		av.accessPolicyWindow.num_bytes = bytes;
+		av.accessPolicyWindow.hitRatio = 1.0f;
+		av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+	}
 	CU_TRY(cudaMemsetAsync(idx->d_counter, 0, sizeof(unsigned int), s));
 	const uint32_t grid = (uint32_t) (nq < slots ? nq : slots);
 	if (time_it) CU_TRY(cudaEventRecord(idx->ev0, s));

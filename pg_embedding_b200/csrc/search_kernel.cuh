@@ -57,20 +57,22 @@ struct SearchParams
 	uint32_t	 *vlog;			 // [slots][vlog_cap] ids whose bit was set (for O(visited) cleanup)
 	uint64_t	 *ovf;			 // [slots][ef]
 	uint32_t	  vis_words, vlog_cap;
+	uint32_t	 *vhash;		 // [slots][vh_size] open-addressing visited set (0xffffffff = empty), see "visited set"
+	uint32_t	  vh_size, vh_shift;  // vh_size = 2^k entries (0: bitmap only), hash = (id * 2654435761) >> vh_shift
+	uint32_t	  copy_mode;	 // 0: 16-byte cp.async (LDGSTS) pieces, 1: one bulk-TMA copy per row chunk
 	unsigned int *counter;		 // work-stealing query counter
 	int			 *error_flag;	 // sticky: 1 = bad link id, 2 = overflow buffer exceeded
 	// shared-memory layout (bytes from the dynamic smem base)
-	uint32_t stages, row_smem, row_bytes;
-	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_hopnorm, off_mbar;
+	uint32_t stages, stage_bytes, row_smem, row_bytes;
+	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_mbar;
 };
 
 constexpr uint32_t kNone = 0xffffffffu;
 
-template <int METRIC, int TPR>
+template <int METRIC>
 __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	constexpr int R = 32 / TPR;	 // rows scored per stage
 	float		  *q_s = reinterpret_cast<float *>(smem + p.off_q);
 	unsigned char *ring = smem + p.off_ring;
 	uint64_t	  *res = reinterpret_cast<uint64_t *>(smem + p.off_res);	// two buffers of ef keys
@@ -78,20 +80,20 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 	uint64_t	  *acc_key = reinterpret_cast<uint64_t *>(smem + p.off_acckey);
 	uint64_t	  *evict_key = reinterpret_cast<uint64_t *>(smem + p.off_evict);
 	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(smem + p.off_hopid);
-	float		  *hop_norm = reinterpret_cast<float *>(smem + p.off_hopnorm);
-	uint64_t	  *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
 
 	const uint32_t lane = threadIdx.x;
 	const uint32_t lt = lanemask_lt();
-	const int	   row_in_stage = lane / TPR;
-	const int	   sub = lane % TPR;
 	const uint32_t ef = p.ef;
 	const int	   dim = (int) p.dim;
 	const uint32_t S = p.stages;
 	uint32_t	  *vis = p.visited + (size_t) blockIdx.x * p.vis_words;
 	uint32_t	  *vlog = p.vlog + (size_t) blockIdx.x * p.vlog_cap;
 	uint64_t	  *ovf = p.ovf + (size_t) blockIdx.x * ef;
+	uint32_t	  *vh = p.vhash + (size_t) blockIdx.x * p.vh_size;
+	uint64_t	  *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
 	const uint64_t pol = l2_policy_evict_first();
+	const uint32_t H = p.vh_size;
+	constexpr uint32_t kEmpty = 0xffffffffu;
 
 	if (lane == 0)
 	{
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 		fence_mbar_init();
 	}
 	__syncwarp();
-	uint32_t parity = 0;  // bit s: phase parity the next wait on stage s must observe
+	uint32_t parity = 0;  // bit s: phase parity the next TMA wait on stage s must observe
 
 	for (;;)
 	{
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 		uint32_t r = 0;			// results held (<= ef), ascending (dist,id)
 		uint32_t ovf_n = 0, ovf_hw = 0;
 		uint32_t logn = 0;
+		uint32_t vmode = (H == 0) ? 1u : 0u;  // 0: hash set (log holds table positions), 1: bitmap (log holds ids)
 		uint32_t st_dist = 0, st_hops = 0, st_words = 0;
 
 		// ---- entry point (hnswalg.cpp:55-65): scored like a one-element hop ---------------------
@@ -131,8 +134,17 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			if (lane == 0)
 			{
 				hop_id[0] = p.entry;
-				atomicOr(&vis[p.entry >> 5], 1u << (p.entry & 31));
-				if (p.vlog_cap > 0) vlog[0] = p.entry;
+				if (vmode == 0)
+				{
+					const uint32_t h = (p.entry * 2654435761u) >> p.vh_shift;
+					vh[h] = p.entry;
+					vlog[0] = h;
+				}
+				else
+				{
+					atomicOr(&vis[p.entry >> 5], 1u << (p.entry & 31));
+					if (p.vlog_cap > 0) vlog[0] = p.entry;
+				}
 			}
 			n = 1;
 			logn = 1;
@@ -144,38 +156,97 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			if (n > 0)
 			{
 				// ================= K1: gather + score the n rows in hop_id[] ======================
-				const uint32_t G = (n + R - 1) / R;
+				// One thread per row (<= 32 rows per group).  A group's rows stream HBM -> smem in dimension
+				// CHUNKS through an S-stage ring: chunk width is chosen per group so that one chunk of all
+				// its rows fills a stage (few rows -> whole rows in one copy each; 32 rows -> 96-float
+				// slices), which keeps the ring small (more resident query slots per SM) and full.
 				st_dist += n;
-				auto issue = [&](uint32_t g) {
-					const uint32_t st = g % S;
-					const uint32_t rows = min((uint32_t) R, n - g * R);
-					if (lane == 0) mbar_arrive_expect_tx(&mbar[st], rows * p.row_bytes);
-					__syncwarp();
-					if (lane < rows)
+				for (uint32_t gb = 0; gb < n; gb += 32)
+				{
+					const uint32_t gsz = min(32u, n - gb);
+					uint32_t	   CH, pitch;
+					if (gsz * p.row_smem <= p.stage_bytes)
 					{
-						const uint32_t id = hop_id[g * R + lane];
-						tma_load_1d(ring + (size_t) (st * R + lane) * p.row_smem, p.vectors + (size_t) id * p.row_f,
-									p.row_bytes, &mbar[st], pol);
+						CH = p.row_f;
+						pitch = p.row_smem;
 					}
-				};
-				for (uint32_t g = 0; g < G && g < S; g++) issue(g);
-				if (METRIC == M_COS)
-				{
-					for (uint32_t k = lane; k < n; k += 32) hop_norm[k] = p.norms[hop_id[k]];
-					__syncwarp();
-				}
-				for (uint32_t g = 0; g < G; g++)
-				{
-					const uint32_t st = g % S;
-					mbar_wait(&mbar[st], (parity >> st) & 1u);
-					parity ^= 1u << st;
-					const uint32_t k = g * R + row_in_stage;
-					const float	  *rowp = reinterpret_cast<const float *>(ring + (size_t) (st * R + row_in_stage) * p.row_smem);
-					const float	   vn = (METRIC == M_COS && k < n) ? hop_norm[k] : 1.0f;
-					const float	   d = distance_exact<METRIC, TPR>(q_s, rowp, dim, qn, vn, sub);
-					if (sub == 0 && k < n) hop_key[k] = make_key(d, hop_id[k]);
-					__syncwarp();
-					if (g + S < G) issue(g + S);
+					else
+					{
+						CH = (((p.stage_bytes / gsz) - 16u) >> 2) & ~31u;  // multiple of 32 floats
+						pitch = CH * 4u + 16u;							   // == 16 (mod 128): conflict-free LDS.128
+					}
+					const uint32_t NC = (p.row_f + CH - 1) / CH;
+					const uint32_t my_id = hop_id[gb + min(lane, gsz - 1)];
+					// chunk c of all gsz rows -> stage c % S, as 16-byte cp.async pieces; the (row, piece) space is
+					// flattened over the lanes so every instruction moves 512 B, mostly contiguous per row
+					auto issue = [&](uint32_t c) {
+						const uint32_t st = c % S;
+						const uint32_t segs = min(CH, p.row_f - c * CH) >> 2;  // 16-byte pieces per row
+						unsigned char *stage = ring + (size_t) st * p.stage_bytes;
+						const float	  *src0 = p.vectors + (size_t) c * CH;
+						if (p.copy_mode == 1)
+						{
+							// bulk TMA: one elected lane issues one cp.async.bulk per row chunk (L2 evict-first)
+							if (lane == 0)
+							{
+								mbar_arrive_expect_tx(&mbar[st], gsz * segs * 16u);
+								for (uint32_t rr = 0; rr < gsz; rr++)
+									tma_load_1d(stage + (size_t) rr * pitch, src0 + (size_t) hop_id[gb + rr] * p.row_f, segs * 16u, &mbar[st], pol);
+							}
+							__syncwarp();
+							return;
+						}
+						uint32_t	   row = 0, j = lane;
+						while (j >= segs) { j -= segs; row++; }
+						while (row < gsz)
+						{
+							const uint32_t id = hop_id[gb + row];
+							cp_async16(stage + (size_t) row * pitch + (size_t) j * 16u, src0 + (size_t) id * p.row_f + (size_t) j * 4u, pol);
+							j += 32;
+							while (j >= segs) { j -= segs; row++; }
+						}
+					};
+					for (uint32_t c = 0; c < S; c++)
+					{
+						if (c < NC) issue(c);
+						cp_async_commit();	// one group per ring slot, empty when the row has fewer chunks
+					}
+					float vn = 1.0f;
+					if (METRIC == M_COS && lane < gsz) vn = p.norms[my_id];	 // in flight while the rows stream in
+					RowAcc<METRIC> acc;
+					acc_init<METRIC>(acc);
+					const int main_n = main_len<METRIC>(dim);
+					for (uint32_t c = 0; c < NC; c++)
+					{
+						const uint32_t st = c % S;
+						if (p.copy_mode == 1)
+						{
+							mbar_wait(&mbar[st], (parity >> st) & 1u);
+							parity ^= 1u << st;
+						}
+						else
+						{
+							cp_async_wait_dyn(S - 1);  // all but the S-1 most recent groups have landed -> chunk c is in
+							__syncwarp();
+						}
+						if (lane < gsz)
+						{
+							const float *vch = reinterpret_cast<const float *>(ring + (size_t) st * p.stage_bytes + (size_t) lane * pitch);
+							const int	 c0 = (int) (c * CH);
+							const int	 cf = (int) min(CH, p.row_f - c * CH);
+							const int	 nm = max(0, min(main_n - c0, cf));
+							acc_chunk<METRIC>(acc, q_s + c0, vch, nm);
+							if (c + 1 == NC)
+							{
+								const float d = acc_finish<METRIC>(acc, q_s + main_n, vch + (main_n - c0), dim - main_n, qn, vn);
+								hop_key[gb + lane] = make_key(d, my_id);
+							}
+						}
+						__syncwarp();
+						if (c + S < NC) issue(c + S);
+						cp_async_commit();
+					}
+					cp_async_wait<0>();
 				}
 
 				// ================= K2: sequential-equivalent queue update ==========================
@@ -361,6 +432,20 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			st_hops += 1;
 			st_words += 1 + cnt;
 			n = 0;
+			if (vmode == 0 && logn + cnt > (H >> 1))
+			{
+				// the open-addressing set would pass half full: migrate to the exact N-bit bitmap
+				for (uint32_t i = lane; i < logn; i += 32)
+				{
+					const uint32_t pos = vlog[i];
+					const uint32_t vid = __ldcg(&vh[pos]);	// written by L2 atomics: never read through L1
+					vh[pos] = kEmpty;
+					atomicOr(&vis[vid >> 5], 1u << (vid & 31));
+					vlog[i] = vid;
+				}
+				__syncwarp();
+				vmode = 1;
+			}
 			for (uint32_t base = 0; base < cnt; base += 32)
 			{
 				// list position k = base + lane lives in word k + 1
@@ -385,16 +470,35 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 				}
 				const uint32_t mm = __match_any_sync(kFull, valid ? id : (0x80000000u | lane));
 				const bool	   first = valid && ((uint32_t) (__ffs(mm) - 1) == lane);
-				const uint32_t bit = 1u << (id & 31);
-				uint32_t	   old = 0xffffffffu;
-				if (first) old = atomicOr(&vis[id >> 5], bit);
-				const bool	   unv = first && !(old & bit);
+				bool		   unv = false;
+				uint32_t	   logv = id;
+				if (vmode == 0)
+				{
+					if (first)
+					{
+						uint32_t h = (id * 2654435761u) >> p.vh_shift;
+						for (;;)
+						{
+							const uint32_t old = atomicCAS(&vh[h], kEmpty, id);
+							if (old == kEmpty) { unv = true; logv = h; break; }
+							if (old == id) break;
+							h = (h + 1) & (H - 1);
+						}
+					}
+				}
+				else
+				{
+					const uint32_t bit = 1u << (id & 31);
+					uint32_t	   old = 0xffffffffu;
+					if (first) old = atomicOr(&vis[id >> 5], bit);
+					unv = first && !(old & bit);
+				}
 				const uint32_t m = __ballot_sync(kFull, unv);
 				const uint32_t off = __popc(m & lt);
 				if (unv)
 				{
 					hop_id[n + off] = id;
-					if (logn + off < p.vlog_cap) vlog[logn + off] = id;
+					if (logn + off < p.vlog_cap) vlog[logn + off] = logv;
 				}
 				n += __popc(m);
 				logn += __popc(m);
@@ -470,7 +574,9 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 		}
 
 		// ---- reset the visited bitmap: O(visited) via the log, full clear if the log overflowed ----
-		if (logn <= p.vlog_cap)
+		if (vmode == 0)
+			for (uint32_t i = lane; i < logn; i += 32) vh[vlog[i]] = kEmpty;
+		else if (logn <= p.vlog_cap)
 			for (uint32_t i = lane; i < logn; i += 32) vis[vlog[i] >> 5] = 0u;
 		else
 			for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
