@@ -91,8 +91,8 @@ extern "C" bool hnsw_is_deleted(label_t label) { return ((label >> 48) & 1u) != 
 // ------------------------------------------------------------------------------------------------
 struct SearchConfig
 {
-	uint32_t stages = 0, stage_bytes = 0, row_smem = 0, smem = 0, slots = 0;
-	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_mbar;
+	uint32_t stages = 0, row_smem = 0, qt_stride = 0, smem = 0, slots = 0;
+	uint32_t off_qt, off_qtail, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_mbar;
 	uint32_t ef = 0;
 };
 
@@ -407,37 +407,41 @@ static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c)
 {
+	const int	   metric = (int) idx->meta.dist_func;
 	const uint32_t row_bytes = idx->row_f * 4u;
-	// bank-conflict-free pitch of a WHOLE row in shared memory: == 16 (mod 128) so that the LDS.128 of 8
-	// consecutive lanes (8 different rows, same column) hit 8 distinct 16-byte bank groups
-	uint32_t row_smem = row_bytes / 128u * 128u + 16u;
+	// bank-conflict-free pitch of a row in shared memory for the 4-lanes-per-row mapping:
+	// == 16 (mod 128) for the LDS.32 of cosine/manhattan, == 32 (mod 128) for the LDS.64 of L2
+	const uint32_t resid = (metric == DIST_L2) ? 32u : 16u;
+	uint32_t	   row_smem = row_bytes / 128u * 128u + resid;
 	if (row_smem < row_bytes) row_smem += 128u;
 	const uint32_t maxM = (uint32_t) idx->meta.maxM;
 	const uint32_t hopcap = maxM > 1 ? maxM : 1;
+	const uint32_t groups_per_hop = (hopcap + 7u) / 8u;
 	const uint32_t smem_sm = 233472u;  // 228 KB per SM on sm_100
 	const uint32_t max_cta = 232448u;  // 227 KB per CTA
+	// lane-major transposed query: per lane-thread a run of floats padded so that the four runs start
+	// 16 bytes apart modulo 128 (conflict-free LDS.128)
+	const uint32_t dim = (uint32_t) idx->meta.dim;
+	const uint32_t run = (metric == DIST_L2) ? ((dim & ~15u) >> 2) : ((dim & ~3u) >> 2);
+	const uint32_t qt_stride = align_up(run ? run : 1, 32) + 4u;
 
-	// one stage must hold a 32-float slice of 32 rows at least (32 * (128 + 16) bytes)
-	uint32_t stage_bytes = (uint32_t) env_int("PGEMB_STAGE_KB", 12) * 1024u;
-	if (stage_bytes < 4608u) stage_bytes = 4608u;
-	// no point in a stage larger than the widest hop at full row width
-	const uint32_t widest = (hopcap < 32u ? hopcap : 32u) * row_smem;
-	if (stage_bytes > widest) stage_bytes = align_up(widest, 128);
-	uint32_t stages = (uint32_t) env_int("PGEMB_STAGES", 2);
+	uint32_t stages = (uint32_t) env_int("PGEMB_STAGES", 1);
 	if (stages < 1) stages = 1;
-	if (stages > 8) stages = 8;
+	if (stages > groups_per_hop) stages = groups_per_hop;
+	if (stages > 16) stages = 16;
 
 	auto layout = [&](uint32_t nst, SearchConfig *o) {
 		uint32_t off = 0;
-		o->off_q = off;			off = align_up(off + row_bytes, 128);
-		o->off_ring = off;		off = align_up(off + nst * stage_bytes, 16);
+		o->off_qt = off;		off = align_up(off + 4u * qt_stride * 4u, 16);
+		o->off_qtail = off;		off = align_up(off + 16u * 4u, 128);
+		o->off_ring = off;		off = align_up(off + nst * 8u * row_smem, 16);
 		o->off_res = off;		off += 2u * ef * 8u;
 		o->off_hopkey = off;	off += hopcap * 8u;
 		o->off_acckey = off;	off += hopcap * 8u;
 		o->off_evict = off;		off += hopcap * 8u;
-		o->off_hopid = off;		off += hopcap * 4u;
-		off = align_up(off, 8);
-		o->off_mbar = off;		off += nst * 8u;
+		o->off_hopid = off;		off = align_up(off + hopcap * 4u, 16);
+		o->off_pf = off;		off = align_up(off + idx->link_stride * 4u, 8);
+		o->off_mbar = off;		off += (nst + 1u) * 8u;
 		o->smem = align_up(off, 128);
 		o->stages = nst;
 	};
@@ -450,8 +454,8 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	}
 	if (t.smem > max_cta) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
 	*c = t;
-	c->stage_bytes = stage_bytes;
 	c->row_smem = row_smem;
+	c->qt_stride = qt_stride;
 	c->ef = ef;
 	uint32_t slots_sm = smem_sm / (c->smem + 1024u);
 	if (slots_sm < 1) slots_sm = 1;
@@ -589,14 +593,16 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		while ((1u << lg) < vh) lg++;
 		p.vh_shift = 32u - lg;
 	}
-	p.copy_mode = (uint32_t) env_int("PGEMB_COPY", 0);
 	p.counter = idx->d_counter;
 	p.error_flag = idx->d_error;
 	p.stages = cfg.stages;
-	p.stage_bytes = cfg.stage_bytes;
 	p.row_smem = cfg.row_smem;
 	p.row_bytes = idx->row_f * 4u;
-	p.off_q = cfg.off_q;
+	p.qt_stride = cfg.qt_stride;
+	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
+	p.off_qt = cfg.off_qt;
+	p.off_qtail = cfg.off_qtail;
+	p.off_pf = cfg.off_pf;
 	p.off_ring = cfg.off_ring;
 	p.off_res = cfg.off_res;
 	p.off_hopkey = cfg.off_hopkey;

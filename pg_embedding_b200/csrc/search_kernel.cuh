@@ -7,10 +7,11 @@
 //
 // Structure per hop (one iteration of `while (!candidateSet.empty())`, hnswalg.cpp:67-112):
 //   pop      nearest unexpanded candidate; ties: larger id first (pair(-dist,id) max-heap, :53,:69)
-//   expand   read its link list [count, ids...] (:76-77), test-and-set the visited bitmap (:92-93)
-//   gather   K1: the unvisited neighbours' vectors are pulled HBM -> shared memory with 1-D bulk TMA
-//            (cp.async.bulk + mbarrier, S-stage ring of R rows) and scored with the reference's exact
-//            fp32 summation order (dist_exact.cuh)
+//   expand   its link list [count, ids...] (:76-77) -- normally already in shared memory, prefetched by
+//            bulk TMA during the previous hop's queue update -- and test-and-set of the visited set (:92-93)
+//   gather   K1: the unvisited neighbours' vectors are pulled HBM -> shared memory, one 1-D bulk TMA copy
+//            per row (cp.async.bulk + mbarrier, L2 evict-first, S-stage ring of 8 rows), and scored with
+//            the reference's exact fp32 summation order, 4 lanes per row
 //   update   K2: warp-level top-ef queue update that is EQUIVALENT to the reference's sequential
 //            push/pop loop (:99-108), exact distance ties included -- see "sequential equivalence".
 //
@@ -25,8 +26,11 @@
 // (:70).  Overflow entries exist only under exact distance ties; they are bounded by ef-1 and kept
 // in a per-slot global buffer.
 //
-// One warp = one slot: no CTA-wide barriers anywhere; smem per slot ~56 KB at dim=768 so 4 slots
-// share an SM and overlap each other's dependent-latency phases (pop -> links -> bitmap -> rows).
+// Visited set: an open-addressing table (atomicCAS at L2, kept resident with an L2 persistence window)
+// that migrates to the exact N-bit bitmap before it passes half full; both are reset in O(visited).
+//
+// One warp = one slot: no CTA-wide barriers anywhere; ~31 KB of shared memory per slot at dim 768, so 7
+// slots share an SM and overlap each other's dependent-latency phases (pop -> links -> visited -> rows).
 #pragma once
 #include "common.cuh"
 #include "dist_exact.cuh"
@@ -53,55 +57,127 @@ struct SearchParams
 	int32_t	 *n_out;			 // [nq]
 	uint32_t *stats_out;		 // [nq][4]: distance evals, expansions, link words, overflow high-water
 	// per-slot workspace
-	uint32_t	 *visited;		 // [slots][vis_words]
-	uint32_t	 *vlog;			 // [slots][vlog_cap] ids whose bit was set (for O(visited) cleanup)
+	uint32_t	 *visited;		 // [slots][vis_words]   exact bitmap (fallback / small indexes)
+	uint32_t	 *vlog;			 // [slots][vlog_cap]    table positions (hash mode) or ids (bitmap mode) to reset
 	uint64_t	 *ovf;			 // [slots][ef]
+	uint32_t	 *vhash;		 // [slots][vh_size]     open-addressing visited set, 0xffffffff = empty
 	uint32_t	  vis_words, vlog_cap;
-	uint32_t	 *vhash;		 // [slots][vh_size] open-addressing visited set (0xffffffff = empty), see "visited set"
 	uint32_t	  vh_size, vh_shift;  // vh_size = 2^k entries (0: bitmap only), hash = (id * 2654435761) >> vh_shift
-	uint32_t	  copy_mode;	 // 0: 16-byte cp.async (LDGSTS) pieces, 1: one bulk-TMA copy per row chunk
 	unsigned int *counter;		 // work-stealing query counter
-	int			 *error_flag;	 // sticky: 1 = bad link id, 2 = overflow buffer exceeded
+	int			 *error_flag;	 // sticky: 1 = bad link id / count, 2 = overflow buffer exceeded
 	// shared-memory layout (bytes from the dynamic smem base)
-	uint32_t stages, stage_bytes, row_smem, row_bytes;
-	uint32_t off_q, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_mbar;
+	uint32_t stages, row_smem, row_bytes, qt_stride;
+	uint32_t prefetch_links;
+	uint32_t off_qt, off_qtail, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_mbar;
 };
 
 constexpr uint32_t kNone = 0xffffffffu;
+constexpr int	   kTPR = 4;		   // lanes cooperating on one row
+constexpr int	   kRows = 32 / kTPR;  // rows per stage
+
+// ---- 4 lanes per row, query pre-transposed -----------------------------------------------------------
+// The query is stored lane-major in shared memory (qT): thread `sub` finds the values of ITS accumulator
+// chain(s) for four consecutive steps in one 16-byte word, so a step costs one LDS.32 of the row instead
+// of two loads (LDS issue, ~4 cycles per instruction per warp, is what bounds this loop).
+//   cosine / manhattan:  qT[sub*QS + i]        = q[4i + sub]
+//   L2 (2 chains/thread): qT[sub*QS + 4b + ..] = { q[16b+2s], q[16b+2s+1], q[16b+8+2s], q[16b+8+2s+1] }
+template <int METRIC>
+__device__ __forceinline__ float score_row4(const float *__restrict__ qts, const float *__restrict__ rowp, int sub, int main_n,
+											const float *__restrict__ q_tail, int dim, float qn, float vn)
+{
+	if (METRIC == M_L2)
+	{
+		float		 S0 = 0.f, S1 = 0.f;
+		const int	 nb = main_n >> 4;
+		const float *vp = rowp + 2 * sub;
+#pragma unroll 4
+		for (int b = 0; b < nb; b++)
+		{
+			const float4 qq = *reinterpret_cast<const float4 *>(qts + 4 * b);
+			const float2 ya = *reinterpret_cast<const float2 *>(vp + 16 * b);
+			const float2 yb = *reinterpret_cast<const float2 *>(vp + 16 * b + 8);
+			const float	 d00 = __fsub_rn(qq.x, ya.x), d10 = __fsub_rn(qq.z, yb.x);
+			const float	 d01 = __fsub_rn(qq.y, ya.y), d11 = __fsub_rn(qq.w, yb.y);
+			S0 = __fadd_rn(S0, __fadd_rn(__fmul_rn(d00, d00), __fmul_rn(d10, d10)));
+			S1 = __fadd_rn(S1, __fadd_rn(__fmul_rn(d01, d01), __fmul_rn(d11, d11)));
+		}
+		float full[8];
+#pragma unroll
+		for (int l = 0; l < 8; l++) full[l] = __shfl_sync(kFull, (l & 1) ? S1 : S0, l >> 1, 4);
+		float res = hsum4(__fadd_rn(full[0], full[4]), __fadd_rn(full[1], full[5]), __fadd_rn(full[2], full[6]), __fadd_rn(full[3], full[7]));
+		res = l2_tail_exact(res, q_tail, rowp + main_n, dim - main_n);
+		return __fsqrt_rn(res);
+	}
+	else
+	{
+		constexpr int TERM = (METRIC == M_COS) ? 0 : 1;
+		float		  s = 0.f;
+		const int	  n4 = main_n >> 2;
+		const float	 *vp = rowp + sub;
+		int			  k = 0;
+#pragma unroll 2
+		for (; k + 4 <= n4; k += 4)
+		{
+			const float4 qq = *reinterpret_cast<const float4 *>(qts + k);
+			const float	 v0 = vp[4 * k], v1 = vp[4 * k + 4], v2 = vp[4 * k + 8], v3 = vp[4 * k + 12];
+			s = __fadd_rn(s, term4<TERM>(qq.x, v0));
+			s = __fadd_rn(s, term4<TERM>(qq.y, v1));
+			s = __fadd_rn(s, term4<TERM>(qq.z, v2));
+			s = __fadd_rn(s, term4<TERM>(qq.w, v3));
+		}
+		for (; k < n4; k++) s = __fadd_rn(s, term4<TERM>(qts[k], vp[4 * k]));
+		const float f0 = __shfl_sync(kFull, s, 0, 4), f1 = __shfl_sync(kFull, s, 1, 4);
+		const float f2 = __shfl_sync(kFull, s, 2, 4), f3 = __shfl_sync(kFull, s, 3, 4);
+		float		res = hsum4(f0, f1, f2, f3);
+		for (int e = main_n; e < dim; e++) res = __fadd_rn(res, term4<TERM>(q_tail[e - main_n], rowp[e]));
+		if (METRIC == M_COS) return cosine_finish(res, qn, vn);
+		return res;
+	}
+}
 
 template <int METRIC>
 __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	float		  *q_s = reinterpret_cast<float *>(smem + p.off_q);
+	float		  *qT = reinterpret_cast<float *>(smem + p.off_qt);
+	float		  *q_tail = reinterpret_cast<float *>(smem + p.off_qtail);
 	unsigned char *ring = smem + p.off_ring;
 	uint64_t	  *res = reinterpret_cast<uint64_t *>(smem + p.off_res);	// two buffers of ef keys
 	uint64_t	  *hop_key = reinterpret_cast<uint64_t *>(smem + p.off_hopkey);
 	uint64_t	  *acc_key = reinterpret_cast<uint64_t *>(smem + p.off_acckey);
 	uint64_t	  *evict_key = reinterpret_cast<uint64_t *>(smem + p.off_evict);
 	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(smem + p.off_hopid);
+	uint32_t	  *pf_links = reinterpret_cast<uint32_t *>(smem + p.off_pf);
+	uint64_t	  *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);	// [stages] rows, [stages] = link prefetch
 
 	const uint32_t lane = threadIdx.x;
 	const uint32_t lt = lanemask_lt();
+	const int	   row_in_stage = lane / kTPR;
+	const int	   sub = lane % kTPR;
 	const uint32_t ef = p.ef;
 	const int	   dim = (int) p.dim;
+	const int	   main_n = main_len<METRIC>(dim);
 	const uint32_t S = p.stages;
+	const uint32_t H = p.vh_size;
 	uint32_t	  *vis = p.visited + (size_t) blockIdx.x * p.vis_words;
 	uint32_t	  *vlog = p.vlog + (size_t) blockIdx.x * p.vlog_cap;
 	uint64_t	  *ovf = p.ovf + (size_t) blockIdx.x * ef;
-	uint32_t	  *vh = p.vhash + (size_t) blockIdx.x * p.vh_size;
-	uint64_t	  *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);
-	const uint64_t pol = l2_policy_evict_first();
-	const uint32_t H = p.vh_size;
+	uint32_t	  *vh = p.vhash + (size_t) blockIdx.x * H;
+	uint64_t	  *pf_bar = &mbar[S];
+	const uint64_t pol_stream = l2_policy_evict_first();
+	const uint64_t pol_keep = l2_policy_evict_last();
 	constexpr uint32_t kEmpty = 0xffffffffu;
 
 	if (lane == 0)
 	{
-		for (uint32_t s = 0; s < S; s++) mbar_init(&mbar[s], 1);
+		for (uint32_t s = 0; s <= S; s++) mbar_init(&mbar[s], 1);
 		fence_mbar_init();
 	}
 	__syncwarp();
-	uint32_t parity = 0;  // bit s: phase parity the next TMA wait on stage s must observe
+	uint32_t parity = 0;	   // bit s: phase parity the next wait on stage s must observe
+	uint32_t pf_parity = 0;	   // same for the link prefetch barrier
+	bool	 pf_inflight = false;
+	uint32_t pf_id = kNone;
 
 	for (;;)
 	{
@@ -110,15 +186,36 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 		qi = __shfl_sync(kFull, qi, 0);
 		if (qi >= p.nq) break;
 
-		// ---- stage the query in shared memory -------------------------------------------------
+		// ---- stage the query: lane-major transposed copy + natural-order tail -------------------
 		{
-			const float *qsrc = p.query_ids ? p.vectors + (size_t) p.query_ids[qi] * p.row_f
-											: p.queries + (size_t) qi * p.q_stride;
-			for (uint32_t i = lane; i < p.row_f; i += 32) q_s[i] = (i < p.dim) ? qsrc[i] : 0.0f;
+			const float *qsrc = p.query_ids ? p.vectors + (size_t) p.query_ids[qi] * p.row_f : p.queries + (size_t) qi * p.q_stride;
+			for (int e = (int) lane; e < dim; e += 32)
+			{
+				const float v = qsrc[e];
+				if (e >= main_n)
+					q_tail[e - main_n] = v;
+				else if (METRIC == M_L2)
+				{
+					const int b = e >> 4, o = e & 15, l = o & 7;
+					qT[(l >> 1) * p.qt_stride + 4 * b + ((o >> 3) << 1) + (l & 1)] = v;
+				}
+				else
+					qT[(e & 3) * p.qt_stride + (e >> 2)] = v;
+			}
 		}
 		__syncwarp();
 		float qn = 0.0f;
-		if (METRIC == M_COS) qn = sqnorm_exact<4>(q_s, dim, lane & 3);	// distfunc.c:141 once per query
+		if (METRIC == M_COS)
+		{
+			// |q|^2 in the reference's lane order (distfunc.c:141), once per query instead of once per call
+			float		 s = 0.f;
+			const float *qts = qT + sub * p.qt_stride;
+			for (int k = 0; k < (main_n >> 2); k++) s = __fadd_rn(s, __fmul_rn(qts[k], qts[k]));
+			const float f0 = __shfl_sync(kFull, s, 0, 4), f1 = __shfl_sync(kFull, s, 1, 4);
+			const float f2 = __shfl_sync(kFull, s, 2, 4), f3 = __shfl_sync(kFull, s, 3, 4);
+			qn = hsum4(f0, f1, f2, f3);
+			for (int e = main_n; e < dim; e++) qn = __fadd_rn(qn, __fmul_rn(q_tail[e - main_n], q_tail[e - main_n]));
+		}
 
 		int		 cur = 0;		// which res buffer is live
 		uint32_t r = 0;			// results held (<= ef), ascending (dist,id)
@@ -156,105 +253,95 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			if (n > 0)
 			{
 				// ================= K1: gather + score the n rows in hop_id[] ======================
-				// One thread per row (<= 32 rows per group).  A group's rows stream HBM -> smem in dimension
-				// CHUNKS through an S-stage ring: chunk width is chosen per group so that one chunk of all
-				// its rows fills a stage (few rows -> whole rows in one copy each; 32 rows -> 96-float
-				// slices), which keeps the ring small (more resident query slots per SM) and full.
+				const uint32_t G = (n + kRows - 1) / kRows;
 				st_dist += n;
-				for (uint32_t gb = 0; gb < n; gb += 32)
+				auto issue = [&](uint32_t g) {
+					const uint32_t st = g % S;
+					const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
+					if (lane == 0) mbar_arrive_expect_tx(&mbar[st], rows * p.row_bytes);
+					__syncwarp();
+					if (lane < rows)
+					{
+						const uint32_t id = hop_id[g * kRows + lane];
+						tma_load_1d(ring + (size_t) (st * kRows + lane) * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes,
+									&mbar[st], pol_stream);
+					}
+				};
+				for (uint32_t g = 0; g < G && g < S; g++) issue(g);
+				const float *qts = qT + sub * p.qt_stride;
+				for (uint32_t g = 0; g < G; g++)
 				{
-					const uint32_t gsz = min(32u, n - gb);
-					uint32_t	   CH, pitch;
-					if (gsz * p.row_smem <= p.stage_bytes)
+					const uint32_t st = g % S;
+					const uint32_t k = g * kRows + row_in_stage;
+					const uint32_t kk = min(k, n - 1);
+					const uint32_t my_id = hop_id[kk];
+					float		   vn = 1.0f;
+					if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
+					mbar_wait(&mbar[st], (parity >> st) & 1u);
+					parity ^= 1u << st;
+					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) (st * kRows + row_in_stage) * p.row_smem);
+					const float	 d = score_row4<METRIC>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
+					if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
+					__syncwarp();
+					if (g + S < G) issue(g + S);
+				}
+
+				const uint64_t *Rb = res + (size_t) cur * ef;
+				uint64_t	   *Ob = res + (size_t) (cur ^ 1) * ef;
+				const uint32_t	W = (r == ef) ? key_dist(Rb[ef - 1]) : 0xffffffffu;
+
+				// ---- prefetch the link row of the candidate that will be popped next -------------------
+				// Known before the queue update: it is the nearer of (best unexpanded result so far, nearest
+				// new neighbour) -- the nearest new neighbour is always accepted when it beats an existing
+				// result.  Only a hint: a wrong guess (exact ties, overflow list) falls back to global loads.
+				if (p.prefetch_links)
+				{
+					uint64_t bestp = ~0ull;	 // (dist << 32 | 0x7fffffff - id): smaller pops first
+					for (uint32_t base = 0; base < r; base += 32)
 					{
-						CH = p.row_f;
-						pitch = p.row_smem;
+						const uint32_t i = base + lane;
+						const bool	   un = (i < r) && !key_expanded(Rb[i]);
+						const uint32_t m = __ballot_sync(kFull, un);
+						if (m)
+						{
+							const uint64_t kx = Rb[base + __ffs(m) - 1];
+							bestp = ((uint64_t) key_dist(kx) << 32) | (uint64_t) (0x7fffffffu - key_id(kx));
+							break;
+						}
 					}
-					else
+					uint64_t mine = ~0ull;
+					for (uint32_t k = lane; k < n; k += 32)
 					{
-						CH = (((p.stage_bytes / gsz) - 16u) >> 2) & ~31u;  // multiple of 32 floats
-						pitch = CH * 4u + 16u;							   // == 16 (mod 128): conflict-free LDS.128
+						const uint64_t kx = hop_key[k];
+						if (r + n <= ef || key_dist(kx) < W)
+						{
+							const uint64_t pr = ((uint64_t) key_dist(kx) << 32) | (uint64_t) (0x7fffffffu - key_id(kx));
+							mine = min(mine, pr);
+						}
 					}
-					const uint32_t NC = (p.row_f + CH - 1) / CH;
-					const uint32_t my_id = hop_id[gb + min(lane, gsz - 1)];
-					// chunk c of all gsz rows -> stage c % S, as 16-byte cp.async pieces; the (row, piece) space is
-					// flattened over the lanes so every instruction moves 512 B, mostly contiguous per row
-					auto issue = [&](uint32_t c) {
-						const uint32_t st = c % S;
-						const uint32_t segs = min(CH, p.row_f - c * CH) >> 2;  // 16-byte pieces per row
-						unsigned char *stage = ring + (size_t) st * p.stage_bytes;
-						const float	  *src0 = p.vectors + (size_t) c * CH;
-						if (p.copy_mode == 1)
-						{
-							// bulk TMA: one elected lane issues one cp.async.bulk per row chunk (L2 evict-first)
-							if (lane == 0)
-							{
-								mbar_arrive_expect_tx(&mbar[st], gsz * segs * 16u);
-								for (uint32_t rr = 0; rr < gsz; rr++)
-									tma_load_1d(stage + (size_t) rr * pitch, src0 + (size_t) hop_id[gb + rr] * p.row_f, segs * 16u, &mbar[st], pol);
-							}
-							__syncwarp();
-							return;
-						}
-						uint32_t	   row = 0, j = lane;
-						while (j >= segs) { j -= segs; row++; }
-						while (row < gsz)
-						{
-							const uint32_t id = hop_id[gb + row];
-							cp_async16(stage + (size_t) row * pitch + (size_t) j * 16u, src0 + (size_t) id * p.row_f + (size_t) j * 4u, pol);
-							j += 32;
-							while (j >= segs) { j -= segs; row++; }
-						}
-					};
-					for (uint32_t c = 0; c < S; c++)
+					for (int off = 16; off > 0; off >>= 1) mine = min(mine, __shfl_xor_sync(kFull, mine, off));
+					bestp = min(bestp, mine);
+					if (bestp != ~0ull)
 					{
-						if (c < NC) issue(c);
-						cp_async_commit();	// one group per ring slot, empty when the row has fewer chunks
-					}
-					float vn = 1.0f;
-					if (METRIC == M_COS && lane < gsz) vn = p.norms[my_id];	 // in flight while the rows stream in
-					RowAcc<METRIC> acc;
-					acc_init<METRIC>(acc);
-					const int main_n = main_len<METRIC>(dim);
-					for (uint32_t c = 0; c < NC; c++)
-					{
-						const uint32_t st = c % S;
-						if (p.copy_mode == 1)
+						if (pf_inflight)
 						{
-							mbar_wait(&mbar[st], (parity >> st) & 1u);
-							parity ^= 1u << st;
+							mbar_wait(pf_bar, pf_parity);  // an unused earlier prefetch: long complete, frees the buffer
+							pf_parity ^= 1u;
 						}
-						else
-						{
-							cp_async_wait_dyn(S - 1);  // all but the S-1 most recent groups have landed -> chunk c is in
-							__syncwarp();
-						}
-						if (lane < gsz)
-						{
-							const float *vch = reinterpret_cast<const float *>(ring + (size_t) st * p.stage_bytes + (size_t) lane * pitch);
-							const int	 c0 = (int) (c * CH);
-							const int	 cf = (int) min(CH, p.row_f - c * CH);
-							const int	 nm = max(0, min(main_n - c0, cf));
-							acc_chunk<METRIC>(acc, q_s + c0, vch, nm);
-							if (c + 1 == NC)
-							{
-								const float d = acc_finish<METRIC>(acc, q_s + main_n, vch + (main_n - c0), dim - main_n, qn, vn);
-								hop_key[gb + lane] = make_key(d, my_id);
-							}
-						}
+						pf_id = 0x7fffffffu - (uint32_t) (bestp & 0xffffffffu);
 						__syncwarp();
-						if (c + S < NC) issue(c + S);
-						cp_async_commit();
+						if (lane == 0)
+						{
+							mbar_arrive_expect_tx(pf_bar, p.link_stride * 4u);
+							tma_load_1d(pf_links, p.links + (size_t) pf_id * p.link_stride, p.link_stride * 4u, pf_bar, pol_keep);
+						}
+						pf_inflight = true;
 					}
-					cp_async_wait<0>();
 				}
 
 				// ================= K2: sequential-equivalent queue update ==========================
-				const uint64_t *Rb = res + (size_t) cur * ef;
-				uint64_t	   *Ob = res + (size_t) (cur ^ 1) * ef;
-				const bool		all_accept = (r + n <= ef);
-				const uint32_t	W = (r == ef) ? key_dist(Rb[ef - 1]) : 0xffffffffu;
-				uint32_t		a = 0;
+				const bool all_accept = (r + n <= ef);
+				uint32_t   a = 0;
 				for (uint32_t base = 0; base < n; base += 32)
 				{
 					const uint32_t k = base + lane;
@@ -395,8 +482,7 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 					if (op < bp) { bp = op; bi = oi; }
 				}
 				uint64_t rp = ~0ull;
-				if (best >= 0)
-					rp = ((uint64_t) key_dist(Rb[best]) << 32) | (uint64_t) (0x7fffffffu - key_id(Rb[best]));
+				if (best >= 0) rp = ((uint64_t) key_dist(Rb[best]) << 32) | (uint64_t) (0x7fffffffu - key_id(Rb[best]));
 				if (bp < rp)
 				{
 					from_ovf = true;
@@ -415,14 +501,28 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 				__syncwarp();
 			}
 
-			// ================= expand c: link list + visited bitmap (hnswalg.cpp:76-93) ===========
-			// The whole link row is fetched in one round of loads (count and ids together: a dependent
-			// second DRAM round trip for the ids would sit on the critical path of every hop).
+			// ================= expand c: link list + visited set (hnswalg.cpp:76-93) ==============
+			// The whole link row is obtained in one go (count and ids together: a dependent second DRAM
+			// round trip for the ids would sit on the critical path of every hop) -- from the prefetch
+			// buffer when the guess was right, else from global memory.
 			const uint32_t *L = p.links + (size_t) c * p.link_stride;
 			uint32_t		w0 = 0, w1 = 0, w2 = 0;
-			if (lane < p.link_stride) w0 = L[lane];
-			if (lane + 32 < p.link_stride) w1 = L[lane + 32];
-			if (lane + 64 < p.link_stride) w2 = L[lane + 64];
+			const bool		hit = pf_inflight && pf_id == c;
+			if (hit)
+			{
+				mbar_wait(pf_bar, pf_parity);
+				pf_parity ^= 1u;
+				pf_inflight = false;
+				if (lane < p.link_stride) w0 = pf_links[lane];
+				if (lane + 32 < p.link_stride) w1 = pf_links[lane + 32];
+				if (lane + 64 < p.link_stride) w2 = pf_links[lane + 64];
+			}
+			else
+			{
+				if (lane < p.link_stride) w0 = L[lane];
+				if (lane + 32 < p.link_stride) w1 = L[lane + 32];
+				if (lane + 64 < p.link_stride) w2 = L[lane + 64];
+			}
 			uint32_t cnt = __shfl_sync(kFull, w0, 0);
 			if (cnt > p.maxM)
 			{
@@ -461,7 +561,7 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 					id = (lane == 31) ? b : a;
 				}
 				else
-					id = valid ? L[1 + k] : 0u;
+					id = valid ? (hit ? pf_links[1 + k] : L[1 + k]) : 0u;
 				if (!valid) id = 0u;
 				if (valid && id >= p.n_items)
 				{
@@ -573,7 +673,7 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			}
 		}
 
-		// ---- reset the visited bitmap: O(visited) via the log, full clear if the log overflowed ----
+		// ---- reset the visited set: O(visited) via the log, full clear if the log overflowed ---------
 		if (vmode == 0)
 			for (uint32_t i = lane; i < logn; i += 32) vh[vlog[i]] = kEmpty;
 		else if (logn <= p.vlog_cap)
@@ -582,6 +682,8 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 			for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
 		__syncwarp();
 	}
+	// an unconsumed link prefetch must land before the CTA (and its shared memory) goes away
+	if (pf_inflight) mbar_wait(pf_bar, pf_parity);
 }
 
 }  // namespace pgemb
