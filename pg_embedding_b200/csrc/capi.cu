@@ -91,8 +91,9 @@ extern "C" bool hnsw_is_deleted(label_t label) { return ((label >> 48) & 1u) != 
 // ------------------------------------------------------------------------------------------------
 struct SearchConfig
 {
-	uint32_t stages = 0, row_smem = 0, qt_stride = 0, smem = 0, slots = 0;
-	uint32_t off_qt, off_qtail, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_mbar;
+	uint32_t warps = 0, rings = 0, ring_bytes = 0, priv_bytes = 0, row_smem = 0, qt_stride = 0, smem = 0, slots = 0;
+	uint32_t off_pool = 0, off_ring = 0, off_priv = 0;
+	uint32_t off_qt = 0, off_qtail = 0, off_res = 0, off_hopkey = 0, off_acckey = 0, off_evict = 0, off_hopid = 0, off_pf = 0, off_pfbar = 0;
 	uint32_t ef = 0;
 };
 
@@ -416,8 +417,6 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	if (row_smem < row_bytes) row_smem += 128u;
 	const uint32_t maxM = (uint32_t) idx->meta.maxM;
 	const uint32_t hopcap = maxM > 1 ? maxM : 1;
-	const uint32_t groups_per_hop = (hopcap + 7u) / 8u;
-	const uint32_t smem_sm = 233472u;  // 228 KB per SM on sm_100
 	const uint32_t max_cta = 232448u;  // 227 KB per CTA
 	// lane-major transposed query: per lane-thread a run of floats padded so that the four runs start
 	// 16 bytes apart modulo 128 (conflict-free LDS.128)
@@ -425,44 +424,58 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	const uint32_t run = (metric == DIST_L2) ? ((dim & ~15u) >> 2) : ((dim & ~3u) >> 2);
 	const uint32_t qt_stride = align_up(run ? run : 1, 32) + 4u;
 
-	uint32_t stages = (uint32_t) env_int("PGEMB_STAGES", 1);
-	if (stages < 1) stages = 1;
-	if (stages > groups_per_hop) stages = groups_per_hop;
-	if (stages > 16) stages = 16;
-
-	auto layout = [&](uint32_t nst, SearchConfig *o) {
-		uint32_t off = 0;
-		o->off_qt = off;		off = align_up(off + 4u * qt_stride * 4u, 16);
-		o->off_qtail = off;		off = align_up(off + 16u * 4u, 128);
-		o->off_ring = off;		off = align_up(off + nst * 8u * row_smem, 16);
-		o->off_res = off;		off += 2u * ef * 8u;
-		o->off_hopkey = off;	off += hopcap * 8u;
-		o->off_acckey = off;	off += hopcap * 8u;
-		o->off_evict = off;		off += hopcap * 8u;
-		o->off_hopid = off;		off = align_up(off + hopcap * 4u, 16);
-		o->off_pf = off;		off = align_up(off + idx->link_stride * 4u, 8);
-		o->off_mbar = off;		off += (nst + 1u) * 8u;
-		o->smem = align_up(off, 128);
-		o->stages = nst;
-	};
 	SearchConfig t;
-	for (;;)
+	// ---- a slot's private block ----
+	uint32_t off = 0;
+	t.off_qt = off;			off = align_up(off + 4u * qt_stride * 4u, 16);
+	t.off_qtail = off;		off = align_up(off + 16u * 4u, 16);
+	t.off_res = off;		off += 2u * ef * 8u;
+	t.off_hopkey = off;		off += hopcap * 8u;
+	t.off_acckey = off;		off += hopcap * 8u;
+	t.off_evict = off;		off += hopcap * 8u;
+	t.off_hopid = off;		off = align_up(off + hopcap * 4u, 16);
+	t.off_pf = off;			off = align_up(off + idx->link_stride * 4u, 8);
+	t.off_pfbar = off;		off += 8u;
+	t.priv_bytes = align_up(off, 128);
+	t.ring_bytes = align_up(8u * row_smem, 128);
+	const uint32_t pool_bytes = align_up((uint32_t) sizeof(RingPool), 128);
+	// ---- how many slots (warps) and rings per CTA (= per SM) ----
+	// A slot holds a ring for about `duty` of a hop; throughput ~ min(W / T_hop, R / (duty * T_hop)).
+	const double duty = env_int("PGEMB_RING_DUTY_PCT", 55) / 100.0;
+	uint32_t	 bestW = 0, bestR = 0;
+	double		 bestv = -1.0;
+	for (uint32_t W = 1; W <= 32; W++)
 	{
-		layout(stages, &t);
-		if (t.smem <= max_cta || stages == 1) break;
-		stages -= 1;
+		if (pool_bytes + W * t.priv_bytes + t.ring_bytes > max_cta) break;
+		uint32_t R = (max_cta - pool_bytes - W * t.priv_bytes) / t.ring_bytes;
+		if (R > W) R = W;
+		if (R > 31) R = 31;
+		const double v = (W < R / duty) ? (double) W : R / duty;
+		if (v > bestv + 1e-9)
+		{
+			bestv = v;
+			bestW = W;
+			bestR = R;
+		}
 	}
-	if (t.smem > max_cta) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
+	if (bestW == 0) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
+	const int wantW = env_int("PGEMB_WARPS", 0), wantR = env_int("PGEMB_RINGS", 0);
+	if (wantW > 0 && wantW <= 32) bestW = (uint32_t) wantW;
+	if (wantR > 0 && wantR <= 31) bestR = (uint32_t) wantR;
+	if (bestR > bestW) bestR = bestW;
+	while (bestR > 1 && pool_bytes + bestW * t.priv_bytes + bestR * t.ring_bytes > max_cta) bestR--;
+	if (pool_bytes + bestW * t.priv_bytes + bestR * t.ring_bytes > max_cta) return fail(PGEMB_ERR_CAPACITY, "PGEMB_WARPS/PGEMB_RINGS do not fit shared memory");
+	t.warps = bestW;
+	t.rings = bestR;
+	t.off_pool = 0;
+	t.off_ring = pool_bytes;
+	t.off_priv = pool_bytes + bestR * t.ring_bytes;
+	t.smem = t.off_priv + bestW * t.priv_bytes;
+	t.row_smem = row_smem;
+	t.qt_stride = qt_stride;
+	t.ef = ef;
+	t.slots = bestW * (uint32_t) idx->sm_count;
 	*c = t;
-	c->row_smem = row_smem;
-	c->qt_stride = qt_stride;
-	c->ef = ef;
-	uint32_t slots_sm = smem_sm / (c->smem + 1024u);
-	if (slots_sm < 1) slots_sm = 1;
-	if (slots_sm > 16) slots_sm = 16;
-	const int want_slots = env_int("PGEMB_SLOTS_PER_SM", 0);
-	if (want_slots > 0 && (uint32_t) want_slots < slots_sm) slots_sm = (uint32_t) want_slots;
-	c->slots = slots_sm * (uint32_t) idx->sm_count;
 	return PGEMB_OK;
 }
 
@@ -550,10 +563,9 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for this metric");
 	CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.smem));
 	int occ = 0;
-	CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 32, cfg.smem));
-	if (occ < 1) return fail(PGEMB_ERR_CAPACITY, "search kernel cannot be resident (shared memory)");
-	uint32_t slots = cfg.slots;
-	if ((uint32_t) occ * (uint32_t) idx->sm_count < slots) slots = (uint32_t) occ * (uint32_t) idx->sm_count;
+	CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int) cfg.warps * 32, cfg.smem));
+	if (occ < 1) return fail(PGEMB_ERR_CAPACITY, "search kernel cannot be resident (shared memory / registers)");
+	const uint32_t slots = cfg.slots;
 	const uint32_t vh = visited_hash_entries(idx, (uint32_t) ef);
 	st = ensure_workspace(idx, slots, (uint32_t) ef, vh);
 	if (st) return st;
@@ -595,7 +607,12 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	}
 	p.counter = idx->d_counter;
 	p.error_flag = idx->d_error;
-	p.stages = cfg.stages;
+	p.rings = cfg.rings;
+	p.ring_bytes = cfg.ring_bytes;
+	p.off_pool = cfg.off_pool;
+	p.off_priv = cfg.off_priv;
+	p.priv_bytes = cfg.priv_bytes;
+	p.off_pfbar = cfg.off_pfbar;
 	p.row_smem = cfg.row_smem;
 	p.row_bytes = idx->row_f * 4u;
 	p.qt_stride = cfg.qt_stride;
@@ -609,7 +626,6 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.off_acckey = cfg.off_acckey;
 	p.off_evict = cfg.off_evict;
 	p.off_hopid = cfg.off_hopid;
-	p.off_mbar = cfg.off_mbar;
 
 	if (vh && idx->l2_window_max > 0 && env_int("PGEMB_L2_PERSIST", 1))
 	{
@@ -626,9 +642,10 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
 	}
 	CU_TRY(cudaMemsetAsync(idx->d_counter, 0, sizeof(unsigned int), s));
-	const uint32_t grid = (uint32_t) (nq < slots ? nq : slots);
+	uint32_t grid = (uint32_t) ((nq + cfg.warps - 1) / cfg.warps);
+	if (grid > (uint32_t) idx->sm_count) grid = (uint32_t) idx->sm_count;
 	if (time_it) CU_TRY(cudaEventRecord(idx->ev0, s));
-	fn<<<grid, 32, cfg.smem, s>>>(p);
+	fn<<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
 	g_launches++;
 	CU_TRY(cudaGetLastError());
 	if (time_it)

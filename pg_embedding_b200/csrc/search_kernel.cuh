@@ -66,9 +66,20 @@ struct SearchParams
 	unsigned int *counter;		 // work-stealing query counter
 	int			 *error_flag;	 // sticky: 1 = bad link id / count, 2 = overflow buffer exceeded
 	// shared-memory layout (bytes from the dynamic smem base)
-	uint32_t stages, row_smem, row_bytes, qt_stride;
+	// A CTA = W query slots (warps) sharing a POOL of `rings` row rings: a slot needs a ring only while it
+	// gathers+scores (about half of a hop), so rings -- the shared-memory-hungry resource that bounds
+	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
+	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
 	uint32_t prefetch_links;
-	uint32_t off_qt, off_qtail, off_ring, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_mbar;
+	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
+	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
+};
+
+struct RingPool
+{
+	uint32_t free_mask;		// bit b set = ring b is free
+	uint32_t par[31];		// phase parity the next wait on ring b's barrier must observe
+	uint64_t bar[31];		// one mbarrier per ring
 };
 
 constexpr uint32_t kNone = 0xffffffffu;
@@ -115,15 +126,50 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 		const int	  n4 = main_n >> 2;
 		const float	 *vp = rowp + sub;
 		int			  k = 0;
-#pragma unroll 2
-		for (; k + 4 <= n4; k += 4)
+		// Software-pipelined by hand: the chain `s` is one dependent FADD per step (4-cycle latency) and a
+		// warp can issue one LDS every ~4 cycles, so the loads of the NEXT 8 steps are interleaved with
+		// the adds of the CURRENT 8 steps; left to itself ptxas issues 10 loads, stalls on the first
+		// product, then runs the 8-add chain back to back (~115 cycles per 8 steps instead of ~45).
+		const int nit = n4 >> 3;
+		if (nit > 0)
 		{
-			const float4 qq = *reinterpret_cast<const float4 *>(qts + k);
-			const float	 v0 = vp[4 * k], v1 = vp[4 * k + 4], v2 = vp[4 * k + 8], v3 = vp[4 * k + 12];
-			s = __fadd_rn(s, term4<TERM>(qq.x, v0));
-			s = __fadd_rn(s, term4<TERM>(qq.y, v1));
-			s = __fadd_rn(s, term4<TERM>(qq.z, v2));
-			s = __fadd_rn(s, term4<TERM>(qq.w, v3));
+			const float4 *qp = reinterpret_cast<const float4 *>(qts);
+			float4		  qa = qp[0], qb = qp[1];
+			float		  v0 = vp[0], v1 = vp[4], v2 = vp[8], v3 = vp[12], v4 = vp[16], v5 = vp[20], v6 = vp[24], v7 = vp[28];
+#pragma unroll 1
+			for (int it = 1; it < nit; it++)
+			{
+				const float *vn_ = vp + 32 * it;
+				const float4 na = qp[2 * it];
+				s = __fadd_rn(s, term4<TERM>(qa.x, v0));
+				const float w0 = vn_[0];
+				s = __fadd_rn(s, term4<TERM>(qa.y, v1));
+				const float w1 = vn_[4];
+				s = __fadd_rn(s, term4<TERM>(qa.z, v2));
+				const float w2 = vn_[8];
+				s = __fadd_rn(s, term4<TERM>(qa.w, v3));
+				const float w3 = vn_[12];
+				const float4 nb = qp[2 * it + 1];
+				s = __fadd_rn(s, term4<TERM>(qb.x, v4));
+				const float w4 = vn_[16];
+				s = __fadd_rn(s, term4<TERM>(qb.y, v5));
+				const float w5 = vn_[20];
+				s = __fadd_rn(s, term4<TERM>(qb.z, v6));
+				const float w6 = vn_[24];
+				s = __fadd_rn(s, term4<TERM>(qb.w, v7));
+				const float w7 = vn_[28];
+				qa = na; qb = nb;
+				v0 = w0; v1 = w1; v2 = w2; v3 = w3; v4 = w4; v5 = w5; v6 = w6; v7 = w7;
+			}
+			s = __fadd_rn(s, term4<TERM>(qa.x, v0));
+			s = __fadd_rn(s, term4<TERM>(qa.y, v1));
+			s = __fadd_rn(s, term4<TERM>(qa.z, v2));
+			s = __fadd_rn(s, term4<TERM>(qa.w, v3));
+			s = __fadd_rn(s, term4<TERM>(qb.x, v4));
+			s = __fadd_rn(s, term4<TERM>(qb.y, v5));
+			s = __fadd_rn(s, term4<TERM>(qb.z, v6));
+			s = __fadd_rn(s, term4<TERM>(qb.w, v7));
+			k = nit << 3;
 		}
 		for (; k < n4; k++) s = __fadd_rn(s, term4<TERM>(qts[k], vp[4 * k]));
 		const float f0 = __shfl_sync(kFull, s, 0, 4), f1 = __shfl_sync(kFull, s, 1, 4);
@@ -136,46 +182,53 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
+__global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
-	float		  *qT = reinterpret_cast<float *>(smem + p.off_qt);
-	float		  *q_tail = reinterpret_cast<float *>(smem + p.off_qtail);
-	unsigned char *ring = smem + p.off_ring;
-	uint64_t	  *res = reinterpret_cast<uint64_t *>(smem + p.off_res);	// two buffers of ef keys
-	uint64_t	  *hop_key = reinterpret_cast<uint64_t *>(smem + p.off_hopkey);
-	uint64_t	  *acc_key = reinterpret_cast<uint64_t *>(smem + p.off_acckey);
-	uint64_t	  *evict_key = reinterpret_cast<uint64_t *>(smem + p.off_evict);
-	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(smem + p.off_hopid);
-	uint32_t	  *pf_links = reinterpret_cast<uint32_t *>(smem + p.off_pf);
-	uint64_t	  *mbar = reinterpret_cast<uint64_t *>(smem + p.off_mbar);	// [stages] rows, [stages] = link prefetch
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warp = threadIdx.x >> 5;
+	const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;
+	RingPool	  *pool = reinterpret_cast<RingPool *>(smem + p.off_pool);
+	unsigned char *ring_base = smem + p.off_ring;
+	unsigned char *priv = smem + p.off_priv + (size_t) warp * p.priv_bytes;	// this slot's private block
+	float		  *qT = reinterpret_cast<float *>(priv + p.off_qt);
+	float		  *q_tail = reinterpret_cast<float *>(priv + p.off_qtail);
+	uint64_t	  *res = reinterpret_cast<uint64_t *>(priv + p.off_res);	// two buffers of ef keys
+	uint64_t	  *hop_key = reinterpret_cast<uint64_t *>(priv + p.off_hopkey);
+	uint64_t	  *acc_key = reinterpret_cast<uint64_t *>(priv + p.off_acckey);
+	uint64_t	  *evict_key = reinterpret_cast<uint64_t *>(priv + p.off_evict);
+	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(priv + p.off_hopid);
+	uint32_t	  *pf_links = reinterpret_cast<uint32_t *>(priv + p.off_pf);
+	uint64_t	  *pf_bar = reinterpret_cast<uint64_t *>(priv + p.off_pfbar);
 
-	const uint32_t lane = threadIdx.x;
 	const uint32_t lt = lanemask_lt();
 	const int	   row_in_stage = lane / kTPR;
 	const int	   sub = lane % kTPR;
 	const uint32_t ef = p.ef;
 	const int	   dim = (int) p.dim;
 	const int	   main_n = main_len<METRIC>(dim);
-	const uint32_t S = p.stages;
 	const uint32_t H = p.vh_size;
-	uint32_t	  *vis = p.visited + (size_t) blockIdx.x * p.vis_words;
-	uint32_t	  *vlog = p.vlog + (size_t) blockIdx.x * p.vlog_cap;
-	uint64_t	  *ovf = p.ovf + (size_t) blockIdx.x * ef;
-	uint32_t	  *vh = p.vhash + (size_t) blockIdx.x * H;
-	uint64_t	  *pf_bar = &mbar[S];
+	uint32_t	  *vis = p.visited + (size_t) slot * p.vis_words;
+	uint32_t	  *vlog = p.vlog + (size_t) slot * p.vlog_cap;
+	uint64_t	  *ovf = p.ovf + (size_t) slot * ef;
+	uint32_t	  *vh = p.vhash + (size_t) slot * H;
 	const uint64_t pol_stream = l2_policy_evict_first();
 	const uint64_t pol_keep = l2_policy_evict_last();
 	constexpr uint32_t kEmpty = 0xffffffffu;
 
-	if (lane == 0)
+	if (threadIdx.x == 0)
 	{
-		for (uint32_t s = 0; s <= S; s++) mbar_init(&mbar[s], 1);
-		fence_mbar_init();
+		pool->free_mask = (p.rings >= 32) ? 0xffffffffu : ((1u << p.rings) - 1u);
+		for (uint32_t b = 0; b < p.rings; b++)
+		{
+			pool->par[b] = 0;
+			mbar_init(&pool->bar[b], 1);
+		}
 	}
-	__syncwarp();
-	uint32_t parity = 0;	   // bit s: phase parity the next wait on stage s must observe
-	uint32_t pf_parity = 0;	   // same for the link prefetch barrier
+	if (lane == 0) mbar_init(pf_bar, 1);
+	fence_mbar_init();
+	__syncthreads();		   // the only CTA-wide barrier: from here on the slots run independently
+	uint32_t pf_parity = 0;	   // phase parity for the link prefetch barrier
 	bool	 pf_inflight = false;
 	uint32_t pf_id = kNone;
 
@@ -255,35 +308,64 @@ __global__ void __launch_bounds__(32) search_kernel(const SearchParams p)
 				// ================= K1: gather + score the n rows in hop_id[] ======================
 				const uint32_t G = (n + kRows - 1) / kRows;
 				st_dist += n;
-				auto issue = [&](uint32_t g) {
-					const uint32_t st = g % S;
-					const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
-					if (lane == 0) mbar_arrive_expect_tx(&mbar[st], rows * p.row_bytes);
-					__syncwarp();
-					if (lane < rows)
+				// ---- take a ring from the CTA's pool (held for this hop's gather only) ----------------
+				uint32_t rb = 0;
+				if (lane == 0)
+				{
+					for (;;)
 					{
-						const uint32_t id = hop_id[g * kRows + lane];
-						tma_load_1d(ring + (size_t) (st * kRows + lane) * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes,
-									&mbar[st], pol_stream);
+						const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&pool->free_mask);
+						if (m != 0u)
+						{
+							const uint32_t b = (uint32_t) __ffs(m) - 1u;
+							if (atomicCAS(&pool->free_mask, m, m & ~(1u << b)) == m)
+							{
+								rb = b;
+								break;
+							}
+						}
+						else
+							__nanosleep(100);
 					}
+					__threadfence_block();
+				}
+				rb = __shfl_sync(kFull, rb, 0);
+				unsigned char *ring = ring_base + (size_t) rb * p.ring_bytes;
+				uint64_t	  *rbar = &pool->bar[rb];
+				uint32_t	   rpar = *reinterpret_cast<volatile uint32_t *>(&pool->par[rb]);
+				auto		   issue = [&](uint32_t g) {
+					  const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
+					  if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
+					  __syncwarp();
+					  if (lane < rows)
+					  {
+						  const uint32_t id = hop_id[g * kRows + lane];
+						  tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
+					  }
 				};
-				for (uint32_t g = 0; g < G && g < S; g++) issue(g);
+				issue(0);
 				const float *qts = qT + sub * p.qt_stride;
 				for (uint32_t g = 0; g < G; g++)
 				{
-					const uint32_t st = g % S;
 					const uint32_t k = g * kRows + row_in_stage;
 					const uint32_t kk = min(k, n - 1);
 					const uint32_t my_id = hop_id[kk];
 					float		   vn = 1.0f;
 					if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
-					mbar_wait(&mbar[st], (parity >> st) & 1u);
-					parity ^= 1u << st;
-					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) (st * kRows + row_in_stage) * p.row_smem);
+					mbar_wait(rbar, rpar);
+					rpar ^= 1u;
+					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
 					const float	 d = score_row4<METRIC>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
 					if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
 					__syncwarp();
-					if (g + S < G) issue(g + S);
+					if (g + 1 < G) issue(g + 1);
+				}
+				// ---- give the ring back ---------------------------------------------------------------
+				if (lane == 0)
+				{
+					*reinterpret_cast<volatile uint32_t *>(&pool->par[rb]) = rpar;
+					__threadfence_block();
+					atomicOr(&pool->free_mask, 1u << rb);
 				}
 
 				const uint64_t *Rb = res + (size_t) cur * ef;
