@@ -113,6 +113,7 @@ struct pgemb_index
 	static constexpr int kMaxChunks = 16;
 	cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host-pointer batch API
 	cudaEvent_t	 ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
+	unsigned int *h_avail = nullptr;  // pinned: values the copy stream publishes to the running kernel
 	bool		 ev_valid = false;
 	// search workspace
 	uint32_t	  ws_slots = 0, ws_ef = 0, vis_words = 0, vlog_cap = 0;
@@ -199,6 +200,7 @@ extern "C" void pgemb_index_destroy(pgemb_index *idx)
 	bind_ws_free(idx->bind_ws);
 	if (idx->stream) cudaStreamDestroy(idx->stream);
 	if (idx->s_in) cudaStreamDestroy(idx->s_in);
+	if (idx->h_avail) cudaFreeHost(idx->h_avail);
 	if (idx->s_out) cudaStreamDestroy(idx->s_out);
 	for (int i = 0; i < pgemb_index::kMaxChunks; i++)
 	{
@@ -558,7 +560,7 @@ static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t 
 // Launch the traversal for nq queries.  All pointers are device pointers.
 pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, uint32_t q_stride, const uint32_t *d_query_ids,
 						   uint32_t n_items, size_t ef, int raw_mode, label_t *d_labels_out, dist_t *d_dists_out, idx_t *d_ids_out,
-						   int32_t *d_n_out, uint32_t *d_stats_out, cudaStream_t s, bool time_it)
+						   int32_t *d_n_out, uint32_t *d_stats_out, cudaStream_t s, bool time_it, const unsigned int *d_avail = nullptr)
 {
 	if (!idx || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
 	if (ef < 1 || ef > (1u << 20)) return fail(PGEMB_ERR_ARG, "ef out of range");
@@ -616,6 +618,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		p.vh_shift = 32u - lg;
 	}
 	p.counter = idx->d_counter;
+	p.avail = d_avail;
 	p.error_flag = idx->d_error;
 	p.rings = cfg.rings;
 	p.ring_bytes = cfg.ring_bytes;
@@ -711,45 +714,41 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 	uint32_t *d_i = (uint32_t *) base;			base += up(ib);
 	int32_t	 *d_n = (int32_t *) base;			base += up(nb);
 	uint32_t *d_s = (uint32_t *) base;
-	// Pipeline over query chunks on three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the traversal
-	// of chunk c (kernels themselves stay serialised on one stream: they share the per-slot workspace).
+	// ONE traversal launch; the query batch is streamed in behind it: the copy stream moves chunk after chunk
+	// H2D and publishes "queries available" after each, the kernel's slots wait for their query to land
+	// (SearchParams::avail).  So the PCIe transfer hides behind the traversal instead of preceding it.
 	cudaStream_t s = idx->stream;
 	if (!idx->s_in)
 	{
 		CU_TRY(cudaStreamCreateWithFlags(&idx->s_in, cudaStreamNonBlocking));
-		CU_TRY(cudaStreamCreateWithFlags(&idx->s_out, cudaStreamNonBlocking));
-		for (int i = 0; i < pgemb_index::kMaxChunks; i++)
-		{
-			CU_TRY(cudaEventCreateWithFlags(&idx->ev_in[i], cudaEventDisableTiming));
-			CU_TRY(cudaEventCreateWithFlags(&idx->ev_k[i], cudaEventDisableTiming));
-		}
+		CU_TRY(cudaEventCreateWithFlags(&idx->ev_in[0], cudaEventDisableTiming));
+		CU_TRY(cudaMallocHost((void **) &idx->h_avail, sizeof(unsigned int) * pgemb_index::kMaxChunks));
 	}
-	size_t nchunks = (nq + 8191) / 8192;
+	unsigned int *d_avail = idx->d_counter + 2;
+	size_t		  nchunks = (nq + 4095) / 4096;
 	if (nchunks > (size_t) pgemb_index::kMaxChunks) nchunks = pgemb_index::kMaxChunks;
-	if (nchunks < 1) nchunks = 1;
 	const size_t per = (nq + nchunks - 1) / nchunks;
-	// the staging buffers may still be read/written by the previous call's copy streams: order after them
-	CU_TRY(cudaStreamSynchronize(idx->s_out));
+	CU_TRY(cudaMemsetAsync(d_avail, 0, sizeof(unsigned int), idx->s_in));
+	CU_TRY(cudaEventRecord(idx->ev_in[0], idx->s_in));
+	CU_TRY(cudaStreamWaitEvent(s, idx->ev_in[0], 0));
+	st = launch_search(idx, nq, d_q, (uint32_t) dim, nullptr, (uint32_t) idx->n, ef, 0, labels_out ? d_l : nullptr, dists_out ? d_d : nullptr,
+					   ids_out ? d_i : nullptr, d_n, stats_out ? d_s : nullptr, s, true, d_avail);
+	if (st) return st;
 	for (size_t c = 0; c < nchunks; c++)
 	{
-		const size_t q0 = c * per, qn_ = (q0 + per <= nq) ? per : (nq - q0);
-		if (q0 >= nq) { nchunks = c; break; }
+		const size_t q0 = c * per;
+		if (q0 >= nq) break;
+		const size_t qn_ = (q0 + per <= nq) ? per : (nq - q0);
 		CU_TRY(cudaMemcpyAsync(d_q + q0 * dim, queries + q0 * dim, qn_ * dim * sizeof(float), cudaMemcpyHostToDevice, idx->s_in));
-		CU_TRY(cudaEventRecord(idx->ev_in[c], idx->s_in));
-		CU_TRY(cudaStreamWaitEvent(s, idx->ev_in[c], 0));
-		st = launch_search(idx, qn_, d_q + q0 * dim, (uint32_t) dim, nullptr, (uint32_t) idx->n, ef, 0, labels_out ? d_l + q0 * ef : nullptr,
-						   dists_out ? d_d + q0 * ef : nullptr, ids_out ? d_i + q0 * ef : nullptr, d_n + q0, stats_out ? d_s + q0 * 4 : nullptr, s,
-						   c == 0);
-		if (st) return st;
-		CU_TRY(cudaEventRecord(idx->ev_k[c], s));
-		CU_TRY(cudaStreamWaitEvent(idx->s_out, idx->ev_k[c], 0));
-		if (labels_out) CU_TRY(cudaMemcpyAsync(labels_out + q0 * ef, d_l + q0 * ef, qn_ * ef * sizeof(uint64_t), cudaMemcpyDeviceToHost, idx->s_out));
-		if (dists_out) CU_TRY(cudaMemcpyAsync(dists_out + q0 * ef, d_d + q0 * ef, qn_ * ef * sizeof(float), cudaMemcpyDeviceToHost, idx->s_out));
-		if (ids_out) CU_TRY(cudaMemcpyAsync(ids_out + q0 * ef, d_i + q0 * ef, qn_ * ef * sizeof(uint32_t), cudaMemcpyDeviceToHost, idx->s_out));
-		CU_TRY(cudaMemcpyAsync(n_out + q0, d_n + q0, qn_ * sizeof(int32_t), cudaMemcpyDeviceToHost, idx->s_out));
-		if (stats_out) CU_TRY(cudaMemcpyAsync(stats_out + q0 * 4, d_s + q0 * 4, qn_ * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, idx->s_out));
+		idx->h_avail[c] = (unsigned int) (q0 + qn_);
+		CU_TRY(cudaMemcpyAsync(d_avail, &idx->h_avail[c], sizeof(unsigned int), cudaMemcpyHostToDevice, idx->s_in));
 	}
-	CU_TRY(cudaStreamSynchronize(idx->s_out));
+	if (labels_out) CU_TRY(cudaMemcpyAsync(labels_out, d_l, lb, cudaMemcpyDeviceToHost, s));
+	if (dists_out) CU_TRY(cudaMemcpyAsync(dists_out, d_d, db, cudaMemcpyDeviceToHost, s));
+	if (ids_out) CU_TRY(cudaMemcpyAsync(ids_out, d_i, ib, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaMemcpyAsync(n_out, d_n, nb, cudaMemcpyDeviceToHost, s));
+	if (stats_out) CU_TRY(cudaMemcpyAsync(stats_out, d_s, sb, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaStreamSynchronize(idx->s_in));
 	return check_device_error(idx, s);
 }
 

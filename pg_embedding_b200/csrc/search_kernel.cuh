@@ -64,6 +64,7 @@ struct SearchParams
 	uint32_t	  vis_words, vlog_cap;
 	uint32_t	  vh_size, vh_shift;  // vh_size = 2^k entries (0: bitmap only), hash = (id * 2654435761) >> vh_shift
 	unsigned int *counter;		 // work-stealing query counter
+	const unsigned int *avail;	 // optional: number of queries whose data has landed (host API streams them in while the kernel runs)
 	int			 *error_flag;	 // sticky: 1 = bad link id / count, 2 = overflow buffer exceeded
 	// shared-memory layout (bytes from the dynamic smem base)
 	// A CTA = W query slots (warps) sharing a POOL of `rings` row rings: a slot needs a ring only while it
@@ -238,6 +239,13 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 		if (lane == 0) qi = atomicAdd(p.counter, 1u);
 		qi = __shfl_sync(kFull, qi, 0);
 		if (qi >= p.nq) break;
+		if (p.avail)
+		{
+			// the batch is still being copied in by the DMA engine: wait until query qi is there
+			if (lane == 0)
+				while (*reinterpret_cast<const volatile unsigned int *>(p.avail) <= qi) __nanosleep(500);
+			__syncwarp();
+		}
 
 		// ---- stage the query: lane-major transposed copy + natural-order tail -------------------
 		{
