@@ -337,3 +337,89 @@ def test_merge_topk(pg):
         pairs = sorted((float(d[s, qi, i]), int(l[s, qi, i])) for s in range(S) for i in range(nin[s, qi]))[:k]
         assert on[qi] == len(pairs)
         assert [(float(a), int(b)) for a, b in zip(od[qi, :on[qi]], ol[qi, :on[qi]])] == pairs
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE-sized checks: configs[1] against the oracle on a CPU-built graph, configs[2] (N=1M) through
+# size-independent properties + an oracle sample on the GPU-built graph
+# ---------------------------------------------------------------------------------------------------
+def _clustered(rng, n, dim, centres):
+    sigma = 0.3 * np.sqrt(2.0 * dim) / np.sqrt(dim)
+    a = rng.integers(0, centres.shape[0], n)
+    x = centres[a] + sigma * rng.standard_normal((n, dim)).astype(np.float32)
+    return np.ascontiguousarray(x.astype(np.float32))
+
+
+def test_config1_dims128_l2_vs_oracle(pg, oracle_mod):
+    """BASELINE configs[1] shape (dims=128, L2, m=16, efC=200, efS=64) at N=30K: the graph is built by the
+    reference algorithm on the CPU (sequential, exact), searched by both; 4096 queries must match exactly."""
+    rng = np.random.default_rng(128)
+    n, dims, m, efc, efs = 30_000, 128, 16, 200, 64
+    centres = rng.standard_normal((173, dims)).astype(np.float32)
+    x, q = _clustered(rng, n, dims, centres), _clustered(rng, 4096, dims, centres)
+    which = "ref" if oracle_mod.available("ref") else "port"
+    orc = oracle_mod.FlatIndex(which, dims, m, efc, efs, "l2", capacity=n)
+    orc.build(x)
+    idx = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=n)
+    idx.load_records(orc.records())
+    out = idx.search_batch(q, efs, want_stats=True)
+    want = orc.search_many(q, efs, nthreads=os.cpu_count() or 4, want_counters=True)
+    assert out["labels"].tobytes() == want["labels"].tobytes()
+    assert (out["stats"][:, :3].astype(np.uint64) == want["counters"]).all()
+    # exact sequential GPU binds reproduce the tail of the CPU build bit for bit: re-bind the last 300 nodes
+    idx2 = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=n)
+    cut = n - 300
+    orc2 = oracle_mod.FlatIndex(which, dims, m, efc, efs, "l2", capacity=n)
+    orc2.build(x[:cut])
+    idx2.load_records(orc2.records())
+    idx2.insert_many(x[cut:])
+    assert idx2.links().tobytes() == orc.links().tobytes()
+    idx.close(); idx2.close()
+
+
+def test_config2_full_size_properties(pg, oracle_mod):
+    """BASELINE configs[2] at FULL size (dims=768, N=1M, cosine, m=32, efC=200, efS=64), GPU bulk build.
+    Size-independent properties on 8192 queries + exact agreement with the CPU oracle on a 96-query sample."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+        pytest.skip("needs a large-memory GPU")
+    import ctypes as C
+    from pg_embedding_b200 import _lib
+    lib = _lib.load()
+    n, dims, m, efc, efs = 1_000_000, 768, 32, 200, 64
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    centres = torch.randn((1000, dims), generator=g, device="cuda")
+    def gen(k):
+        a = torch.randint(0, 1000, (k,), generator=g, device="cuda")
+        x = centres[a] + 0.424 * torch.randn((k, dims), generator=g, device="cuda")
+        return x / x.norm(dim=1, keepdim=True)
+    X = torch.cat([gen(250_000) for _ in range(4)])
+    Q = gen(8192)
+    idx = pg.HnswIndex(dims, m, efc, efs, "cosine", capacity=n)
+    _lib.check(lib.pgemb_index_append_device(idx.dev, n, X.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    idx.build_appended(0, n, 4096)
+    q = Q.cpu().numpy()
+    out = idx.search_batch(q, efs, want_stats=True)
+    again = idx.search_batch(q, efs)
+    assert out["labels"].tobytes() == again["labels"].tobytes()            # idempotent / deterministic
+    assert (out["n"] == efs).all()
+    d, ids = out["dists"], out["ids"]
+    assert (np.diff(d, axis=1) >= 0).all()                                 # ascending by distance
+    assert all(len(set(r.tolist())) == efs for r in ids[::64])             # distinct nodes
+    assert (out["labels"] == ids).all()                                    # label == id here
+    re = idx.dist_gather(q[:512], ids[:512])                               # distances recomputed pair by pair
+    assert re.tobytes() == d[:512].tobytes()
+    assert (out["stats"][:, 0] >= efs).all() and (out["stats"][:, 1] >= 1).all()
+    # graph structure
+    links = idx.links(0, 200_000)
+    assert (links[:, 0] <= 2 * m).all() and (links[1:, 0] > 0).all()
+    # oracle sample on the identical graph (reference record layout exported from HBM)
+    which = "ref" if oracle_mod.available("ref") else "port"
+    orc = oracle_mod.FlatIndex(which, dims, m, efc, efs, "cosine", capacity=n)
+    for s in range(0, n, 1 << 16):
+        orc.load_records(idx.export_records(s, min(1 << 16, n - s)))
+    want = orc.search_many(q[:96], efs, nthreads=min(96, os.cpu_count() or 4), want_counters=True)
+    assert out["labels"][:96].tobytes() == want["labels"].tobytes()
+    assert (out["stats"][:96, :3].astype(np.uint64) == want["counters"]).all()
+    idx.close()
