@@ -508,7 +508,7 @@ static search_fn_t pick_search_kernel(int metric)
 // kernel, which then migrates to the exact bitmap).  A search touches ~20*ef nodes on typical data.
 static uint32_t visited_hash_entries(const pgemb_index *idx, uint32_t ef)
 {
-	uint64_t want = (uint64_t) ef * 64u;
+	uint64_t want = (uint64_t) ef * (uint64_t) env_int("PGEMB_VH_PER_EF", 64);
 	if (want < 4096) want = 4096;
 	uint32_t h = 4096;
 	while (h < want && h < (1u << 20)) h <<= 1;

@@ -102,17 +102,48 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 		float		 S0 = 0.f, S1 = 0.f;
 		const int	 nb = main_n >> 4;
 		const float *vp = rowp + 2 * sub;
-#pragma unroll 4
-		for (int b = 0; b < nb; b++)
+		// two 16-float blocks per iteration, the loads of the next pair interleaved with the arithmetic of the
+		// current one (same reasoning as the cosine loop below)
+#define PGEMB_L2_BLOCK(QQ, YA, YB)                                                                      \
+	{                                                                                                   \
+		const float d00 = __fsub_rn(QQ.x, YA.x), d10 = __fsub_rn(QQ.z, YB.x);                           \
+		const float d01 = __fsub_rn(QQ.y, YA.y), d11 = __fsub_rn(QQ.w, YB.y);                           \
+		S0 = __fadd_rn(S0, __fadd_rn(__fmul_rn(d00, d00), __fmul_rn(d10, d10)));                        \
+		S1 = __fadd_rn(S1, __fadd_rn(__fmul_rn(d01, d01), __fmul_rn(d11, d11)));                        \
+	}
+		int		  b = 0;
+		const int npair = nb >> 1;
+		if (npair > 0)
+		{
+			float4 qa = *reinterpret_cast<const float4 *>(qts), qb = *reinterpret_cast<const float4 *>(qts + 4);
+			float2 a0 = *reinterpret_cast<const float2 *>(vp), a1 = *reinterpret_cast<const float2 *>(vp + 8);
+			float2 b0 = *reinterpret_cast<const float2 *>(vp + 16), b1 = *reinterpret_cast<const float2 *>(vp + 24);
+#pragma unroll 1
+			for (int it = 1; it < npair; it++)
+			{
+				const float *vn_ = vp + 32 * it;
+				const float4 nqa = *reinterpret_cast<const float4 *>(qts + 8 * it);
+				const float2 na0 = *reinterpret_cast<const float2 *>(vn_);
+				const float2 na1 = *reinterpret_cast<const float2 *>(vn_ + 8);
+				PGEMB_L2_BLOCK(qa, a0, a1)
+				const float4 nqb = *reinterpret_cast<const float4 *>(qts + 8 * it + 4);
+				const float2 nb0 = *reinterpret_cast<const float2 *>(vn_ + 16);
+				const float2 nb1 = *reinterpret_cast<const float2 *>(vn_ + 24);
+				PGEMB_L2_BLOCK(qb, b0, b1)
+				qa = nqa; qb = nqb; a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+			}
+			PGEMB_L2_BLOCK(qa, a0, a1)
+			PGEMB_L2_BLOCK(qb, b0, b1)
+			b = npair << 1;
+		}
+		for (; b < nb; b++)
 		{
 			const float4 qq = *reinterpret_cast<const float4 *>(qts + 4 * b);
 			const float2 ya = *reinterpret_cast<const float2 *>(vp + 16 * b);
 			const float2 yb = *reinterpret_cast<const float2 *>(vp + 16 * b + 8);
-			const float	 d00 = __fsub_rn(qq.x, ya.x), d10 = __fsub_rn(qq.z, yb.x);
-			const float	 d01 = __fsub_rn(qq.y, ya.y), d11 = __fsub_rn(qq.w, yb.y);
-			S0 = __fadd_rn(S0, __fadd_rn(__fmul_rn(d00, d00), __fmul_rn(d10, d10)));
-			S1 = __fadd_rn(S1, __fadd_rn(__fmul_rn(d01, d01), __fmul_rn(d11, d11)));
+			PGEMB_L2_BLOCK(qq, ya, yb)
 		}
+#undef PGEMB_L2_BLOCK
 		float full[8];
 #pragma unroll
 		for (int l = 0; l < 8; l++) full[l] = __shfl_sync(kFull, (l & 1) ? S1 : S0, l >> 1, 4);
