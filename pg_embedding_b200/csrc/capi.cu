@@ -453,7 +453,7 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	const uint32_t pool_bytes = align_up((uint32_t) sizeof(RingPool), 128);
 	// ---- how many slots (warps) and rings per CTA (= per SM) ----
 	// A slot holds a ring for about `duty` of a hop; throughput ~ min(W / T_hop, R / (duty * T_hop)).
-	const double duty = env_int("PGEMB_RING_DUTY_PCT", 55) / 100.0;
+	const double duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
 	uint32_t	 bestW = 0, bestR = 0;
 	double		 bestv = -1.0;
 	for (uint32_t W = 1; W <= 32; W++)

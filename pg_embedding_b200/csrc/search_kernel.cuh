@@ -208,7 +208,7 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 		const float f2 = __shfl_sync(kFull, s, 2, 4), f3 = __shfl_sync(kFull, s, 3, 4);
 		float		res = hsum4(f0, f1, f2, f3);
 		for (int e = main_n; e < dim; e++) res = __fadd_rn(res, term4<TERM>(q_tail[e - main_n], rowp[e]));
-		if (METRIC == M_COS) return cosine_finish(res, qn, vn);
+		if (METRIC == M_COS) return (sub == 0) ? cosine_finish(res, qn, vn) : res;
 		return res;
 	}
 }
@@ -626,25 +626,26 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			// The whole link row is obtained in one go (count and ids together: a dependent second DRAM
 			// round trip for the ids would sit on the critical path of every hop) -- from the prefetch
 			// buffer when the guess was right, else from global memory.
-			const uint32_t *L = p.links + (size_t) c * p.link_stride;
-			uint32_t		w0 = 0, w1 = 0, w2 = 0;
-			const bool		hit = pf_inflight && pf_id == c;
+			const bool hit = pf_inflight && pf_id == c;
 			if (hit)
 			{
 				mbar_wait(pf_bar, pf_parity);
 				pf_parity ^= 1u;
 				pf_inflight = false;
-				if (lane < p.link_stride) w0 = pf_links[lane];
-				if (lane + 32 < p.link_stride) w1 = pf_links[lane + 32];
-				if (lane + 64 < p.link_stride) w2 = pf_links[lane + 64];
 			}
 			else
 			{
-				if (lane < p.link_stride) w0 = L[lane];
-				if (lane + 32 < p.link_stride) w1 = L[lane + 32];
-				if (lane + 64 < p.link_stride) w2 = L[lane + 64];
+				if (pf_inflight)
+				{
+					mbar_wait(pf_bar, pf_parity);  // wrong guess still in flight into the buffer we are about to fill
+					pf_parity ^= 1u;
+					pf_inflight = false;
+				}
+				const uint32_t *L = p.links + (size_t) c * p.link_stride;
+				for (uint32_t i = lane; i < p.link_stride; i += 32) pf_links[i] = L[i];
+				__syncwarp();
 			}
-			uint32_t cnt = __shfl_sync(kFull, w0, 0);
+			uint32_t cnt = pf_links[0];
 			if (cnt > p.maxM)
 			{
 				cnt = p.maxM;
@@ -672,17 +673,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				// list position k = base + lane lives in word k + 1
 				const uint32_t k = base + lane;
 				bool		   valid = k < cnt;
-				uint32_t	   id;
-				if (base < 64)
-				{
-					// word k+1 is held by lane (k+1)&31 in register (k+1)>>5
-					const uint32_t src = (lane + 1) & 31;
-					const uint32_t a = __shfl_sync(kFull, base == 0 ? w0 : w1, src);
-					const uint32_t b = __shfl_sync(kFull, base == 0 ? w1 : w2, src);
-					id = (lane == 31) ? b : a;
-				}
-				else
-					id = valid ? (hit ? pf_links[1 + k] : L[1 + k]) : 0u;
+				uint32_t	   id = valid ? pf_links[1 + k] : 0u;
 				if (!valid) id = 0u;
 				if (valid && id >= p.n_items)
 				{
