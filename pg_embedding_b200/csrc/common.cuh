@@ -59,10 +59,6 @@ __device__ __forceinline__ void fence_mbar_init()
 {
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async()
-{
-	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -104,33 +100,9 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 		: "memory");
 }
 
-// Ampere-style 16-byte async copy global -> shared (SASS LDGSTS), L1 bypassed (.cg), with an L2 policy.
-// Used for the chunked row gather: one warp instruction moves 32 x 16 B with per-lane addresses and no
-// uniform-register traffic (a bulk-TMA copy costs ~75 issue cycles each on this path, see profiles/).
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem, uint64_t policy)
-{
-	// NOTE: no `.L2::cache_hint` here.  With the hint, ptxas 12.9 emits `LDGSTS [R+UR0], desc[UR1]` whose
-	// uniform registers are never written, and the instruction traps ("illegal instruction", pinpointed with
-	// compute-sanitizer) on sm_100a.  The bulk-TMA path (tma_load_1d) takes the same policy without trouble.
-	(void) policy;
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void cp_async_wait_dyn(uint32_t pending)
-{
-	switch (pending)
-	{
-		case 0: cp_async_wait<0>(); break;
-		case 1: cp_async_wait<1>(); break;
-		case 2: cp_async_wait<2>(); break;
-		case 3: cp_async_wait<3>(); break;
-		case 4: cp_async_wait<4>(); break;
-		case 5: cp_async_wait<5>(); break;
-		case 6: cp_async_wait<6>(); break;
-		default: cp_async_wait<7>(); break;
-	}
-}
+// NOTE (kept from the LDGSTS experiments, profiles/README.md): `cp.async.cg.shared.global.L2::cache_hint` miscompiles with
+// ptxas 12.9 for sm_100a -- it emits `LDGSTS [R+UR0], desc[UR1]` whose uniform registers are never written and the
+// instruction traps ("illegal instruction", pinpointed with compute-sanitizer).  Bulk TMA takes the same policy fine.
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t lanemask_lt()

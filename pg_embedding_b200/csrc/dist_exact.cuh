@@ -191,78 +191,7 @@ __device__ __forceinline__ float l2_exact(const float *__restrict__ x, const flo
 	return __fsqrt_rn(res);
 }
 
-// ---- streaming form: ONE thread per row, the row arriving in chunks ------------------------------
-// The thread owns all LANES accumulator chains of its row (4 or 8 independent FADD chains -> ILP), reads
-// 16 bytes of the row and of the query per LDS.128, and carries the chains across chunks.  Chunk starts
-// are multiples of 32 floats, so 16-float (L2) / 4-float blocks never straddle a chunk.
-template <int METRIC> struct RowAcc { float s[MetricLanes<METRIC>::LANES]; };
-
-template <int METRIC>
-__device__ __forceinline__ void acc_init(RowAcc<METRIC> &a)
-{
-#pragma unroll
-	for (int j = 0; j < MetricLanes<METRIC>::LANES; j++) a.s[j] = 0.0f;
-}
-
-// q, v: 16-B aligned, first float of the chunk; nmain: floats of this chunk inside the vector loop
-// (multiple of 16 for L2, of 4 otherwise; may be 0).
-template <int METRIC>
-__device__ __forceinline__ void acc_chunk(RowAcc<METRIC> &a, const float *__restrict__ q, const float *__restrict__ v, int nmain)
-{
-	if (METRIC == M_L2)
-	{
-#pragma unroll 2
-		for (int i = 0; i < nmain; i += 16)
-		{
-			const float4 x0 = *reinterpret_cast<const float4 *>(q + i), y0 = *reinterpret_cast<const float4 *>(v + i);
-			const float4 x1 = *reinterpret_cast<const float4 *>(q + i + 4), y1 = *reinterpret_cast<const float4 *>(v + i + 4);
-			const float4 x2 = *reinterpret_cast<const float4 *>(q + i + 8), y2 = *reinterpret_cast<const float4 *>(v + i + 8);
-			const float4 x3 = *reinterpret_cast<const float4 *>(q + i + 12), y3 = *reinterpret_cast<const float4 *>(v + i + 12);
-#define PGEMB_L2_STEP(J, XA, YA, XB, YB)                                                          \
-	{                                                                                             \
-		const float d0 = __fsub_rn(XA, YA), d1 = __fsub_rn(XB, YB);                               \
-		a.s[J] = __fadd_rn(a.s[J], __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));              \
-	}
-			PGEMB_L2_STEP(0, x0.x, y0.x, x2.x, y2.x) PGEMB_L2_STEP(1, x0.y, y0.y, x2.y, y2.y)
-			PGEMB_L2_STEP(2, x0.z, y0.z, x2.z, y2.z) PGEMB_L2_STEP(3, x0.w, y0.w, x2.w, y2.w)
-			PGEMB_L2_STEP(4, x1.x, y1.x, x3.x, y3.x) PGEMB_L2_STEP(5, x1.y, y1.y, x3.y, y3.y)
-			PGEMB_L2_STEP(6, x1.z, y1.z, x3.z, y3.z) PGEMB_L2_STEP(7, x1.w, y1.w, x3.w, y3.w)
-#undef PGEMB_L2_STEP
-		}
-	}
-	else
-	{
-		constexpr int TERM = (METRIC == M_COS) ? 0 : 1;
-#pragma unroll 4
-		for (int i = 0; i < nmain; i += 4)
-		{
-			const float4 x = *reinterpret_cast<const float4 *>(q + i), y = *reinterpret_cast<const float4 *>(v + i);
-			a.s[0] = __fadd_rn(a.s[0], term4<TERM>(x.x, y.x));
-			a.s[1] = __fadd_rn(a.s[1], term4<TERM>(x.y, y.y));
-			a.s[2] = __fadd_rn(a.s[2], term4<TERM>(x.z, y.z));
-			a.s[3] = __fadd_rn(a.s[3], term4<TERM>(x.w, y.w));
-		}
-	}
-}
-
-// q_tail / v_tail point at element main_n of the query / row; r = dim - main_n leftover floats.
-template <int METRIC>
-__device__ __forceinline__ float acc_finish(const RowAcc<METRIC> &a, const float *__restrict__ q_tail,
-											const float *__restrict__ v_tail, int r, float qn, float vn)
-{
-	if (METRIC == M_L2)
-	{
-		float res = hsum4(__fadd_rn(a.s[0], a.s[4]), __fadd_rn(a.s[1], a.s[5]), __fadd_rn(a.s[2], a.s[6]), __fadd_rn(a.s[3], a.s[7]));
-		res = l2_tail_exact(res, q_tail, v_tail, r);
-		return __fsqrt_rn(res);
-	}
-	constexpr int TERM = (METRIC == M_COS) ? 0 : 1;
-	float		  res = hsum4(a.s[0], a.s[1], a.s[2], a.s[3]);
-	for (int k = 0; k < r; k++) res = __fadd_rn(res, term4<TERM>(q_tail[k], v_tail[k]));
-	if (METRIC == M_COS) return cosine_finish(res, qn, vn);
-	return res;
-}
-
+// length of the vectorised main loop of the reference: dim rounded down to its SIMD block (16 floats for the AVX2 L2 loop, 4 otherwise)
 template <int METRIC>
 __device__ __forceinline__ int main_len(int dim) { return (METRIC == M_L2) ? (dim & ~15) : (dim & ~3); }
 

@@ -10,7 +10,7 @@
 //   expand   its link list [count, ids...] (:76-77) -- normally already in shared memory, prefetched by
 //            bulk TMA during the previous hop's queue update -- and test-and-set of the visited set (:92-93)
 //   gather   K1: the unvisited neighbours' vectors are pulled HBM -> shared memory, one 1-D bulk TMA copy
-//            per row (cp.async.bulk + mbarrier, L2 evict-first, S-stage ring of 8 rows), and scored with
+//            per row (cp.async.bulk + mbarrier, L2 evict-first, a ring of 8 rows from the CTA's pool), scored with
 //            the reference's exact fp32 summation order, 4 lanes per row
 //   update   K2: warp-level top-ef queue update that is EQUIVALENT to the reference's sequential
 //            push/pop loop (:99-108), exact distance ties included -- see "sequential equivalence".
@@ -29,8 +29,10 @@
 // Visited set: an open-addressing table (atomicCAS at L2, kept resident with an L2 persistence window)
 // that migrates to the exact N-bit bitmap before it passes half full; both are reset in O(visited).
 //
-// One warp = one slot: no CTA-wide barriers anywhere; ~31 KB of shared memory per slot at dim 768, so 7
-// slots share an SM and overlap each other's dependent-latency phases (pop -> links -> visited -> rows).
+// One warp = one query slot; a CTA (one per SM) holds W slots that share a pool of R row rings (RingPool):
+// a slot needs a ring only while it gathers+scores, so 12 slots time-share 6 rings in the 227 KB of an SM
+// at dim 768 and overlap each other's dependent-latency phases (pop -> links -> visited -> rows).
+// The only CTA-wide barrier is the one after the pool is initialised.
 #pragma once
 #include "common.cuh"
 #include "dist_exact.cuh"
