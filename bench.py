@@ -130,6 +130,24 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_bytes(batch):
+    """DRAM read+write bytes of one traversal launch from the committed ncu --set full capture (profiles/), valid for
+    the default 32768-query launch of this workload only; None otherwise."""
+    p = os.path.join(ROOT, "profiles", "r1_search_kernel_cosine768_metrics.csv")
+    if batch != 32768 or not os.path.isfile(p):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = 0.0
+    try:
+        for line in open(p):
+            f = line.strip().split(",")
+            if len(f) >= 4 and f[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[-1]) * scale.get(f[-2], 1.0)
+    except Exception:
+        return None
+    return int(tot) if tot > 0 else None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -232,7 +250,7 @@ def main():
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "search_kernel<cosine> (K3: TMA row gather + exact distance + queue update)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": ncu_traffic_bytes(B) if n == 1_000_000 else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kms, 3),
                 "per_query": {"dist_evals": float(st[:, 0].mean()), "expansions": float(st[:, 1].mean()),
                               "bytes": float(alg_bytes / B)}}

@@ -194,6 +194,13 @@ pgemb_status pgemb_insert_batch(pgemb_index *idx, size_t n, const coord_t *coord
  * seconds_out (optional) receives the wall time including the final synchronisation. */
 pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t n, size_t batch_max, double *seconds_out);
 
+/* Exact AND parallel build: same preconditions as pgemb_build_bulk, but the result is bit-identical to n
+ * sequential hnsw_add_point calls (embedding.c:606-701).  Speculative batches of searches against the graph as of
+ * the batch start; the longest prefix whose searches provably equal the sequential ones (no expanded node's link
+ * list is modified by an earlier insert of the batch) is connected, the rest is retried.  batch_max <= 4096.
+ * stats_out (optional, 3 x u64): batches, searches run, inserts. */
+pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t n, size_t batch_max, double *seconds_out, uint64_t *stats_out);
+
 /* Shard top-k merge: for each of nq queries merge n_shards lists of
  * (dist,label) ascending lists of length k (n valid per list in n_in) into the k best by
  * (dist,label) lexicographic order (hnswalg.cpp:236-247 pair order). Device pointers. */

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "pgemb_index_set_links", "pgemb_index_get_labels", "pgemb_index_set_labels",
     "pgemb_index_truncate", "pgemb_search_batch", "pgemb_search_batch_device",
     "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather",
-    "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_build_bulk",
+    "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_build_bulk", "pgemb_build_exact",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     lib.pgemb_insert_batch.argtypes = [vp, sz, f32p, u64p]
     lib.pgemb_merge_topk_device.argtypes = [sz, sz, sz, vp, vp, vp, vp, vp, vp, vp]
     lib.pgemb_build_bulk.argtypes = [vp, sz, sz, sz, C.POINTER(C.c_double)]
+    lib.pgemb_build_exact.argtypes = [vp, sz, sz, sz, C.POINTER(C.c_double), u64p]
     lib.hnsw_search.argtypes = [mp, f32p, C.POINTER(sz), C.POINTER(u64p)]
     lib.hnsw_search.restype = C.c_bool
     lib.hnsw_bind_point.argtypes = [mp, f32p, C.c_uint32]

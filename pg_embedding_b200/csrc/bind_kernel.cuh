@@ -44,6 +44,13 @@ struct BindWorkspace
 	uint64_t *d_pairs_sorted = nullptr;
 	void	 *d_cub = nullptr;
 	size_t	  cub_bytes = 0;
+	// exact parallel build (speculative batches)
+	static constexpr uint32_t kExpCap = 1024;
+	uint32_t *d_exp = nullptr;		 // [points][kExpCap] expanded nodes of each speculative search
+	uint32_t *d_exp_n = nullptr;	 // [points]
+	uint32_t *d_stamp = nullptr;	 // [capacity] see validate_kernel
+	uint32_t *d_first = nullptr;	 // first conflicting batch index
+	size_t	  stamp_cap = 0;
 };
 
 inline void bind_ws_free(BindWorkspace &w)
@@ -55,6 +62,10 @@ inline void bind_ws_free(BindWorkspace &w)
 	cudaFree(w.d_pairs);
 	cudaFree(w.d_pairs_sorted);
 	cudaFree(w.d_cub);
+	cudaFree(w.d_exp);
+	cudaFree(w.d_exp_n);
+	cudaFree(w.d_stamp);
+	cudaFree(w.d_first);
 	w = BindWorkspace();
 }
 
@@ -263,6 +274,58 @@ __global__ void __launch_bounds__(kBindThreads) backlink_kernel(GraphView g, con
 		write_list_desc(L, kept, nk);  // hnswalg.cpp:213-219 (slots beyond the new count keep stale ids, as in the reference)
 		__syncthreads();
 	}
+}
+
+// ---- exact parallel build: validation of speculative searches -------------------------------------------
+// A batch of inserts i..i+B-1 is searched in parallel against the graph G0 as it was before the batch.
+// Insert k's search is exactly the search the sequential algorithm would have run iff none of the nodes it
+// EXPANDED (whose link lists it read) is modified by an earlier insert of the batch: the traversal is a
+// function of the lists of the expanded nodes only.  Insert j modifies the lists of its selected neighbours
+// (back-links, hnswalg.cpp:182-222); its own node is not in G0 and is reachable only through those lists.
+// stamp[t] = smallest id of a batch insert that modifies node t (0xffffffff = none);
+// insert k conflicts iff some expanded node e has stamp[e] < id_k.
+
+__global__ void stamp_targets_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_t *__restrict__ stamp)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pairs) return;
+	const uint64_t pr = pairs[i];
+	if (pr == ~0ull) return;
+	atomicMin(&stamp[(uint32_t) (pr >> 32)], (uint32_t) pr);
+}
+
+__global__ void clear_stamps_kernel(const uint64_t *__restrict__ pairs, uint32_t n_pairs, uint32_t *__restrict__ stamp)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_pairs) return;
+	const uint64_t pr = pairs[i];
+	if (pr == ~0ull) return;
+	stamp[(uint32_t) (pr >> 32)] = 0xffffffffu;
+}
+
+// one warp per batch insert; first_conflict = smallest batch index whose speculative search is invalid
+__global__ void validate_kernel(const uint32_t *__restrict__ exp_ids, const uint32_t *__restrict__ exp_n, uint32_t exp_cap,
+								const uint32_t *__restrict__ new_ids, uint32_t B, const uint32_t *__restrict__ stamp,
+								uint32_t *__restrict__ first_conflict)
+{
+	const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (k >= B) return;
+	const uint32_t id_k = new_ids[k];
+	const uint32_t cnt = exp_n[k];
+	bool		   bad = cnt > exp_cap;	 // incomplete list: cannot be validated
+	const uint32_t m = cnt < exp_cap ? cnt : exp_cap;
+	for (uint32_t i = lane; i < m; i += 32) bad |= stamp[exp_ids[(size_t) k * exp_cap + i]] < id_k;
+	if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMin(first_conflict, k);
+}
+
+// undo the own-list writes of the rejected tail of a batch (their slots must be blank again, hnswalg.cpp:170-177)
+__global__ void zero_links_kernel(uint32_t *__restrict__ links, uint32_t link_stride, const uint32_t *__restrict__ ids, uint32_t n)
+{
+	const uint32_t w = blockIdx.x;
+	if (w >= n) return;
+	uint32_t *L = links + (size_t) ids[w] * link_stride;
+	for (uint32_t i = threadIdx.x; i < link_stride; i += blockDim.x) L[i] = 0u;
 }
 
 }  // namespace pgemb

@@ -560,7 +560,8 @@ static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t 
 // Launch the traversal for nq queries.  All pointers are device pointers.
 pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, uint32_t q_stride, const uint32_t *d_query_ids,
 						   uint32_t n_items, size_t ef, int raw_mode, label_t *d_labels_out, dist_t *d_dists_out, idx_t *d_ids_out,
-						   int32_t *d_n_out, uint32_t *d_stats_out, cudaStream_t s, bool time_it, const unsigned int *d_avail = nullptr)
+						   int32_t *d_n_out, uint32_t *d_stats_out, cudaStream_t s, bool time_it, const unsigned int *d_avail = nullptr, uint32_t *d_exp = nullptr,
+						   uint32_t exp_cap = 0, uint32_t *d_exp_n = nullptr)
 {
 	if (!idx || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
 	if (ef < 1 || ef > (1u << 20)) return fail(PGEMB_ERR_ARG, "ef out of range");
@@ -619,6 +620,9 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	}
 	p.counter = idx->d_counter;
 	p.avail = d_avail;
+	p.exp_out = d_exp;
+	p.exp_cap = exp_cap;
+	p.exp_n_out = d_exp_n;
 	p.error_flag = idx->d_error;
 	p.rings = cfg.rings;
 	p.ring_bytes = cfg.ring_bytes;
@@ -1088,6 +1092,141 @@ extern "C" pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t 
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 	if (seconds_out) *seconds_out = ms * 1e-3;
+	return st;
+}
+
+// Exact AND parallel build: the result is bit-identical to n sequential hnsw_add_point calls (embedding.c:606-701).
+// Speculative batches: all inserts of a batch search the graph as it was before the batch (one launch); the
+// longest prefix whose searches provably equal the sequential ones (validate_kernel) is connected -- own lists
+// + back-links per target in source-id order, which is the sequential order -- and the batch restarts at the
+// first conflicting insert.  The first insert of a batch is always valid, so the build always progresses.
+extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t n, size_t batch_max, double *seconds_out,
+										  uint64_t *stats_out /* [3]: batches, searches run, inserts */)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	if (first + n > idx->n) return fail(PGEMB_ERR_ARG, "build: nodes not stored");
+	if (batch_max < 1) batch_max = 1;
+	if (batch_max > 4096) batch_max = 4096;
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t efc = idx->meta.efConstruction;
+	if (efc < 1) return fail(PGEMB_ERR_ARG, "efConstruction must be >= 1");
+	cudaStream_t s = idx->stream;
+	st = ensure_bind_ws(idx, batch_max, efc);
+	if (st) return st;
+	BindWorkspace &w = idx->bind_ws;
+	const uint32_t ecap = BindWorkspace::kExpCap;
+	if (!w.d_exp || w.stamp_cap < idx->capacity)
+	{
+		cudaFree(w.d_exp); cudaFree(w.d_exp_n); cudaFree(w.d_stamp); cudaFree(w.d_first);
+		w.d_exp = w.d_exp_n = w.d_stamp = w.d_first = nullptr;
+		CU_TRY(cudaMalloc((void **) &w.d_exp, w.cap_points * (size_t) ecap * 4));
+		CU_TRY(cudaMalloc((void **) &w.d_exp_n, w.cap_points * 4));
+		CU_TRY(cudaMalloc((void **) &w.d_stamp, idx->capacity * 4));
+		CU_TRY(cudaMalloc((void **) &w.d_first, 4));
+		CU_TRY(cudaMemset(w.d_stamp, 0xff, idx->capacity * 4));
+		w.stamp_cap = idx->capacity;
+	}
+	const size_t M = idx->meta.M ? idx->meta.M : 1;
+	cudaEvent_t	 e0, e1;
+	CU_TRY(cudaEventCreate(&e0));
+	CU_TRY(cudaEventCreate(&e1));
+	CU_TRY(cudaEventRecord(e0, s));
+	size_t	 pos = first;
+	const size_t end = first + n;
+	size_t	 B = 1;
+	uint64_t batches = 0, searches = 0;
+	while (pos < end)
+	{
+		if (pos == 0)
+		{
+			pos = 1;  // node 0 has nothing to connect to (hnswalg.cpp:227-228)
+			continue;
+		}
+		if (B > batch_max) B = batch_max;
+		if (B > end - pos) B = end - pos;
+		iota_kernel<<<(uint32_t) ((B + 255) / 256), 256, 0, s>>>(w.d_qids, (uint32_t) pos, (uint32_t) B);
+		g_launches++;
+		st = launch_search(idx, B, nullptr, 0, w.d_qids, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n, nullptr, s,
+						   false, nullptr, w.d_exp, ecap, w.d_exp_n);
+		if (st) return st;
+		batches++;
+		searches += B;
+		size_t acc = B;
+		GraphView g = graph_view(idx);
+		const int metric = (int) idx->meta.dist_func;
+		const size_t sel_smem = efc * 8 + M * 8 + efc * 4;
+#define LAUNCH_SELECT_X(MM)                                                                                                     \
+	do {                                                                                                                         \
+		if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
+		select_kernel<MM><<<(uint32_t) B, kBindThreads, sel_smem, s>>>(g, w.d_qids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) efc, w.d_pairs); \
+	} while (0)
+		if (metric == DIST_L2) LAUNCH_SELECT_X(M_L2);
+		else if (metric == DIST_COSINE) LAUNCH_SELECT_X(M_COS);
+		else LAUNCH_SELECT_X(M_MAN);
+#undef LAUNCH_SELECT_X
+		g_launches++;
+		CU_TRY(cudaGetLastError());
+		const uint32_t n_pairs_all = (uint32_t) (B * M);
+		if (B > 1)
+		{
+			uint32_t hfirst = (uint32_t) B;
+			CU_TRY(cudaMemcpyAsync(w.d_first, &hfirst, 4, cudaMemcpyHostToDevice, s));
+			stamp_targets_kernel<<<(n_pairs_all + 255) / 256, 256, 0, s>>>(w.d_pairs, n_pairs_all, w.d_stamp);
+			validate_kernel<<<(uint32_t) ((B * 32 + 255) / 256), 256, 0, s>>>(w.d_exp, w.d_exp_n, ecap, w.d_qids, (uint32_t) B, w.d_stamp, w.d_first);
+			clear_stamps_kernel<<<(n_pairs_all + 255) / 256, 256, 0, s>>>(w.d_pairs, n_pairs_all, w.d_stamp);
+			g_launches += 3;
+			CU_TRY(cudaMemcpyAsync(&hfirst, w.d_first, 4, cudaMemcpyDeviceToHost, s));
+			CU_TRY(cudaStreamSynchronize(s));
+			acc = hfirst < B ? hfirst : B;
+			if (acc < 1) acc = 1;
+			if (acc < B)
+			{
+				zero_links_kernel<<<(uint32_t) (B - acc), 64, 0, s>>>(idx->d_links, idx->link_stride, w.d_qids + acc, (uint32_t) (B - acc));
+				g_launches++;
+			}
+		}
+		// back-links of the accepted prefix, per target in source order
+		const uint32_t	n_pairs = (uint32_t) (acc * M);
+		const uint64_t *sorted = w.d_pairs;
+		if (acc > 1)
+		{
+			size_t bytes = w.cub_bytes;
+			CU_TRY(cub::DeviceRadixSort::SortKeys(w.d_cub, bytes, w.d_pairs, w.d_pairs_sorted, (int) n_pairs, 0, 64, s));
+			g_launches++;
+			sorted = w.d_pairs_sorted;
+		}
+		const size_t maxM1 = idx->meta.maxM + 1;
+		const size_t bl_smem = maxM1 * 8 * 2 + (idx->meta.maxM ? idx->meta.maxM : 1) * 8 + maxM1 * 4;
+#define LAUNCH_BACK_X(MM)                                                                                                        \
+	do {                                                                                                                         \
+		if (bl_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(backlink_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bl_smem)); \
+		backlink_kernel<MM><<<n_pairs, kBindThreads, bl_smem, s>>>(g, sorted, n_pairs);                                          \
+	} while (0)
+		if (metric == DIST_L2) LAUNCH_BACK_X(M_L2);
+		else if (metric == DIST_COSINE) LAUNCH_BACK_X(M_COS);
+		else LAUNCH_BACK_X(M_MAN);
+#undef LAUNCH_BACK_X
+		g_launches++;
+		CU_TRY(cudaGetLastError());
+		pos += acc;
+		// Speculative searches are nearly free (one launch, one warp each, latency-bound), so the batch only
+		// shrinks while the graph is tiny (every search expands most of it and everything conflicts).
+		B = (acc == B) ? B * 2 : (acc * 8 > batch_max ? batch_max : acc * 8 + 1);
+	}
+	CU_TRY(cudaEventRecord(e1, s));
+	st = check_device_error(idx, s);
+	float ms = 0.f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	if (seconds_out) *seconds_out = ms * 1e-3;
+	if (stats_out)
+	{
+		stats_out[0] = batches;
+		stats_out[1] = searches;
+		stats_out[2] = n;
+	}
 	return st;
 }
 

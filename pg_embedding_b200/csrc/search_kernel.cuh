@@ -58,6 +58,9 @@ struct SearchParams
 	uint32_t *ids_out;			 // [nq][ef]
 	int32_t	 *n_out;			 // [nq]
 	uint32_t *stats_out;		 // [nq][4]: distance evals, expansions, link words, overflow high-water
+	uint32_t *exp_out;			 // [nq][exp_cap] ids of the expanded nodes in order, or NULL (exact parallel build)
+	uint32_t  exp_cap;
+	uint32_t *exp_n_out;		 // [nq] number of expansions (may exceed exp_cap: the list is then incomplete)
 	// per-slot workspace
 	uint32_t	 *visited;		 // [slots][vis_words]   exact bitmap (fallback / small indexes)
 	uint32_t	 *vlog;			 // [slots][vlog_cap]    table positions (hash mode) or ids (bitmap mode) to reset
@@ -653,6 +656,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				cnt = p.maxM;
 				*p.error_flag = 1;
 			}
+			if (p.exp_out && lane == 0 && st_hops < p.exp_cap) p.exp_out[(size_t) qi * p.exp_cap + st_hops] = c;
 			st_hops += 1;
 			st_words += 1 + cnt;
 			n = 0;
@@ -778,6 +782,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 		if (lane == 0)
 		{
 			p.n_out[qi] = (int32_t) count;
+			if (p.exp_n_out) p.exp_n_out[qi] = st_hops;
 			if (p.stats_out)
 			{
 				p.stats_out[(size_t) qi * 4 + 0] = st_dist;

@@ -170,6 +170,14 @@ class HnswIndex:
         check(self.lib.pgemb_build_bulk(self.dev, int(first), int(n), int(batch_max), C.byref(secs)))
         return secs.value
 
+    def build_exact(self, first: int, n: int, batch_max: int = 256):
+        """Exact parallel build of already appended nodes: bit-identical to sequential inserts.
+        Returns (device seconds, dict(batches, searches, inserts))."""
+        secs = C.c_double(0)
+        st = (C.c_uint64 * 3)()
+        check(self.lib.pgemb_build_exact(self.dev, int(first), int(n), int(batch_max), C.byref(secs), st))
+        return secs.value, {"batches": int(st[0]), "searches": int(st[1]), "inserts": int(st[2])}
+
     def load_records(self, records: np.ndarray) -> None:
         """Ingest nodes in the reference's on-page record layout (embedding.c:224-228)."""
         r = np.ascontiguousarray(records, dtype=np.uint8)

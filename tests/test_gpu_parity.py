@@ -423,3 +423,37 @@ def test_config2_full_size_properties(pg, oracle_mod):
     assert out["labels"][:96].tobytes() == want["labels"].tobytes()
     assert (out["stats"][:96, :3].astype(np.uint64) == want["counters"]).all()
     idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# exact parallel build: speculative batches must reproduce the sequential reference build bit for bit
+# ---------------------------------------------------------------------------------------------------
+EXACT_CFGS = [
+    (3, 3, 16, 400, dict(levels=3), "l2"),            # ties + duplicates: conflicts everywhere
+    (16, 8, 40, 3000, dict(), "cosine"),
+    (32, 8, 64, 6000, dict(), "l2"),
+    (128, 16, 100, 4000, dict(), "manhattan"),
+    (768, 32, 200, 1500, dict(), "cosine"),
+]
+
+
+@pytest.mark.parametrize("cfg", EXACT_CFGS, ids=[f"d{c[0]}m{c[1]}n{c[3]}{c[5]}" for c in EXACT_CFGS])
+def test_exact_parallel_build_equals_sequential(pg, oracle_mod, cfg):
+    dims, m, efc, n, kw, metric = cfg
+    rng = np.random.default_rng(4242 + dims)
+    x = _data(rng, n, dims, **kw)
+    if metric == "cosine":
+        x = x + 1.0
+    which = "ref" if oracle_mod.available("ref") else "port"
+    orc = oracle_mod.FlatIndex(which, dims, m, efc, 64, metric, capacity=n)
+    orc.build(x)
+    want = orc.links()
+    for bmax in (64, 1024):
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+        idx.append(x)
+        secs, st = idx.build_exact(0, n, bmax)
+        got = idx.links()
+        bad = np.flatnonzero((got != want).any(1))
+        assert bad.size == 0, f"{metric} bmax={bmax}: link lists differ at nodes {bad[:10]}; stats {st}"
+        assert st["searches"] >= n - 1 and st["batches"] <= n
+        idx.close()
