@@ -457,3 +457,34 @@ def test_exact_parallel_build_equals_sequential(pg, oracle_mod, cfg):
         assert bad.size == 0, f"{metric} bmax={bmax}: link lists differ at nodes {bad[:10]}; stats {st}"
         assert st["searches"] >= n - 1 and st["batches"] <= n
         idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge parameters: dims=1, m=0/1, ef far above N and above 1000 (queue buffers scale), odd dims
+# ---------------------------------------------------------------------------------------------------
+EDGE_CFGS = [
+    (1, 1, 4, 200, "l2", (1, 7, 1000)),
+    (5, 0, 8, 50, "manhattan", (1, 64)),            # m=0: maxM=0, no links at all (reloption minimum, embedding.c:132)
+    (7, 2, 300, 500, "cosine", (3, 600)),           # efconstruction > N for most of the build
+    (2000, 2, 8, 60, "l2", (16,)),                  # largest dims a page can hold (embedding.c:229-231)
+    (1999, 3, 8, 60, "cosine", (16,)),
+]
+
+
+@pytest.mark.parametrize("cfg", EDGE_CFGS, ids=[f"d{c[0]}m{c[1]}n{c[3]}{c[4]}" for c in EDGE_CFGS])
+def test_edge_parameters(pg, oracle_mod, cfg):
+    dims, m, efc, n, metric, efs = cfg
+    rng = np.random.default_rng(dims * 31 + m)
+    x = rng.standard_normal((n, dims)).astype(np.float32) + (1.5 if metric == "cosine" else 0.0)
+    q = rng.standard_normal((16, dims)).astype(np.float32) + (1.5 if metric == "cosine" else 0.0)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+    orc.build(x)
+    idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+    idx.insert_many(x)
+    assert idx.links().tobytes() == orc.links().tobytes()
+    for ef in efs:
+        out = idx.search_batch(q, ef)
+        want = orc.search_many(q, ef)
+        assert out["n"].tolist() == want["n"].tolist()
+        assert out["labels"].tobytes() == want["labels"].tobytes()
+    idx.close()
