@@ -682,7 +682,8 @@ static pgemb_status check_device_error(pgemb_index *idx, cudaStream_t s)
 	{
 		CU_TRY(cudaMemsetAsync(idx->d_error, 0, sizeof(int), s));
 		return fail(PGEMB_ERR_STATE, err == 1 ? "corrupt graph: link id / count out of range"
-											  : (err == 2 ? "tie-overflow buffer exceeded" : "bind failed (reference would throw)"));
+											  : (err == 2 ? "tie-overflow buffer exceeded"
+														  : (err == 4 ? "query batch never arrived on the device" : "bind failed (reference would throw)")));
 	}
 	return PGEMB_OK;
 }
@@ -743,9 +744,16 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 		const size_t q0 = c * per;
 		if (q0 >= nq) break;
 		const size_t qn_ = (q0 + per <= nq) ? per : (nq - q0);
-		CU_TRY(cudaMemcpyAsync(d_q + q0 * dim, queries + q0 * dim, qn_ * dim * sizeof(float), cudaMemcpyHostToDevice, idx->s_in));
+		cudaError_t ce = cudaMemcpyAsync(d_q + q0 * dim, queries + q0 * dim, qn_ * dim * sizeof(float), cudaMemcpyHostToDevice, idx->s_in);
 		idx->h_avail[c] = (unsigned int) (q0 + qn_);
-		CU_TRY(cudaMemcpyAsync(d_avail, &idx->h_avail[c], sizeof(unsigned int), cudaMemcpyHostToDevice, idx->s_in));
+		if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_avail, &idx->h_avail[c], sizeof(unsigned int), cudaMemcpyHostToDevice, idx->s_in);
+		if (ce != cudaSuccess)
+		{
+			// never leave the running kernel waiting for queries that will not arrive: release it, then report
+			cudaMemset(d_avail, 0xff, sizeof(unsigned int));
+			cudaStreamSynchronize(s);
+			return fail(PGEMB_ERR_CUDA, std::string("pgemb_search_batch: streaming the queries in failed: ") + cudaGetErrorString(ce));
+		}
 	}
 	if (labels_out) CU_TRY(cudaMemcpyAsync(labels_out, d_l, lb, cudaMemcpyDeviceToHost, s));
 	if (dists_out) CU_TRY(cudaMemcpyAsync(dists_out, d_d, db, cudaMemcpyDeviceToHost, s));

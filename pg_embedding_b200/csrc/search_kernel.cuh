@@ -278,8 +278,20 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 		if (p.avail)
 		{
 			// the batch is still being copied in by the DMA engine: wait until query qi is there
+			// (bounded: ~30 s of polling, then the query is processed anyway and the launch is flagged)
 			if (lane == 0)
-				while (*reinterpret_cast<const volatile unsigned int *>(p.avail) <= qi) __nanosleep(500);
+			{
+				uint32_t spins = 0;
+				while (*reinterpret_cast<const volatile unsigned int *>(p.avail) <= qi)
+				{
+					__nanosleep(500);
+					if (++spins > (60u << 20))
+					{
+						*p.error_flag = 4;
+						break;
+					}
+				}
+			}
 			__syncwarp();
 		}
 
