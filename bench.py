@@ -341,7 +341,7 @@ def cpu_leg(args, idx, q_dev, gpu_labels, gpu_n, n):
     cal = orc.search_many(q[:cores * 2], EFS, nthreads=cores, want_labels=False)
     qps_est = max(1.0, cores * 2 / max(cal["seconds"], 1e-6))
     ns = int(min(q.shape[0], max(cores * 4, qps_est * args.cpu_seconds)))
-    orc.search_many(q[:max(cores * 8, ns // 4)], EFS, nthreads=cores, want_labels=False)   # warm the 3.3 GB graph (page faults, caches)
+    orc.search_many(q[:ns], EFS, nthreads=cores, want_labels=False)   # untimed pass: warm the 3.3 GB graph (page faults, caches), like --impl reference's warm-up step
     res = orc.search_many(q[:ns], EFS, nthreads=cores)
     same = bool((res["labels"] == gpu_labels[:ns].view(np.uint64)).all() and (res["n"] == gpu_n[:ns]).all())
     base = {"value": round(ns / res["seconds"], 1), "unit": "queries/s", "cores": cores, "kind": kind,
