@@ -43,6 +43,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DIMS, M, EFC, EFS = 768, 32, 200, 64
+JSON_OUT = sys.stdout
 METRIC = "cosine"
 
 
@@ -56,7 +57,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("PGEMB_BENCH_N", 1_000_000)),
+    ap.add_argument("--rows", dest="n", type=int, default=int(os.environ.get("PGEMB_BENCH_N", 1_000_000)),
                     help="index size (default 1M = the BASELINE config; smaller values are for development only)")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("PGEMB_BENCH_BATCH", 32768)), help="queries per step per GPU")
     ap.add_argument("--build-batch", type=int, default=int(os.environ.get("PGEMB_BENCH_BUILD_BATCH", 4096)))
@@ -158,8 +159,19 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) write to fd 1 too, so fd 1 is
+    pointed at stderr for the whole run and the JSON line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
     args = parse()
+    global JSON_OUT
+    JSON_OUT = protect_stdout()
     import torch
     import torch.distributed as dist
 
@@ -218,6 +230,7 @@ def main():
     for s in range(W):
         step_device(s)
     barrier()
+    log(f"[rank {rank}] warm-up done, timing {K} steps of {B} queries")
     if os.environ.get("PGEMB_PROFILE"):   # ncu --profile-from-start off: capture exactly the timed region
         torch.cuda.profiler.start()
     launches0 = int(lib.pgemb_launch_count())
@@ -238,6 +251,7 @@ def main():
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
     value = world * B * K / (ms_max * 1e-3)
+    log(f"[rank {rank}] timed region: {ms_max:.1f} ms (max over ranks)")
 
     # ---- roofline of the dominant kernel (the traversal = gather+score): one more step with counters ----
     step_device(W, want_stats=True)
@@ -279,6 +293,7 @@ def main():
     te = torch.tensor([e2e_s], device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    log(f"[rank {rank}] e2e region: {float(te.item()):.3f} s")
     e2e = {"value": round(world * B * K / float(te.item()), 1), "unit": "queries/s",
            "h2d_bytes_per_step": B * DIMS * 4, "d2h_bytes_per_step": B * ef * 8 + B * 4}
 
@@ -311,7 +326,8 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
-        print(json.dumps(out), flush=True)
+        JSON_OUT.write(json.dumps(out) + "\n")
+        JSON_OUT.flush()
     return 0
 
 
@@ -374,7 +390,8 @@ def reference_arm(args, torch, pg, idx, X, Q, n, K, W):
                       "queries_per_step": per_step, "graph": "GPU bulk build, shared by both arms"},
            "cpu_baseline": {"value": v, "unit": "queries/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    JSON_OUT.write(json.dumps(out) + "\n")
+    JSON_OUT.flush()
     return 0
 
 
