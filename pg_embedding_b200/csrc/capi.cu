@@ -461,7 +461,7 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 		if (pool_bytes + W * t.priv_bytes + t.ring_bytes > max_cta) break;
 		uint32_t R = (max_cta - pool_bytes - W * t.priv_bytes) / t.ring_bytes;
 		if (R > W) R = W;
-		if (R > 31) R = 31;
+		if (R > kMaxRings) R = kMaxRings;
 		const double v = (W < R / duty) ? (double) W : R / duty;
 		if (v > bestv + 1e-9)
 		{
@@ -473,7 +473,7 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	if (bestW == 0) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
 	const int wantW = env_int("PGEMB_WARPS", 0), wantR = env_int("PGEMB_RINGS", 0);
 	if (wantW > 0 && wantW <= 32) bestW = (uint32_t) wantW;
-	if (wantR > 0 && wantR <= 31) bestR = (uint32_t) wantR;
+	if (wantR > 0 && wantR <= (int) kMaxRings) bestR = (uint32_t) wantR;
 	if (bestR > bestW) bestR = bestW;
 	while (bestR > 1 && pool_bytes + bestW * t.priv_bytes + bestR * t.ring_bytes > max_cta) bestR--;
 	if (pool_bytes + bestW * t.priv_bytes + bestR * t.ring_bytes > max_cta) return fail(PGEMB_ERR_CAPACITY, "PGEMB_WARPS/PGEMB_RINGS do not fit shared memory");

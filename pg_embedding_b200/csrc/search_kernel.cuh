@@ -83,10 +83,15 @@ struct SearchParams
 
 struct RingPool
 {
-	uint32_t free_mask;		// bit b set = ring b is free
-	uint32_t par[31];		// phase parity the next wait on ring b's barrier must observe
-	uint64_t bar[31];		// one mbarrier per ring
+	// One atomic word is the whole lock state: bit b (b < 16) set = ring b is free; bit 16+b = the phase parity the
+	// next wait on ring b's mbarrier must observe.  A slot learns the parity from the very value its acquiring
+	// atomicCAS observed and hands the updated parity back with atomics before it sets the free bit again, so no
+	// plain shared-memory word is ever shared between slots.
+	uint32_t state;
+	uint32_t pad;
+	uint64_t bar[15];		// one mbarrier per ring
 };
+constexpr uint32_t kMaxRings = 15;
 
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr int	   kTPR = 4;		   // lanes cooperating on one row
@@ -255,10 +260,9 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 
 	if (threadIdx.x == 0)
 	{
-		pool->free_mask = (p.rings >= 32) ? 0xffffffffu : ((1u << p.rings) - 1u);
+		pool->state = (1u << p.rings) - 1u;	// all free, all parities 0
 		for (uint32_t b = 0; b < p.rings; b++)
 		{
-			pool->par[b] = 0;
 			mbar_init(&pool->bar[b], 1);
 		}
 	}
@@ -365,18 +369,18 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				const uint32_t G = (n + kRows - 1) / kRows;
 				st_dist += n;
 				// ---- take a ring from the CTA's pool (held for this hop's gather only) ----------------
-				uint32_t rb = 0;
+				uint32_t rb = 0;  // low byte: ring index, bit 8: its barrier's phase parity
 				if (lane == 0)
 				{
 					for (;;)
 					{
-						const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&pool->free_mask);
-						if (m != 0u)
+						const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&pool->state);
+						if ((m & 0xffffu) != 0u)
 						{
-							const uint32_t b = (uint32_t) __ffs(m) - 1u;
-							if (atomicCAS(&pool->free_mask, m, m & ~(1u << b)) == m)
+							const uint32_t b = (uint32_t) __ffs(m & 0xffffu) - 1u;
+							if (atomicCAS(&pool->state, m, m & ~(1u << b)) == m)
 							{
-								rb = b;
+								rb = b | (((m >> (16u + b)) & 1u) << 8);
 								break;
 							}
 						}
@@ -386,9 +390,11 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					__threadfence_block();
 				}
 				rb = __shfl_sync(kFull, rb, 0);
+				uint32_t rpar = (rb >> 8) & 1u;
+				rb &= 0xffu;
+				const uint32_t rpar0 = rpar;
 				unsigned char *ring = ring_base + (size_t) rb * p.ring_bytes;
 				uint64_t	  *rbar = &pool->bar[rb];
-				uint32_t	   rpar = *reinterpret_cast<volatile uint32_t *>(&pool->par[rb]);
 				auto		   issue = [&](uint32_t g) {
 					  const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
 					  if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
@@ -419,9 +425,9 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				// ---- give the ring back ---------------------------------------------------------------
 				if (lane == 0)
 				{
-					*reinterpret_cast<volatile uint32_t *>(&pool->par[rb]) = rpar;
 					__threadfence_block();
-					atomicOr(&pool->free_mask, 1u << rb);
+					if (rpar != rpar0) atomicXor(&pool->state, 1u << (16u + rb));  // hand the new parity on ...
+					atomicOr(&pool->state, 1u << rb);								 // ... then free the ring
 				}
 
 				const uint64_t *Rb = res + (size_t) cur * ef;
@@ -635,6 +641,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			{
 				if (best < 0) break;  // candidateSet exhausted (or only entries beyond lowerBound)
 				c = key_id(Rb[best]);
+				__syncwarp();
 				if (lane == 0) res[(size_t) cur * ef + best] |= 1ull;
 				__syncwarp();
 			}
