@@ -176,6 +176,13 @@ pgemb_status pgemb_dist_batch(dist_func_t dist, size_t dim, size_t n, const coor
 pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k,
                                const idx_t *ids, dist_t *out);
 
+/* Exact (brute-force) k-NN over all stored nodes: what `SELECT ... ORDER BY val <op> q LIMIT k` computes WITHOUT the index
+ * (one hnsw_dist_func per row, embedding.c:1022-1062, then the executor's sort; test/expected/knn.out:63-91), batched.
+ * Distances bit-identical to the reference's; results ascending by (dist,label); labels with DELETED_FLAG skipped.
+ * labels_out[nq*k] (unused tail ~0), dists_out[nq*k] optional, n_out[nq]. Host pointers. */
+pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out,
+                             dist_t *dists_out, int32_t *n_out);
+
 /* hnsw_bind_point against the device mirror (hnswalg.cpp:225-232): node `id` must be stored and
  * unbound.  Sequential semantics: one call at a time per index. */
 pgemb_status pgemb_bind_point(pgemb_index *idx, idx_t id);

@@ -38,7 +38,7 @@ ABI_SYMBOLS = [
     "pgemb_index_append_records", "pgemb_index_export_records", "pgemb_index_get_links",
     "pgemb_index_set_links", "pgemb_index_get_labels", "pgemb_index_set_labels",
     "pgemb_index_truncate", "pgemb_search_batch", "pgemb_search_batch_device",
-    "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather",
+    "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather", "pgemb_scan_topk",
     "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_build_bulk", "pgemb_build_exact",
 ]
 
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
     lib.pgemb_last_kernel_ms.restype = C.c_float
     lib.pgemb_dist_batch.argtypes = [C.c_int, sz, sz, f32p, C.c_int, f32p, f32p]
     lib.pgemb_dist_gather.argtypes = [vp, sz, f32p, sz, u32p, f32p]
+    lib.pgemb_scan_topk.argtypes = [vp, sz, f32p, sz, u64p, f32p, i32p]
     lib.pgemb_bind_point.argtypes = [vp, C.c_uint32]
     lib.pgemb_insert_batch.argtypes = [vp, sz, f32p, u64p]
     lib.pgemb_merge_topk_device.argtypes = [sz, sz, sz, vp, vp, vp, vp, vp, vp, vp]

@@ -74,6 +74,110 @@ __global__ void dist_gather_kernel(const float *__restrict__ vectors, const floa
 	if (pair < total && sub == 0) out[pair] = ok ? d : __int_as_float(0x7fc00000);
 }
 
+// ---- exact scan (seq-scan `ORDER BY val <op> q LIMIT k`, embedding.c:1022-1062 + executor sort; knn.out:63-91) ----
+// Step 1: out[q][j] = dist(query q, stored node r0 + j) for a chunk of nr rows, reference-exact arithmetic.
+template <int METRIC>
+__global__ void scan_dist_kernel(const float *__restrict__ vectors, const float *__restrict__ norms, uint32_t row_f, uint32_t dim,
+								 const float *__restrict__ queries, uint32_t q_stride, uint32_t nq, uint32_t r0, uint32_t nr,
+								 float *__restrict__ out)
+{
+	constexpr int  TPR = MetricLanes<METRIC>::LANES;
+	const uint64_t t = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	const uint64_t pair = t / TPR;
+	const int	   sub = (int) (t % TPR);
+	const uint64_t total = (uint64_t) nq * nr;
+	if (total == 0) return;
+	const uint64_t pp = pair < total ? pair : total - 1;  // clamp: all lanes of a warp take part in the shuffles
+	const uint32_t q = (uint32_t) (pp / nr), j = (uint32_t) (pp % nr);
+	const float	  *av = queries + (size_t) q * q_stride;
+	const float	  *bv = vectors + (size_t) (r0 + j) * row_f;
+	float		   qn = 0.f, vn = 0.f;
+	if (METRIC == M_COS)
+	{
+		qn = sqnorm_exact<4>(av, (int) dim, sub & 3);
+		vn = norms[r0 + j];
+	}
+	const float d = distance_exact<METRIC, TPR>(av, bv, (int) dim, qn, vn, sub);
+	if (pair < total && sub == 0) out[pair] = d;
+}
+
+// Step 2: fold a chunk of distances into the running k smallest (dist,label) pairs of every query.
+// One warp per query.  top_d holds f2o(dist); candidates better than the current worst pair are gathered in shared
+// memory and merged by rank whenever the buffer fills (the threshold only tightens, so gathering with a stale
+// threshold is conservative and the final set is exact).
+constexpr uint32_t kScanCand = 256;
+__global__ void scan_select_kernel(const float *__restrict__ dist, const uint64_t *__restrict__ labels, uint32_t nq, uint32_t r0,
+								   uint32_t nr, uint32_t k, uint32_t *__restrict__ top_d, uint64_t *__restrict__ top_l,
+								   uint32_t *__restrict__ top_n, uint32_t *__restrict__ tmp_d, uint64_t *__restrict__ tmp_l)
+{
+	__shared__ uint32_t cd[4][kScanCand];
+	__shared__ uint64_t cl[4][kScanCand];
+	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t q = blockIdx.x * 4 + w;
+	if (q >= nq) return;
+	uint32_t *td = top_d + (size_t) q * k, *sd = tmp_d + (size_t) q * k;
+	uint64_t *tl = top_l + (size_t) q * k, *sl = tmp_l + (size_t) q * k;
+	uint32_t  n = top_n[q];
+	uint32_t  nc = 0;
+	const uint32_t lt = (1u << lane) - 1u;
+	auto less = [](uint32_t d1, uint64_t l1, uint32_t d2, uint64_t l2) { return d1 < d2 || (d1 == d2 && l1 < l2); };
+	auto merge = [&]() {
+		// rank every element of top (n) and cand (nc) in their union; keep ranks < k
+		__syncwarp();
+		const uint32_t total = n + nc;
+		for (uint32_t i = lane; i < total; i += 32)
+		{
+			const bool	   from_top = i < n;
+			const uint32_t d = from_top ? td[i] : cd[w][i - n];
+			const uint64_t l = from_top ? tl[i] : cl[w][i - n];
+			uint32_t	   rank = 0;
+			for (uint32_t j = 0; j < n; j++) rank += (j != i && (less(td[j], tl[j], d, l) || (!less(d, l, td[j], tl[j]) && j < i))) ? 1u : 0u;
+			for (uint32_t j = 0; j < nc; j++)
+			{
+				const uint32_t jj = n + j;
+				rank += (jj != i && (less(cd[w][j], cl[w][j], d, l) || (!less(d, l, cd[w][j], cl[w][j]) && jj < i))) ? 1u : 0u;
+			}
+			if (rank < k) { sd[rank] = d; sl[rank] = l; }
+		}
+		__syncwarp();
+		n = total < k ? total : k;
+		for (uint32_t i = lane; i < n; i += 32) { td[i] = sd[i]; tl[i] = sl[i]; }
+		nc = 0;
+		__syncwarp();
+	};
+	for (uint32_t base = 0; base < nr; base += 32)
+	{
+		const uint32_t j = base + lane;
+		bool		   take = false;
+		uint32_t	   d = 0;
+		uint64_t	   l = 0;
+		if (j < nr)
+		{
+			l = labels[r0 + j];
+			if (((l >> 48) & 1ull) == 0)
+			{
+				d = f2o(dist[(size_t) q * nr + j]);
+				take = (n < k) || less(d, l, td[k - 1], tl[k - 1]);
+			}
+		}
+		const uint32_t m = __ballot_sync(0xffffffffu, take);
+		if (m)
+		{
+			if (nc + (uint32_t) __popc(m) > kScanCand) merge();
+			// (after a merge the threshold is tighter; keeping the already tested candidates is still exact)
+			if (take)
+			{
+				const uint32_t at = nc + __popc(m & lt);
+				cd[w][at] = d;
+				cl[w][at] = l;
+			}
+			nc += __popc(m);
+		}
+	}
+	if (nc) merge();
+	if (lane == 0) top_n[q] = n;
+}
+
 // ---- reference record layout (embedding.c:224-228, :619-621) <-> SoA --------------------------------
 // record = [u32 count | u32 links[maxM] | f32 coords[dim] | u64 label], records `stride` bytes apart.
 // One warp per record; byte-granular because the 8-byte label is only 4-byte aligned in general.

@@ -857,6 +857,71 @@ extern "C" pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coo
 	return PGEMB_OK;
 }
 
+extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
+										int32_t *n_out)
+{
+	if (!idx || ((!queries || !labels_out || !n_out) && nq)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (nq == 0) return PGEMB_OK;
+	if (k < 1 || k > 4096) return fail(PGEMB_ERR_ARG, "k out of range (1..4096)");
+	if (nq > (1u << 20)) return fail(PGEMB_ERR_ARG, "too many queries in one scan batch");
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	const size_t dim = idx->meta.dim;
+	const size_t N = idx->n;
+	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+	size_t		 chunk = (size_t) 1 << 14;
+	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
+	const size_t qb = nq * dim * 4, db = nq * chunk * 4, kd = nq * k * 4, kl = nq * k * 8, nb = nq * 4;
+	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + up(nb));
+	if (st) return st;
+	char	 *base = (char *) idx->d_stage;
+	float	 *d_q = (float *) base;			base += up(qb);
+	float	 *d_dist = (float *) base;		base += up(db);
+	uint32_t *d_td = (uint32_t *) base;		base += up(kd);
+	uint32_t *d_sd = (uint32_t *) base;		base += up(kd);
+	uint64_t *d_tl = (uint64_t *) base;		base += up(kl);
+	uint64_t *d_sl = (uint64_t *) base;		base += up(kl);
+	uint32_t *d_tn = (uint32_t *) base;
+	cudaStream_t s = idx->stream;
+	CU_TRY(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, s));
+	CU_TRY(cudaMemsetAsync(d_tn, 0, nb, s));
+	const int	   metric = (int) idx->meta.dist_func;
+	const uint32_t lanes = (metric == DIST_L2) ? 8 : 4;
+	for (size_t r0 = 0; r0 < N; r0 += chunk)
+	{
+		const size_t   nr = (N - r0 < chunk) ? (N - r0) : chunk;
+		const uint32_t threads = 128;
+		const uint32_t blocks = (uint32_t) ((nq * nr * lanes + threads - 1) / threads);
+#define SCAN_DIST(MM)                                                                                                              \
+	scan_dist_kernel<MM><<<blocks, threads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, \
+													(uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
+		if (metric == DIST_L2) SCAN_DIST(M_L2);
+		else if (metric == DIST_COSINE) SCAN_DIST(M_COS);
+		else SCAN_DIST(M_MAN);
+#undef SCAN_DIST
+		scan_select_kernel<<<(uint32_t) ((nq + 3) / 4), 128, 0, s>>>(d_dist, idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k,
+																	 d_td, d_tl, d_tn, d_sd, d_sl);
+		g_launches += 2;
+		CU_TRY(cudaGetLastError());
+	}
+	std::vector<uint32_t> hd(nq * k), hn(nq);
+	CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaStreamSynchronize(s));
+	for (size_t q = 0; q < nq; q++)
+	{
+		n_out[q] = (int32_t) hn[q];
+		for (size_t i = 0; i < k; i++)
+		{
+			const bool ok = i < hn[q];
+			if (!ok) labels_out[q * k + i] = ~(label_t) 0;
+			if (dists_out) dists_out[q * k + i] = ok ? o2f(hd[q * k + i]) : INFINITY;
+		}
+	}
+	return PGEMB_OK;
+}
+
 extern "C" void hnsw_init_dist_func(void)
 {
 	// distfunc.c:159-169 picks the CPU SIMD variant here; the CUDA path has a single variant per metric

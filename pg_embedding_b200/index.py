@@ -283,6 +283,17 @@ class HnswIndex:
         finally:
             self.host.meta.efSearch = ef0  # the reference's HnswIndex is per-scan (embedding.c:254)
 
+    def scan_topk(self, queries, k: int):
+        """Exact brute-force k-NN (the seq-scan answer, knn.out:63-91), batched. Returns dict(labels, dists, n)."""
+        q = _f32(queries)
+        self._check_dims(q)
+        nq = q.shape[0]
+        labels = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=np.float32)
+        n = np.zeros(nq, dtype=np.int32)
+        check(self.lib.pgemb_scan_topk(self.dev, nq, _p(q, C.c_float), int(k), _p(labels, C.c_uint64), _p(dists, C.c_float), _p(n, C.c_int32)))
+        return {"labels": labels, "dists": dists, "n": n}
+
     def dist_gather(self, queries, ids) -> np.ndarray:
         q = _f32(queries)
         i = np.ascontiguousarray(ids, dtype=np.uint32)

@@ -488,3 +488,44 @@ def test_edge_parameters(pg, oracle_mod, cfg):
         assert out["n"].tolist() == want["n"].tolist()
         assert out["labels"].tobytes() == want["labels"].tobytes()
     idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# f3: exact scan (what ORDER BY val <op> q LIMIT k returns without the index; knn.out:63-91)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", METRICS)
+def test_scan_topk_matches_exact_order(pg, oracle_mod, metric):
+    rng = np.random.default_rng(99)
+    for dims, n, k, levels in ((3, 500, 7, 3), (33, 3000, 64, 0), (128, 20000, 10, 0)):
+        x = _data(rng, n, dims, levels=levels)
+        q = _data(rng, 24, dims, levels=levels)
+        if metric == "cosine":
+            x, q = x + 1.0, q + 1.0
+        labels = rng.permutation(n).astype(np.uint64) + np.uint64(5)
+        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
+        idx.append(x, labels)
+        dead = np.arange(0, n, 9)
+        idx.mark_deleted(dead)
+        out = idx.scan_topk(q, k)
+        alive = np.ones(n, bool); alive[dead] = False
+        for i in range(q.shape[0]):
+            d = oracle_mod.dist_many("port", metric, q[i], x)
+            order = sorted((float(d[j]), int(labels[j])) for j in range(n) if alive[j])[:k]
+            c = int(out["n"][i])
+            assert c == len(order)
+            assert out["labels"][i, :c].tolist() == [o[1] for o in order], (metric, dims, i)
+            assert out["dists"][i, :c].tobytes() == np.array([o[0] for o in order], np.float32).tobytes()
+        idx.close()
+
+
+def test_scan_topk_regress_seqscan(pg):
+    """knn.out:63-91: the seq-scan orders of the regress table for the three operators."""
+    case = GOLD[0]
+    for metric, want in case["expected"].items():
+        idx = pg.HnswIndex(3, 3, 16, 64, metric, capacity=8)
+        rows = case["rows"]
+        idx.append(np.array([r["val"] for r in rows], np.float32), np.array([tid_label(*r["tid"]) for r in rows], np.uint64))
+        out = idx.scan_topk(np.array([case["query"]], np.float32), 4)
+        by_label = {tid_label(*r["tid"]): r["val"] for r in rows}
+        assert [by_label[int(l)] for l in out["labels"][0, : out["n"][0]]] == want, metric
+        idx.close()
