@@ -15,7 +15,8 @@ ap.add_argument("--dims", type=int, default=128); ap.add_argument("--n", type=in
 ap.add_argument("--metric", default="l2"); ap.add_argument("--m", type=int, default=16)
 ap.add_argument("--efc", type=int, default=200); ap.add_argument("--efs", type=int, default=64)
 ap.add_argument("--batch", type=int, default=32768); ap.add_argument("--steps", type=int, default=10)
-ap.add_argument("--build-batch", type=int, default=4096)
+ap.add_argument("--build-batch", type=int, default=4096); ap.add_argument("--dist", default="clustered", choices=["clustered", "iid"])
+ap.add_argument("--scan-queries", type=int, default=0, help="also time the exact scan (pgemb_scan_topk) on this many queries and use it as ground truth")
 a = ap.parse_args()
 lib = _lib.load()
 g = torch.Generator(device="cuda"); g.manual_seed(99)
@@ -27,7 +28,7 @@ def gen(k, seed):
     for s in range(0, k, 1 << 16):
         e = min(k, s + (1 << 16))
         c = torch.randint(0, centres.shape[0], (e - s,), generator=g, device="cuda")
-        x = centres[c] + sigma * torch.randn((e - s, a.dims), generator=g, device="cuda")
+        x = torch.randn((e - s, a.dims), generator=g, device="cuda") if a.dist == "iid" else centres[c] + sigma * torch.randn((e - s, a.dims), generator=g, device="cuda")
         out[s:e] = x / x.norm(dim=1, keepdim=True) if a.metric == "cosine" else x
     return out
 X, Q = gen(a.n, 1234), gen(a.batch * (a.steps + 3), 5678)
@@ -60,6 +61,13 @@ else:
 got = d_lab[:ns, :10].cpu().numpy(); truth = truth.cpu().numpy()
 rec = float(np.mean([len(set(truth[i].tolist()) & set(got[i].tolist())) / 10 for i in range(ns)]))
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-print(json.dumps({"shape": vars(a), "build_s": round(build_s, 2), "qps": round(B / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
+scan = None
+if a.scan_queries:
+    import time
+    qh = qs[:a.scan_queries].cpu().numpy()
+    t0 = time.perf_counter(); sc = idx.scan_topk(qh, 10); t1 = time.perf_counter() - t0
+    agree = float(np.mean([len(set(sc["labels"][i].tolist()) & set(truth[i].tolist())) / 10 for i in range(len(qh))]))
+    scan = {"queries": len(qh), "seconds": round(t1, 3), "pairs_per_s": round(len(qh) * a.n / t1, 0), "top10_overlap_with_torch_truth": round(agree, 4)}
+print(json.dumps({"scan_topk": scan, "shape": vars(a), "build_s": round(build_s, 2), "qps": round(B / (ms * 1e-3), 1), "ms_per_step": round(ms, 3),
                   "achieved_gbs": round(byt / (kms * 1e-3) / 1e9, 1), "frac": round(byt / (kms * 1e-3) / 1e9 / peak, 4),
                   "dist_evals_per_query": float(stt[:, 0].mean()), "expansions_per_query": float(stt[:, 1].mean()), "recall_at_10": round(rec, 4)}))
