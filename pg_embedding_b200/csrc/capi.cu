@@ -418,7 +418,7 @@ static int env_int(const char *name, int dflt)
 
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
-static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c)
+static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c, bool coop = false)
 {
 	const int	   metric = (int) idx->meta.dist_func;
 	const uint32_t row_bytes = idx->row_f * 4u;
@@ -471,6 +471,29 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 		}
 	}
 	if (bestW == 0) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
+	if (coop)
+	{
+		// latency mode: one slot per CTA, every warp owns a ring; no more warps than a full hop has row groups
+		uint32_t R = (max_cta - pool_bytes - t.priv_bytes) / t.ring_bytes;
+		const uint32_t groups = (hopcap + 7u) / 8u;
+		if (R > groups) R = groups;
+		if (R > kMaxRings) R = kMaxRings;
+		const int wantC = env_int("PGEMB_COOP_WARPS", 0);
+		if (wantC > 0 && (uint32_t) wantC < R) R = (uint32_t) wantC;
+		if (R < 1) R = 1;
+		t.warps = R;
+		t.rings = R;
+		t.off_pool = 0;
+		t.off_ring = pool_bytes;
+		t.off_priv = pool_bytes + R * t.ring_bytes;
+		t.smem = t.off_priv + t.priv_bytes;
+		t.row_smem = row_smem;
+		t.qt_stride = qt_stride;
+		t.ef = ef;
+		t.slots = (uint32_t) idx->sm_count;
+		*c = t;
+		return PGEMB_OK;
+	}
 	const int wantW = env_int("PGEMB_WARPS", 0), wantR = env_int("PGEMB_RINGS", 0);
 	if (wantW > 0 && wantW <= 32) bestW = (uint32_t) wantW;
 	if (wantR > 0 && wantR <= (int) kMaxRings) bestR = (uint32_t) wantR;
@@ -493,13 +516,13 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 
 typedef void (*search_fn_t)(const SearchParams);
 
-static search_fn_t pick_search_kernel(int metric)
+static search_fn_t pick_search_kernel(int metric, bool coop)
 {
 	switch (metric)
 	{
-		case DIST_L2: return search_kernel<M_L2>;
-		case DIST_COSINE: return search_kernel<M_COS>;
-		case DIST_MANHATTAN: return search_kernel<M_MAN>;
+		case DIST_L2: return coop ? search_kernel<M_L2, true> : search_kernel<M_L2, false>;
+		case DIST_COSINE: return coop ? search_kernel<M_COS, true> : search_kernel<M_COS, false>;
+		case DIST_MANHATTAN: return coop ? search_kernel<M_MAN, true> : search_kernel<M_MAN, false>;
 	}
 	return nullptr;
 }
@@ -569,10 +592,12 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	if (nq >= (1ull << 31)) return fail(PGEMB_ERR_ARG, "too many queries in one batch");
 	pgemb_status st = set_device(idx);
 	if (st) return st;
+	// fewer queries than SMs: latency mode, a whole CTA cooperates on each query (search_kernel.cuh, COOP)
+	const bool	 coop = nq <= (size_t) idx->sm_count && env_int("PGEMB_COOP", 1) != 0;
 	SearchConfig cfg;
-	st = make_config(idx, (uint32_t) ef, &cfg);
+	st = make_config(idx, (uint32_t) ef, &cfg, coop);
 	if (st) return st;
-	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func);
+	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, coop);
 	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for this metric");
 	CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.smem));
 	int occ = 0;
@@ -659,8 +684,8 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
 	}
 	CU_TRY(cudaMemsetAsync(idx->d_counter, 0, sizeof(unsigned int), s));
-	uint32_t grid = (uint32_t) ((nq + cfg.warps - 1) / cfg.warps);
-	if (grid > (uint32_t) idx->sm_count) grid = (uint32_t) idx->sm_count;
+	// small batches are spread over all SMs (the slots steal queries from one counter), not packed into few CTAs
+	uint32_t grid = (uint32_t) (nq < (size_t) idx->sm_count ? nq : (size_t) idx->sm_count);
 	if (time_it) CU_TRY(cudaEventRecord(idx->ev0, s));
 	fn<<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
 	g_launches++;
@@ -697,6 +722,20 @@ extern "C" pgemb_status pgemb_search_batch_device(pgemb_index *idx, size_t nq, c
 						 d_ids_out, d_n_out, d_stats_out, (cudaStream_t) stream, true);
 }
 
+// Streaming the batch in behind the running kernel needs kernels and copies to overlap.  Tools that serialise
+// or replay kernel launches (Nsight Compute, compute-sanitizer: both arrive through CUDA_INJECTION64_PATH;
+// CUDA_LAUNCH_BLOCKING=1) get the plain copy-then-launch order.  PGEMB_STREAM_QUERIES=0/1 overrides.
+static bool stream_queries_enabled()
+{
+	const char *force = getenv("PGEMB_STREAM_QUERIES");
+	if (force && *force) return atoi(force) != 0;
+	const char *inj = getenv("CUDA_INJECTION64_PATH");
+	if (inj && *inj) return false;
+	const char *blk = getenv("CUDA_LAUNCH_BLOCKING");
+	if (blk && *blk && atoi(blk) != 0) return false;
+	return true;
+}
+
 extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const coord_t *queries, size_t ef, label_t *labels_out,
 										   dist_t *dists_out, idx_t *ids_out, int32_t *n_out, uint32_t *stats_out)
 {
@@ -719,9 +758,13 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 	uint32_t *d_i = (uint32_t *) base;			base += up(ib);
 	int32_t	 *d_n = (int32_t *) base;			base += up(nb);
 	uint32_t *d_s = (uint32_t *) base;
-	// ONE traversal launch; the query batch is streamed in behind it: the copy stream moves chunk after chunk
+	// ONE traversal launch; the query batch is streamed in next to it: the copy stream moves chunk after chunk
 	// H2D and publishes "queries available" after each, the kernel's slots wait for their query to land
 	// (SearchParams::avail).  So the PCIe transfer hides behind the traversal instead of preceding it.
+	// The copies are ENQUEUED FIRST: they then make progress whether or not the launch call returns at once, so a
+	// blocking launch (CUDA_LAUNCH_BLOCKING, a profiler or sanitizer serialising kernels) cannot leave the kernel
+	// waiting for data that was never queued.  Under such a tool (detected by its injection variable) the batch is
+	// simply copied before the launch: replayed kernels must not depend on a concurrent copy.
 	cudaStream_t s = idx->stream;
 	if (!idx->s_in)
 	{
@@ -729,31 +772,45 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 		CU_TRY(cudaEventCreateWithFlags(&idx->ev_in[0], cudaEventDisableTiming));
 		CU_TRY(cudaMallocHost((void **) &idx->h_avail, sizeof(unsigned int) * pgemb_index::kMaxChunks));
 	}
+	const bool	  streamed = stream_queries_enabled();
 	unsigned int *d_avail = idx->d_counter + 2;
-	size_t		  nchunks = (nq + 4095) / 4096;
+	size_t		  nchunks = streamed ? (nq + 4095) / 4096 : 1;
 	if (nchunks > (size_t) pgemb_index::kMaxChunks) nchunks = pgemb_index::kMaxChunks;
 	const size_t per = (nq + nchunks - 1) / nchunks;
 	CU_TRY(cudaMemsetAsync(d_avail, 0, sizeof(unsigned int), idx->s_in));
-	CU_TRY(cudaEventRecord(idx->ev_in[0], idx->s_in));
-	CU_TRY(cudaStreamWaitEvent(s, idx->ev_in[0], 0));
-	st = launch_search(idx, nq, d_q, (uint32_t) dim, nullptr, (uint32_t) idx->n, ef, 0, labels_out ? d_l : nullptr, dists_out ? d_d : nullptr,
-					   ids_out ? d_i : nullptr, d_n, stats_out ? d_s : nullptr, s, true, d_avail);
-	if (st) return st;
-	for (size_t c = 0; c < nchunks; c++)
+	if (streamed)
+	{
+		// the kernel may start as soon as `avail` reads 0 ...
+		CU_TRY(cudaEventRecord(idx->ev_in[0], idx->s_in));
+		CU_TRY(cudaStreamWaitEvent(s, idx->ev_in[0], 0));
+	}
+	cudaError_t ce = cudaSuccess;
+	for (size_t c = 0; c < nchunks && ce == cudaSuccess; c++)
 	{
 		const size_t q0 = c * per;
 		if (q0 >= nq) break;
 		const size_t qn_ = (q0 + per <= nq) ? per : (nq - q0);
-		cudaError_t ce = cudaMemcpyAsync(d_q + q0 * dim, queries + q0 * dim, qn_ * dim * sizeof(float), cudaMemcpyHostToDevice, idx->s_in);
+		ce = cudaMemcpyAsync(d_q + q0 * dim, queries + q0 * dim, qn_ * dim * sizeof(float), cudaMemcpyHostToDevice, idx->s_in);
 		idx->h_avail[c] = (unsigned int) (q0 + qn_);
 		if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_avail, &idx->h_avail[c], sizeof(unsigned int), cudaMemcpyHostToDevice, idx->s_in);
-		if (ce != cudaSuccess)
-		{
-			// never leave the running kernel waiting for queries that will not arrive: release it, then report
-			cudaMemset(d_avail, 0xff, sizeof(unsigned int));
-			cudaStreamSynchronize(s);
-			return fail(PGEMB_ERR_CUDA, std::string("pgemb_search_batch: streaming the queries in failed: ") + cudaGetErrorString(ce));
-		}
+	}
+	if (ce != cudaSuccess)
+	{
+		cudaStreamSynchronize(idx->s_in);  // nothing was launched; the caller's buffer must not be read after we return
+		return fail(PGEMB_ERR_CUDA, std::string("pgemb_search_batch: copying the queries in failed: ") + cudaGetErrorString(ce));
+	}
+	if (!streamed)
+	{
+		// ... or, not streamed, only after the whole batch has landed
+		CU_TRY(cudaEventRecord(idx->ev_in[0], idx->s_in));
+		CU_TRY(cudaStreamWaitEvent(s, idx->ev_in[0], 0));
+	}
+	st = launch_search(idx, nq, d_q, (uint32_t) dim, nullptr, (uint32_t) idx->n, ef, 0, labels_out ? d_l : nullptr, dists_out ? d_d : nullptr,
+					   ids_out ? d_i : nullptr, d_n, stats_out ? d_s : nullptr, s, true, streamed ? d_avail : nullptr);
+	if (st)
+	{
+		cudaStreamSynchronize(idx->s_in);
+		return st;
 	}
 	if (labels_out) CU_TRY(cudaMemcpyAsync(labels_out, d_l, lb, cudaMemcpyDeviceToHost, s));
 	if (dists_out) CU_TRY(cudaMemcpyAsync(dists_out, d_d, db, cudaMemcpyDeviceToHost, s));

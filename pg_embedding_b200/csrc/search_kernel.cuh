@@ -90,6 +90,9 @@ struct RingPool
 	uint32_t state;
 	uint32_t pad;
 	uint64_t bar[15];		// one mbarrier per ring
+	// latency mode (COOP): the owner warp publishes the hop's row count (kNone = quit) and |q|^2 here
+	uint32_t coop_n;
+	float	 coop_qn;
 };
 constexpr uint32_t kMaxRings = 15;
 
@@ -223,16 +226,59 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 	}
 }
 
+// ---- latency mode (COOP) -------------------------------------------------------------------------------
+// With fewer queries than SMs a query has a whole SM to itself, and the per-hop latency -- not bytes in
+// flight -- is what a caller of hnsw_search() waits for.  The CTA then runs ONE slot: warp 0 owns the
+// traversal exactly as in the throughput kernel, and all warps (each with its own ring and mbarrier) gather
+// and score one 8-row group of the hop at the same time, so a hop costs one DRAM round trip + one row
+// scoring instead of ceil(n/8) of them back to back.  Two named barriers bracket the shared phase; every
+// row is scored by the same score_row4 (same bits).
+__device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 template <int METRIC>
+__device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char *ring, uint64_t *rbar, uint32_t &rpar, uint32_t warp,
+											uint32_t nwarps, uint32_t n, const uint32_t *hop_id, uint64_t *hop_key, const float *qT,
+											const float *q_tail, float qn, int main_n, uint64_t pol_stream)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const int	   row_in_stage = lane / kTPR;
+	const int	   sub = lane % kTPR;
+	const uint32_t G = (n + kRows - 1) / kRows;
+	const float	  *qts = qT + sub * p.qt_stride;
+	for (uint32_t g = warp; g < G; g += nwarps)
+	{
+		const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
+		if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
+		__syncwarp();
+		if (lane < rows)
+		{
+			const uint32_t id = hop_id[g * kRows + lane];
+			tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
+		}
+		const uint32_t k = g * kRows + row_in_stage;
+		const uint32_t kk = min(k, n - 1);
+		const uint32_t my_id = hop_id[kk];
+		float		   vn = 1.0f;
+		if (METRIC == M_COS) vn = p.norms[my_id];
+		mbar_wait(rbar, rpar);
+		rpar ^= 1u;
+		const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
+		const float	 d = score_row4<METRIC>(qts, rowp, sub, main_n, q_tail, (int) p.dim, qn, vn);
+		if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
+		__syncwarp();
+	}
+}
+
+template <int METRIC, bool COOP>
 __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
-	const uint32_t slot = blockIdx.x * (blockDim.x >> 5) + warp;
+	const uint32_t slot = COOP ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;
 	RingPool	  *pool = reinterpret_cast<RingPool *>(smem + p.off_pool);
 	unsigned char *ring_base = smem + p.off_ring;
-	unsigned char *priv = smem + p.off_priv + (size_t) warp * p.priv_bytes;	// this slot's private block
+	unsigned char *priv = smem + p.off_priv + (COOP ? 0 : (size_t) warp * p.priv_bytes);  // this slot's private block
 	float		  *qT = reinterpret_cast<float *>(priv + p.off_qt);
 	float		  *q_tail = reinterpret_cast<float *>(priv + p.off_qtail);
 	uint64_t	  *res = reinterpret_cast<uint64_t *>(priv + p.off_res);	// two buffers of ef keys
@@ -266,9 +312,25 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			mbar_init(&pool->bar[b], 1);
 		}
 	}
-	if (lane == 0) mbar_init(pf_bar, 1);
+	if (lane == 0 && (!COOP || warp == 0)) mbar_init(pf_bar, 1);
 	fence_mbar_init();
 	__syncthreads();		   // the only CTA-wide barrier: from here on the slots run independently
+	uint32_t coop_par = 0;	   // COOP: phase parity of this warp's own ring barrier
+	if (COOP && warp != 0)
+	{
+		// helper warp: score one row group per hop on command of the owner (warp 0)
+		unsigned char *my_ring = ring_base + (size_t) warp * p.ring_bytes;
+		for (;;)
+		{
+			coop_bar(1, blockDim.x);
+			const uint32_t hn = *reinterpret_cast<volatile uint32_t *>(&pool->coop_n);
+			if (hn == kNone) break;
+			const float hq = *reinterpret_cast<volatile float *>(&pool->coop_qn);
+			coop_gather<METRIC>(p, my_ring, &pool->bar[warp], coop_par, warp, blockDim.x >> 5, hn, hop_id, hop_key, qT, q_tail, hq, main_n, pol_stream);
+			coop_bar(2, blockDim.x);
+		}
+		return;
+	}
 	uint32_t pf_parity = 0;	   // phase parity for the link prefetch barrier
 	bool	 pf_inflight = false;
 	uint32_t pf_id = kNone;
@@ -282,14 +344,15 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 		if (p.avail)
 		{
 			// the batch is still being copied in by the DMA engine: wait until query qi is there
-			// (bounded: ~30 s of polling, then the query is processed anyway and the launch is flagged)
+			// (bounded: a few seconds of polling -- a chunk takes < 1 ms over PCIe -- then the query is processed
+			// anyway and the launch is flagged)
 			if (lane == 0)
 			{
 				uint32_t spins = 0;
 				while (*reinterpret_cast<const volatile unsigned int *>(p.avail) <= qi)
 				{
 					__nanosleep(500);
-					if (++spins > (60u << 20))
+					if (++spins > (8u << 20))
 					{
 						*p.error_flag = 4;
 						break;
@@ -302,18 +365,33 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 		// ---- stage the query: lane-major transposed copy + natural-order tail -------------------
 		{
 			const float *qsrc = p.query_ids ? p.vectors + (size_t) p.query_ids[qi] * p.row_f : p.queries + (size_t) qi * p.q_stride;
-			for (int e = (int) lane; e < dim; e += 32)
+			// eight loads in flight per lane before the first dependent store (one DRAM round trip per 256 floats)
+			for (int e0 = 0; e0 < dim; e0 += 256)
 			{
-				const float v = qsrc[e];
-				if (e >= main_n)
-					q_tail[e - main_n] = v;
-				else if (METRIC == M_L2)
+				float v8[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++)
 				{
-					const int b = e >> 4, o = e & 15, l = o & 7;
-					qT[(l >> 1) * p.qt_stride + 4 * b + ((o >> 3) << 1) + (l & 1)] = v;
+					const int e = e0 + j * 32 + (int) lane;
+					v8[j] = (e < dim) ? __ldcg(qsrc + e) : 0.0f;  // L2 only: the batch may still be streaming in (avail)
 				}
-				else
-					qT[(e & 3) * p.qt_stride + (e >> 2)] = v;
+#pragma unroll
+				for (int j = 0; j < 8; j++)
+				{
+					const int	e = e0 + j * 32 + (int) lane;
+					const float v = v8[j];
+					if (e >= dim)
+						continue;
+					if (e >= main_n)
+						q_tail[e - main_n] = v;
+					else if (METRIC == M_L2)
+					{
+						const int b = e >> 4, o = e & 15, l = o & 7;
+						qT[(l >> 1) * p.qt_stride + 4 * b + ((o >> 3) << 1) + (l & 1)] = v;
+					}
+					else
+						qT[(e & 3) * p.qt_stride + (e >> 2)] = v;
+				}
 			}
 		}
 		__syncwarp();
@@ -329,6 +407,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			qn = hsum4(f0, f1, f2, f3);
 			for (int e = main_n; e < dim; e++) qn = __fadd_rn(qn, __fmul_rn(q_tail[e - main_n], q_tail[e - main_n]));
 		}
+		if (COOP && lane == 0) pool->coop_qn = qn;
 
 		int		 cur = 0;		// which res buffer is live
 		uint32_t r = 0;			// results held (<= ef), ascending (dist,id)
@@ -366,8 +445,18 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			if (n > 0)
 			{
 				// ================= K1: gather + score the n rows in hop_id[] ======================
-				const uint32_t G = (n + kRows - 1) / kRows;
 				st_dist += n;
+				if constexpr (COOP)
+				{
+					if (lane == 0) pool->coop_n = n;
+					__syncwarp();
+					coop_bar(1, blockDim.x);
+					coop_gather<METRIC>(p, ring_base, &pool->bar[0], coop_par, 0, blockDim.x >> 5, n, hop_id, hop_key, qT, q_tail, qn, main_n, pol_stream);
+					coop_bar(2, blockDim.x);
+				}
+				else
+				{
+				const uint32_t G = (n + kRows - 1) / kRows;
 				// ---- take a ring from the CTA's pool (held for this hop's gather only) ----------------
 				uint32_t rb = 0;  // low byte: ring index, bit 8: its barrier's phase parity
 				if (lane == 0)
@@ -429,6 +518,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					if (rpar != rpar0) atomicXor(&pool->state, 1u << (16u + rb));  // hand the new parity on ...
 					atomicOr(&pool->state, 1u << rb);								 // ... then free the ring
 				}
+				}  // !COOP
 
 				const uint64_t *Rb = res + (size_t) cur * ef;
 				uint64_t	   *Ob = res + (size_t) (cur ^ 1) * ef;
@@ -819,6 +909,13 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 		else
 			for (uint32_t i = lane; i < p.vis_words; i += 32) vis[i] = 0u;
 		__syncwarp();
+	}
+	if (COOP)
+	{
+		// release the helper warps
+		if (lane == 0) pool->coop_n = kNone;
+		__syncwarp();
+		coop_bar(1, blockDim.x);
 	}
 	// an unconsumed link prefetch must land before the CTA (and its shared memory) goes away
 	if (pf_inflight) mbar_wait(pf_bar, pf_parity);

@@ -25,6 +25,24 @@ def pg():
     return pg
 
 
+class kernel_mode:
+    """Pin the traversal kernel variant: "1" = latency mode (a CTA per query, used by default below one query per
+    SM), "0" = throughput mode (a warp per query).  Both must give the reference's results."""
+
+    def __init__(self, coop):
+        self.coop = coop
+
+    def __enter__(self):
+        self.old = os.environ.get("PGEMB_COOP")
+        os.environ["PGEMB_COOP"] = self.coop
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("PGEMB_COOP", None)
+        else:
+            os.environ["PGEMB_COOP"] = self.old
+
+
 def checkers(oracle_mod):
     return ["port"] + (["ref"] if oracle_mod.available("ref") else [])
 
@@ -154,11 +172,12 @@ def test_search_identical_to_oracle(pg, oracle_mod, metric, cfg):
     idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
     idx.append(x, labs, links)
     assert idx.links().tobytes() == links.tobytes()
-    for ef in efs:
-        out = idx.search_batch(q, ef, want_stats=True)
+    for ef, coop in [(e, c) for e in efs for c in ("1", "0")]:
+        with kernel_mode(coop):
+            out = idx.search_batch(q, ef, want_stats=True)
         want = orc.search_many(q, ef, want_counters=True)
-        assert out["n"].tolist() == want["n"].tolist(), (metric, ef)
-        assert out["labels"].tobytes() == want["labels"].tobytes(), (metric, ef)
+        assert out["n"].tolist() == want["n"].tolist(), (metric, ef, coop)
+        assert out["labels"].tobytes() == want["labels"].tobytes(), (metric, ef, coop)
         if ref is not None:
             w2 = ref.search_many(q, ef, nthreads=2)
             assert out["labels"].tobytes() == w2["labels"].tobytes(), (metric, ef, "compiled reference")
@@ -225,9 +244,10 @@ def test_bind_links_identical_to_oracle(pg, oracle_mod, metric, cfg):
     got, want = idx.links(), orc.links()
     bad = np.flatnonzero((got != want).any(1))
     assert bad.size == 0, f"{metric}: link lists differ at nodes {bad[:10]} (first: {got[bad[0]][:8]} vs {want[bad[0]][:8]})"
-    # bulk build with batch_max=1 is the same sequence of exact binds
+    # bulk build with batch_max=1 is the same sequence of exact binds (here with the throughput-mode kernel)
     idx2 = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
-    idx2.build(x, batch_max=1)
+    with kernel_mode("0"):
+        idx2.build(x, batch_max=1)
     assert idx2.links().tobytes() == want.tobytes()
     idx.close()
     idx2.close()

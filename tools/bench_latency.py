@@ -16,13 +16,21 @@ idx = pg.HnswIndex(bench.DIMS, bench.M, bench.EFC, bench.EFS, bench.METRIC, capa
 _lib.check(lib.pgemb_index_append_device(idx.dev, n, X.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)); torch.cuda.synchronize()
 idx.build_appended(0, n, 4096)
 q = Q.cpu().numpy()
-for i in range(20): idx.search(q[i])
-ts = []
-for i in range(20, 320):
-    t0 = time.perf_counter(); idx.search(q[i]); ts.append(time.perf_counter() - t0)
-out = idx.search_batch(q[20:21], 64)
-res = {"n": n, "gpu_hnsw_search_ms_median": round(1e3 * float(np.median(ts)), 3), "gpu_hnsw_search_ms_p95": round(1e3 * float(np.percentile(ts, 95)), 3),
-       "gpu_kernel_ms_one_query": round(out["kernel_ms"], 3)}
+res = {"n": n}
+for mode, tag in (("1", "latency_mode"), ("0", "throughput_mode")):
+    os.environ["PGEMB_COOP"] = mode     # read by the library at every launch
+    for i in range(20): idx.search(q[i])
+    ts = []
+    for i in range(20, 320):
+        t0 = time.perf_counter(); idx.search(q[i]); ts.append(time.perf_counter() - t0)
+    out = idx.search_batch(q[20:21], 64)
+    res[tag] = {"hnsw_search_ms_median": round(1e3 * float(np.median(ts)), 3), "hnsw_search_ms_p95": round(1e3 * float(np.percentile(ts, 95)), 3),
+                "kernel_ms_one_query": round(out["kernel_ms"], 3)}
+    for nb in (16, 148, 512):
+        idx.search_batch(q[:nb], 64)
+        o2 = idx.search_batch(q[:nb], 64)
+        res[tag][f"kernel_ms_batch{nb}"] = round(o2["kernel_ms"], 3)
+os.environ.pop("PGEMB_COOP")
 if "--cpu" in sys.argv:
     which, kind = bench.pick_checker()
     orc = bench.host_graph(idx, n, which)
