@@ -154,29 +154,37 @@ extern "C" pgemb_status pgemb_index_create(const HnswMetadata *meta, size_t capa
 	idx->capacity = capacity;
 	idx->row_f = (uint32_t) ((meta->dim + 3) & ~(size_t) 3);
 	idx->link_stride = (uint32_t) ((meta->maxM + 1 + 3) & ~(size_t) 3);
-	cudaDeviceProp prop;
-	CU_TRY(cudaGetDeviceProperties(&prop, device));
-	idx->sm_count = prop.multiProcessorCount;
-	idx->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
-	idx->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
 	cudaError_t e;
+	// from here on a failure must not leak the half-built index
+#define CU_TRY_IDX(expr)                                                                                  \
+	if ((e = (expr)) != cudaSuccess)                                                                      \
+	{                                                                                                     \
+		pgemb_index_destroy(idx);                                                                         \
+		return fail(PGEMB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e));                   \
+	}
 #define ALLOC(ptr, bytes)                                                                                 \
 	if ((e = cudaMalloc((void **) &(ptr), (bytes))) != cudaSuccess)                                       \
 	{                                                                                                     \
 		pgemb_index_destroy(idx);                                                                         \
 		return fail(PGEMB_ERR_NOMEM, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e));       \
 	}
+	cudaDeviceProp prop;
+	CU_TRY_IDX(cudaGetDeviceProperties(&prop, device));
+	idx->sm_count = prop.multiProcessorCount;
+	idx->l2_persist_max = (size_t) prop.persistingL2CacheMaxSize;
+	idx->l2_window_max = (size_t) prop.accessPolicyMaxWindowSize;
 	ALLOC(idx->d_vectors, capacity * idx->row_f * sizeof(float));
 	ALLOC(idx->d_links, capacity * idx->link_stride * sizeof(uint32_t));
 	ALLOC(idx->d_labels, capacity * sizeof(uint64_t));
 	ALLOC(idx->d_norms, capacity * sizeof(float));
 	ALLOC(idx->d_counter, sizeof(unsigned int) * 4);
 	ALLOC(idx->d_error, sizeof(int));
+	CU_TRY_IDX(cudaMemset(idx->d_error, 0, sizeof(int)));
+	CU_TRY_IDX(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+	CU_TRY_IDX(cudaEventCreate(&idx->ev0));
+	CU_TRY_IDX(cudaEventCreate(&idx->ev1));
 #undef ALLOC
-	CU_TRY(cudaMemset(idx->d_error, 0, sizeof(int)));
-	CU_TRY(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
-	CU_TRY(cudaEventCreate(&idx->ev0));
-	CU_TRY(cudaEventCreate(&idx->ev1));
+#undef CU_TRY_IDX
 	*out = idx;
 	return PGEMB_OK;
 }
@@ -262,7 +270,15 @@ static pgemb_status append_common(pgemb_index *idx, size_t n, const coord_t *coo
 		CU_TRY(cudaMemcpyAsync(idx->d_labels + first, labels, n * sizeof(uint64_t), kind, s));
 	else
 	{
-		std::vector<uint64_t> tmp(n);
+		std::vector<uint64_t> tmp;
+		try
+		{
+			tmp.resize(n);
+		}
+		catch (const std::bad_alloc &)
+		{
+			return fail(PGEMB_ERR_NOMEM, "out of host memory");
+		}
 		for (size_t i = 0; i < n; i++) tmp[i] = first + i;
 		CU_TRY(cudaMemcpyAsync(idx->d_labels + first, tmp.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
 		CU_TRY(cudaStreamSynchronize(s));
@@ -961,7 +977,17 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 		g_launches += 2;
 		CU_TRY(cudaGetLastError());
 	}
-	std::vector<uint32_t> hd(nq * k), hn(nq);
+	std::vector<uint32_t> hd, hn;
+	try
+	{
+		hd.resize(nq * k);
+		hn.resize(nq);
+	}
+	catch (const std::bad_alloc &)
+	{
+		cudaStreamSynchronize(s);
+		return fail(PGEMB_ERR_NOMEM, "out of host memory");  // no C++ exception crosses the C ABI
+	}
 	CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
@@ -1169,6 +1195,22 @@ pgemb_status bind_points(pgemb_index *idx, idx_t first, size_t n)
 	return PGEMB_OK;
 }
 
+// two timing events that go away on every return path
+struct EventPair
+{
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	cudaError_t create()
+	{
+		cudaError_t e = cudaEventCreate(&e0);
+		return e != cudaSuccess ? e : cudaEventCreate(&e1);
+	}
+	~EventPair()
+	{
+		if (e0) cudaEventDestroy(e0);
+		if (e1) cudaEventDestroy(e1);
+	}
+};
+
 __global__ void iota_kernel(uint32_t *out, uint32_t start, uint32_t n)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1189,9 +1231,9 @@ extern "C" pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t 
 	st = ensure_bind_ws(idx, batch_max, efc);
 	if (st) return st;
 	BindWorkspace &w = idx->bind_ws;
-	cudaEvent_t	   e0, e1;
-	CU_TRY(cudaEventCreate(&e0));
-	CU_TRY(cudaEventCreate(&e1));
+	EventPair ev;
+	CU_TRY(ev.create());
+	const cudaEvent_t e0 = ev.e0, e1 = ev.e1;
 	CU_TRY(cudaEventRecord(e0, s));
 	size_t pos = first;
 	const size_t end = first + n;
@@ -1219,8 +1261,6 @@ extern "C" pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t 
 	st = check_device_error(idx, s);
 	float ms = 0.f;
 	cudaEventElapsedTime(&ms, e0, e1);
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
 	if (seconds_out) *seconds_out = ms * 1e-3;
 	return st;
 }
@@ -1258,9 +1298,9 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 		w.stamp_cap = idx->capacity;
 	}
 	const size_t M = idx->meta.M ? idx->meta.M : 1;
-	cudaEvent_t	 e0, e1;
-	CU_TRY(cudaEventCreate(&e0));
-	CU_TRY(cudaEventCreate(&e1));
+	EventPair ev;
+	CU_TRY(ev.create());
+	const cudaEvent_t e0 = ev.e0, e1 = ev.e1;
 	CU_TRY(cudaEventRecord(e0, s));
 	size_t	 pos = first;
 	const size_t end = first + n;
@@ -1348,8 +1388,6 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 	st = check_device_error(idx, s);
 	float ms = 0.f;
 	cudaEventElapsedTime(&ms, e0, e1);
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
 	if (seconds_out) *seconds_out = ms * 1e-3;
 	if (stats_out)
 	{
