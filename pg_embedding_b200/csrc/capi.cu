@@ -18,6 +18,7 @@
 #include "aux_kernels.cuh"
 #include "bind_kernel.cuh"
 #include "common.cuh"
+#include "scan_tile_kernel.cuh"
 #include "search_kernel.cuh"
 
 using namespace pgemb;
@@ -945,7 +946,7 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	size_t		 chunk = (size_t) 1 << 14;
 	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
 	const size_t qb = nq * dim * 4, db = nq * chunk * 4, kd = nq * k * 4, kl = nq * k * 8, nb = nq * 4;
-	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + up(nb));
+	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + 2 * up(nb));
 	if (st) return st;
 	char	 *base = (char *) idx->d_stage;
 	float	 *d_q = (float *) base;			base += up(qb);
@@ -954,12 +955,21 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	uint32_t *d_sd = (uint32_t *) base;		base += up(kd);
 	uint64_t *d_tl = (uint64_t *) base;		base += up(kl);
 	uint64_t *d_sl = (uint64_t *) base;		base += up(kl);
-	uint32_t *d_tn = (uint32_t *) base;
+	uint32_t *d_tn = (uint32_t *) base;			base += up(nb);
+	float	 *d_qn = (float *) base;
 	cudaStream_t s = idx->stream;
 	CU_TRY(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, s));
 	CU_TRY(cudaMemsetAsync(d_tn, 0, nb, s));
 	const int	   metric = (int) idx->meta.dist_func;
 	const uint32_t lanes = (metric == DIST_L2) ? 8 : 4;
+	// tiled distance step (scan_tile_kernel.cuh): same bits, rows read once per query tile.  Opt-in until measured.
+	const bool tiled = env_int("PGEMB_SCAN_TILED", 0) != 0;
+	if (tiled && metric == DIST_COSINE)
+	{
+		norms_kernel<<<(uint32_t) ((nq * 4 + 127) / 128), 128, 0, s>>>(d_q, (uint32_t) dim, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
+		g_launches++;
+		CU_TRY(cudaGetLastError());
+	}
 	for (size_t r0 = 0; r0 < N; r0 += chunk)
 	{
 		const size_t   nr = (N - r0 < chunk) ? (N - r0) : chunk;
@@ -968,9 +978,20 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 #define SCAN_DIST(MM)                                                                                                              \
 	scan_dist_kernel<MM><<<blocks, threads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, \
 													(uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
-		if (metric == DIST_L2) SCAN_DIST(M_L2);
+#define SCAN_TILE(MM)                                                                                                              \
+	scan_tile_kernel<MM><<<dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), \
+						   kScanThreads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, d_qn,  \
+												 (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
+		if (tiled)
+		{
+			if (metric == DIST_L2) SCAN_TILE(M_L2);
+			else if (metric == DIST_COSINE) SCAN_TILE(M_COS);
+			else SCAN_TILE(M_MAN);
+		}
+		else if (metric == DIST_L2) SCAN_DIST(M_L2);
 		else if (metric == DIST_COSINE) SCAN_DIST(M_COS);
 		else SCAN_DIST(M_MAN);
+#undef SCAN_TILE
 #undef SCAN_DIST
 		scan_select_kernel<<<(uint32_t) ((nq + 3) / 4), 128, 0, s>>>(d_dist, idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k,
 																	 d_td, d_tl, d_tn, d_sd, d_sl);

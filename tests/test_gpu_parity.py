@@ -513,10 +513,12 @@ def test_edge_parameters(pg, oracle_mod, cfg):
 # ---------------------------------------------------------------------------------------------------
 # f3: exact scan (what ORDER BY val <op> q LIMIT k returns without the index; knn.out:63-91)
 # ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tiled", ["0", "1"])
 @pytest.mark.parametrize("metric", METRICS)
-def test_scan_topk_matches_exact_order(pg, oracle_mod, metric):
+def test_scan_topk_matches_exact_order(pg, oracle_mod, metric, tiled, monkeypatch):
+    monkeypatch.setenv("PGEMB_SCAN_TILED", tiled)      # 1: scan_tile_kernel (shared-memory tiles), 0: one pair per thread group
     rng = np.random.default_rng(99)
-    for dims, n, k, levels in ((3, 500, 7, 3), (33, 3000, 64, 0), (128, 20000, 10, 0)):
+    for dims, n, k, levels in ((3, 500, 7, 3), (33, 3000, 64, 0), (128, 20000, 10, 0), (203, 4000, 10, 0), (768, 1500, 10, 0)):
         x = _data(rng, n, dims, levels=levels)
         q = _data(rng, 24, dims, levels=levels)
         if metric == "cosine":
