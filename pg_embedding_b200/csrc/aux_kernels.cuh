@@ -22,6 +22,27 @@ __global__ void norms_kernel(const float *__restrict__ vectors, uint32_t row_f, 
 	if (row < n && sub == 0) norms[first + row] = s;
 }
 
+// ---- invariant check for caller-provided link lists: are the ids of every list distinct? ----------------
+// (Lists written by the bind kernels always are; the traversal may then test-and-set both halves of a list
+// concurrently, search_kernel.cuh `visited_pairs`.)  One warp per node; sets *dup_flag if any list repeats an id.
+__global__ void links_distinct_kernel(const uint32_t *__restrict__ links, uint32_t link_stride, uint32_t maxM, uint32_t first, uint32_t n,
+									  int *__restrict__ dup_flag)
+{
+	const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (w >= n) return;
+	const uint32_t *L = links + (size_t) (first + w) * link_stride;
+	uint32_t		cnt = L[0];
+	if (cnt > maxM) cnt = maxM;
+	bool dup = false;
+	for (uint32_t k = lane; k < cnt; k += 32)
+	{
+		const uint32_t id = L[1 + k];
+		for (uint32_t j = 0; j < k; j++) dup |= (L[1 + j] == id);
+	}
+	if (dup) *dup_flag = 1;
+}
+
 // ---- pair distances: out[i] = dist(a[i] | a[0], b[i]); LANES threads per pair, scalar loads --------
 template <int METRIC>
 __global__ void dist_pairs_kernel(const float *__restrict__ a, const float *__restrict__ b, uint32_t dim, uint32_t a_stride,

@@ -121,6 +121,8 @@ struct pgemb_index
 	uint32_t	 *d_visited = nullptr, *d_vlog = nullptr, *d_vhash = nullptr;
 	uint32_t	  ws_vh = 0;  // allocated hash entries per slot
 	size_t		  l2_persist_max = 0, l2_window_max = 0;
+	// link lists that came from the caller have not been checked for repeated ids yet / result of the last check
+	bool links_checked = true, links_distinct = true;
 	uint64_t	 *d_ovf = nullptr;
 	unsigned int *d_counter = nullptr;
 	int			 *d_error = nullptr;
@@ -265,8 +267,11 @@ static pgemb_status append_common(pgemb_index *idx, size_t n, const coord_t *coo
 							 dim * sizeof(float), n, kind, s));
 	CU_TRY(cudaMemsetAsync(idx->d_links + first * idx->link_stride, 0, n * idx->link_stride * sizeof(uint32_t), s));
 	if (links)
+	{
 		CU_TRY(cudaMemcpy2DAsync(idx->d_links + first * idx->link_stride, idx->link_stride * sizeof(uint32_t), links,
 								 maxM1 * sizeof(uint32_t), maxM1 * sizeof(uint32_t), n, kind, s));
+		idx->links_checked = false;
+	}
 	if (labels)
 		CU_TRY(cudaMemcpyAsync(idx->d_labels + first, labels, n * sizeof(uint64_t), kind, s));
 	else
@@ -336,6 +341,7 @@ extern "C" pgemb_status pgemb_index_append_records(pgemb_index *idx, size_t n, c
 	if (st) return st;
 	CU_TRY(cudaStreamSynchronize(idx->stream));
 	idx->n += n;
+	idx->links_checked = false;
 	return PGEMB_OK;
 }
 
@@ -392,6 +398,7 @@ extern "C" pgemb_status pgemb_index_set_links(pgemb_index *idx, size_t first, si
 	CU_TRY(cudaMemcpy2DAsync(idx->d_links + first * idx->link_stride, idx->link_stride * sizeof(uint32_t), links,
 							 maxM1 * sizeof(uint32_t), maxM1 * sizeof(uint32_t), n, cudaMemcpyHostToDevice, idx->stream));
 	CU_TRY(cudaStreamSynchronize(idx->stream));
+	idx->links_checked = false;
 	return PGEMB_OK;
 }
 
@@ -421,6 +428,7 @@ extern "C" pgemb_status pgemb_index_truncate(pgemb_index *idx)
 {
 	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
 	idx->n = 0;
+	idx->links_checked = idx->links_distinct = true;
 	return PGEMB_OK;
 }
 
@@ -676,6 +684,24 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.row_bytes = idx->row_f * 4u;
 	p.qt_stride = cfg.qt_stride;
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
+	p.visited_pairs = 0;
+	if (env_int("PGEMB_VISITED_PAIRS", 0) != 0)
+	{
+		if (!idx->links_checked)
+		{
+			// caller-provided link lists: one pass to learn whether any list repeats an id (sticky until truncate)
+			const uint32_t nn = (uint32_t) idx->n;
+			int			   dup = 0;
+			CU_TRY(cudaMemsetAsync(idx->d_counter + 3, 0, sizeof(int), s));
+			if (nn) links_distinct_kernel<<<(nn + 3) / 4, 128, 0, s>>>(idx->d_links, idx->link_stride, (uint32_t) idx->meta.maxM, 0u, nn, (int *) (idx->d_counter + 3));
+			g_launches++;
+			CU_TRY(cudaMemcpyAsync(&dup, idx->d_counter + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+			CU_TRY(cudaStreamSynchronize(s));
+			idx->links_distinct = idx->links_distinct && dup == 0;
+			idx->links_checked = true;
+		}
+		p.visited_pairs = idx->links_distinct ? 1u : 0u;
+	}
 	p.off_qt = cfg.off_qt;
 	p.off_qtail = cfg.off_qtail;
 	p.off_pf = cfg.off_pf;

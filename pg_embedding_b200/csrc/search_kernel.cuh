@@ -77,6 +77,7 @@ struct SearchParams
 	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
 	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
 	uint32_t prefetch_links;
+	uint32_t visited_pairs;	 // 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
 	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
 };
@@ -783,6 +784,72 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				__syncwarp();
 				vmode = 1;
 			}
+			if (p.visited_pairs)
+			{
+				// Two 32-id chunks of the list per iteration with BOTH chunks' test-and-set atomics in flight before
+				// the first result is consumed: a full 64-link list costs one L2 round trip instead of two dependent
+				// ones.  Only legal when the ids of a list are distinct (the host guarantees it: links_distinct), so
+				// that the outcome of a chunk's atomics cannot depend on the other chunk's.
+				for (uint32_t base = 0; base < cnt; base += 64)
+				{
+					const uint32_t kA = base + lane, kB = base + 32 + lane;
+					bool		   vA = kA < cnt, vB = kB < cnt;
+					uint32_t	   idA = vA ? pf_links[1 + kA] : 0u, idB = vB ? pf_links[1 + kB] : 0u;
+					if (vA && idA >= p.n_items) { vA = false; *p.error_flag = 1; }
+					if (vB && idB >= p.n_items) { vB = false; *p.error_flag = 1; }
+					bool	 uA = false, uB = false;
+					uint32_t lA = idA, lB = idB;
+					if (vmode == 0)
+					{
+						uint32_t hA = (idA * 2654435761u) >> p.vh_shift, hB = (idB * 2654435761u) >> p.vh_shift;
+						bool	 pA = vA, pB = vB;	// still probing
+						while (pA || pB)
+						{
+							uint32_t oA = 0u, oB = 0u;
+							if (pA) oA = atomicCAS(&vh[hA], kEmpty, idA);
+							if (pB) oB = atomicCAS(&vh[hB], kEmpty, idB);
+							if (pA)
+							{
+								if (oA == kEmpty) { uA = true; lA = hA; pA = false; }
+								else if (oA == idA) pA = false;
+								else hA = (hA + 1) & (H - 1);
+							}
+							if (pB)
+							{
+								if (oB == kEmpty) { uB = true; lB = hB; pB = false; }
+								else if (oB == idB) pB = false;
+								else hB = (hB + 1) & (H - 1);
+							}
+						}
+					}
+					else
+					{
+						const uint32_t bA = 1u << (idA & 31), bB = 1u << (idB & 31);
+						uint32_t	   oA = 0xffffffffu, oB = 0xffffffffu;
+						if (vA) oA = atomicOr(&vis[idA >> 5], bA);
+						if (vB) oB = atomicOr(&vis[idB >> 5], bB);
+						uA = vA && !(oA & bA);
+						uB = vB && !(oB & bB);
+					}
+					const uint32_t mA = __ballot_sync(kFull, uA), mB = __ballot_sync(kFull, uB);
+					const uint32_t cA = (uint32_t) __popc(mA);
+					if (uA)
+					{
+						const uint32_t off = __popc(mA & lt);
+						hop_id[n + off] = idA;
+						if (logn + off < p.vlog_cap) vlog[logn + off] = lA;
+					}
+					if (uB)
+					{
+						const uint32_t off = cA + __popc(mB & lt);
+						hop_id[n + off] = idB;
+						if (logn + off < p.vlog_cap) vlog[logn + off] = lB;
+					}
+					n += cA + (uint32_t) __popc(mB);
+					logn += cA + (uint32_t) __popc(mB);
+				}
+			}
+			else
 			for (uint32_t base = 0; base < cnt; base += 32)
 			{
 				// list position k = base + lane lives in word k + 1

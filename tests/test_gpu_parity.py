@@ -198,6 +198,37 @@ def test_search_identical_to_oracle(pg, oracle_mod, metric, cfg):
     idx.close()
 
 
+@pytest.mark.parametrize("cfg", [SEARCH_CFGS[0], SEARCH_CFGS[5], SEARCH_CFGS[6], SEARCH_CFGS[7]], ids=lambda c: f"d{c[0]}m{c[1]}")
+def test_visited_pairs_mode(pg, oracle_mod, cfg, monkeypatch):
+    """PGEMB_VISITED_PAIRS=1: both 32-id halves of a link list are test-and-set concurrently.  Same results, same
+    traversal counters; a graph whose lists repeat an id must be detected and served by the ordered path."""
+    monkeypatch.setenv("PGEMB_VISITED_PAIRS", "1")
+    dims, m, efc, n, kw, efs = cfg
+    rng = np.random.default_rng(4242 + dims)
+    x = _data(rng, n, dims, **kw)
+    q = _data(rng, 200, dims, **{k: v for k, v in kw.items() if k == "levels"})
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.build(x)
+    links = orc.links()
+    for dup in (False, True):
+        if dup:
+            # repeat an id inside the lists of a few well-connected nodes (positions in different 32-id halves when possible)
+            for node in np.argsort(-links[:, 0].astype(np.int64))[:5]:
+                c = int(links[node, 0])
+                if c >= 2:
+                    links[node, c] = links[node, 1]
+            orc.set_links(links)
+        idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+        idx.append(x, None, links)
+        for coop, nq in (("1", 64), ("0", 200)):
+            with kernel_mode(coop):
+                out = idx.search_batch(q[:nq], efs[-1], want_stats=True)
+            want = orc.search_many(q[:nq], efs[-1], want_counters=True)
+            assert out["labels"].tobytes() == want["labels"].tobytes(), (dup, coop)
+            assert out["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), (dup, coop)
+        idx.close()
+
+
 def test_search_empty_and_tiny(pg, oracle_mod):
     idx = pg.HnswIndex(4, 3, 8, 8, "l2", capacity=8)
     out = idx.search_batch(np.zeros((3, 4), np.float32), 8)
