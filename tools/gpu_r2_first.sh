@@ -1,0 +1,28 @@
+#!/bin/bash
+# First GPU run of round 2 (branch r2-prototypes): validate everything that round 1 could not re-run, then A/B the
+# opt-in prototypes.  One gpurun call, ~6 min of box time.  Output: gpurun_out/r2_first.log (+ bench JSONs).
+mkdir -p gpurun_out
+L=gpurun_out/r2_first.log; : > $L
+say() { echo "== $*" | tee -a $L; }
+say "pytest -m gpu (includes the prototype parametrisations)"
+timeout 900 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider 2>&1 | tail -6 | tee -a $L
+say "smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1 | tee -a $L
+say "bench default"
+timeout 900 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; echo "exit $?" | tee -a $L
+say "bench PGEMB_VISITED_PAIRS=1 (no cpu leg)"
+PGEMB_VISITED_PAIRS=1 timeout 600 python bench.py --no-cpu > gpurun_out/r2_bench_vpairs.json 2> gpurun_out/r2_bench_vpairs.err; echo "exit $?" | tee -a $L
+python - <<'PY' | tee -a $L
+import json
+for f in ("r2_bench_default", "r2_bench_vpairs"):
+    try:
+        d = json.load(open(f"gpurun_out/{f}.json"))
+        print(f, "value", d["value"], "frac", d["roofline"]["frac"], "e2e", d["e2e"]["value"], "parity", d.get("parity"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
+    except Exception as e:
+        print(f, "FAILED", e)
+PY
+say "latency (both kernel modes), default and VISITED_PAIRS"
+timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
+timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
+PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
