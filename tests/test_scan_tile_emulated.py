@@ -1,7 +1,7 @@
 """scan_tile_kernel (the tiled exact-scan distance step) executed on the HOST: the .cuh is compiled by g++ against a
-stand-in <cuda_runtime.h> (tests/emu/fake_cuda) and run with one pthread per CUDA thread, one CTA at a time.  The kernel
-uses only barriers, shared memory and explicitly rounded arithmetic, so this checks its indexing, chunking, tails and
-summation order bit for bit against the oracle without a GPU.  (It says nothing about speed or about nvcc's code.)"""
+stand-in <cuda_runtime.h> (tests/emu/fake_cuda: a small SIMT emulator, warps = OS threads, lanes = fibers) and run one
+CTA at a time.  Checks the kernel's indexing, chunking, tails and summation order bit for bit against the oracle
+without a GPU.  (It says nothing about speed or about nvcc's code generation.)"""
 import ctypes as C
 import os
 import subprocess
@@ -17,7 +17,7 @@ F32P = C.POINTER(C.c_float)
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libscan_emu.so")
     cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "emu", "fake_cuda"),
-           "-o", out, os.path.join(ROOT, "tests", "emu", "scan_tile_emu.cpp")]
+           "-o", out, os.path.join(ROOT, "tests", "emu", "scan_tile_emu.cpp"), os.path.join(ROOT, "tests", "emu", "emu_runtime.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     lib = C.CDLL(out)
