@@ -89,13 +89,6 @@ extern "C" bool hnsw_is_deleted(label_t label) { return ((label >> 48) & 1u) != 
 // ------------------------------------------------------------------------------------------------
 // the device index
 // ------------------------------------------------------------------------------------------------
-struct SearchConfig
-{
-	uint32_t warps = 0, rings = 0, ring_bytes = 0, priv_bytes = 0, row_smem = 0, qt_stride = 0, smem = 0, slots = 0;
-	uint32_t off_pool = 0, off_ring = 0, off_priv = 0;
-	uint32_t off_qt = 0, off_qtail = 0, off_res = 0, off_hopkey = 0, off_acckey = 0, off_evict = 0, off_hopid = 0, off_pf = 0, off_pfbar = 0;
-	uint32_t ef = 0;
-};
 
 struct pgemb_index
 {
@@ -434,100 +427,28 @@ static int env_int(const char *name, int dflt)
 
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+// shared-memory layout + slots/rings per CTA: search_config.h (shared with the host emulation harness in tests/emu)
 static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c, bool coop = false)
 {
-	const int	   metric = (int) idx->meta.dist_func;
-	const uint32_t row_bytes = idx->row_f * 4u;
-	// bank-conflict-free pitch of a row in shared memory for the 4-lanes-per-row mapping:
-	// == 16 (mod 128) for the LDS.32 of cosine/manhattan, == 32 (mod 128) for the LDS.64 of L2
-	const uint32_t resid = (metric == DIST_L2) ? 32u : 16u;
-	uint32_t	   row_smem = row_bytes / 128u * 128u + resid;
-	if (row_smem < row_bytes) row_smem += 128u;
-	const uint32_t maxM = (uint32_t) idx->meta.maxM;
-	const uint32_t hopcap = maxM > 1 ? maxM : 1;
-	const uint32_t max_cta = 232448u;  // 227 KB per CTA
-	// lane-major transposed query: per lane-thread a run of floats padded so that the four runs start
-	// 16 bytes apart modulo 128 (conflict-free LDS.128)
-	const uint32_t dim = (uint32_t) idx->meta.dim;
-	const uint32_t run = (metric == DIST_L2) ? ((dim & ~15u) >> 2) : ((dim & ~3u) >> 2);
-	const uint32_t qt_stride = align_up(run ? run : 1, 32) + 4u;
-
-	SearchConfig t;
-	// ---- a slot's private block ----
-	uint32_t off = 0;
-	t.off_qt = off;			off = align_up(off + 4u * qt_stride * 4u, 16);
-	t.off_qtail = off;		off = align_up(off + 16u * 4u, 16);
-	t.off_res = off;		off += 2u * ef * 8u;
-	t.off_hopkey = off;		off += hopcap * 8u;
-	t.off_acckey = off;		off += hopcap * 8u;
-	t.off_evict = off;		off += hopcap * 8u;
-	t.off_hopid = off;		off = align_up(off + hopcap * 4u, 16);
-	t.off_pf = off;			off = align_up(off + idx->link_stride * 4u, 8);
-	t.off_pfbar = off;		off += 8u;
-	t.priv_bytes = align_up(off, 128);
-	t.ring_bytes = align_up(8u * row_smem, 128);
-	const uint32_t pool_bytes = align_up((uint32_t) sizeof(RingPool), 128);
-	// ---- how many slots (warps) and rings per CTA (= per SM) ----
-	// A slot holds a ring for about `duty` of a hop; throughput ~ min(W / T_hop, R / (duty * T_hop)).
-	const double duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
-	uint32_t	 bestW = 0, bestR = 0;
-	double		 bestv = -1.0;
-	for (uint32_t W = 1; W <= 32; W++)
+	SearchShape sh;
+	sh.metric = (int) idx->meta.dist_func;
+	sh.dim = (uint32_t) idx->meta.dim;
+	sh.row_f = idx->row_f;
+	sh.link_stride = idx->link_stride;
+	sh.maxM = (uint32_t) idx->meta.maxM;
+	sh.ef = ef;
+	sh.sm_count = (uint32_t) idx->sm_count;
+	SearchTuning tu;
+	tu.duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
+	tu.want_warps = env_int("PGEMB_WARPS", 0);
+	tu.want_rings = env_int("PGEMB_RINGS", 0);
+	tu.want_coop_warps = env_int("PGEMB_COOP_WARPS", 0);
+	switch (make_search_config(sh, tu, coop, c))
 	{
-		if (pool_bytes + W * t.priv_bytes + t.ring_bytes > max_cta) break;
-		uint32_t R = (max_cta - pool_bytes - W * t.priv_bytes) / t.ring_bytes;
-		if (R > W) R = W;
-		if (R > kMaxRings) R = kMaxRings;
-		const double v = (W < R / duty) ? (double) W : R / duty;
-		if (v > bestv + 1e-9)
-		{
-			bestv = v;
-			bestW = W;
-			bestR = R;
-		}
+		case 0: return PGEMB_OK;
+		case 1: return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
+		default: return fail(PGEMB_ERR_CAPACITY, "PGEMB_WARPS/PGEMB_RINGS do not fit shared memory");
 	}
-	if (bestW == 0) return fail(PGEMB_ERR_CAPACITY, "search working set does not fit shared memory (dims/ef/maxM too large)");
-	if (coop)
-	{
-		// latency mode: one slot per CTA, every warp owns a ring; no more warps than a full hop has row groups
-		uint32_t R = (max_cta - pool_bytes - t.priv_bytes) / t.ring_bytes;
-		const uint32_t groups = (hopcap + 7u) / 8u;
-		if (R > groups) R = groups;
-		if (R > kMaxRings) R = kMaxRings;
-		const int wantC = env_int("PGEMB_COOP_WARPS", 0);
-		if (wantC > 0 && (uint32_t) wantC < R) R = (uint32_t) wantC;
-		if (R < 1) R = 1;
-		t.warps = R;
-		t.rings = R;
-		t.off_pool = 0;
-		t.off_ring = pool_bytes;
-		t.off_priv = pool_bytes + R * t.ring_bytes;
-		t.smem = t.off_priv + t.priv_bytes;
-		t.row_smem = row_smem;
-		t.qt_stride = qt_stride;
-		t.ef = ef;
-		t.slots = (uint32_t) idx->sm_count;
-		*c = t;
-		return PGEMB_OK;
-	}
-	const int wantW = env_int("PGEMB_WARPS", 0), wantR = env_int("PGEMB_RINGS", 0);
-	if (wantW > 0 && wantW <= 32) bestW = (uint32_t) wantW;
-	if (wantR > 0 && wantR <= (int) kMaxRings) bestR = (uint32_t) wantR;
-	if (bestR > bestW) bestR = bestW;
-	while (bestR > 1 && pool_bytes + bestW * t.priv_bytes + bestR * t.ring_bytes > max_cta) bestR--;
-	if (pool_bytes + bestW * t.priv_bytes + bestR * t.ring_bytes > max_cta) return fail(PGEMB_ERR_CAPACITY, "PGEMB_WARPS/PGEMB_RINGS do not fit shared memory");
-	t.warps = bestW;
-	t.rings = bestR;
-	t.off_pool = 0;
-	t.off_ring = pool_bytes;
-	t.off_priv = pool_bytes + bestR * t.ring_bytes;
-	t.smem = t.off_priv + bestW * t.priv_bytes;
-	t.row_smem = row_smem;
-	t.qt_stride = qt_stride;
-	t.ef = ef;
-	t.slots = bestW * (uint32_t) idx->sm_count;
-	*c = t;
-	return PGEMB_OK;
 }
 
 typedef void (*search_fn_t)(const SearchParams);
@@ -665,25 +586,8 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.exp_cap = exp_cap;
 	p.exp_n_out = d_exp_n;
 	p.error_flag = idx->d_error;
-	p.rings = cfg.rings;
-	p.ring_bytes = cfg.ring_bytes;
-	p.off_pool = cfg.off_pool;
-	p.off_priv = cfg.off_priv;
-	p.priv_bytes = cfg.priv_bytes;
-	p.off_pfbar = cfg.off_pfbar;
-	p.row_smem = cfg.row_smem;
-	p.row_bytes = idx->row_f * 4u;
-	p.qt_stride = cfg.qt_stride;
+	apply_config(p, cfg, idx->row_f);
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
-	p.off_qt = cfg.off_qt;
-	p.off_qtail = cfg.off_qtail;
-	p.off_pf = cfg.off_pf;
-	p.off_ring = cfg.off_ring;
-	p.off_res = cfg.off_res;
-	p.off_hopkey = cfg.off_hopkey;
-	p.off_acckey = cfg.off_acckey;
-	p.off_evict = cfg.off_evict;
-	p.off_hopid = cfg.off_hopid;
 
 	if (vh && idx->l2_window_max > 0 && env_int("PGEMB_L2_PERSIST", 1))
 	{

@@ -46,6 +46,7 @@ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return ((uint32_t) k) >
 __device__ __forceinline__ bool     key_expanded(uint64_t k) { return (k & 1ull) != 0; }
 __device__ __forceinline__ uint64_t key_order(uint64_t k) { return k >> 1; }	// comparable, flag stripped
 
+#ifndef PGEMB_HOST_EMULATION  // tests/emu supplies host versions of the PTX wrappers below
 // ---------------------------------------------------------------------------------------------
 // Blackwell async-copy plumbing: mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP).
 // ---------------------------------------------------------------------------------------------
@@ -100,16 +101,20 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 		: "memory");
 }
 
+#endif  // PGEMB_HOST_EMULATION
+
 // NOTE (kept from the LDGSTS experiments, profiles/README.md): `cp.async.cg.shared.global.L2::cache_hint` miscompiles with
 // ptxas 12.9 for sm_100a -- it emits `LDGSTS [R+UR0], desc[UR1]` whose uniform registers are never written and the
 // instruction traps ("illegal instruction", pinpointed with compute-sanitizer).  Bulk TMA takes the same policy fine.
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+#ifndef PGEMB_HOST_EMULATION
 __device__ __forceinline__ uint32_t lanemask_lt()
 {
 	uint32_t m;
 	asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
 	return m;
 }
+#endif
 
 }  // namespace pgemb

@@ -36,6 +36,7 @@
 #pragma once
 #include "common.cuh"
 #include "dist_exact.cuh"
+#include "search_config.h"  // RingPool, SearchConfig (host-side layout)
 
 namespace pgemb {
 
@@ -81,20 +82,29 @@ struct SearchParams
 	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
 };
 
-struct RingPool
+
+// copy the shared-memory layout chosen by make_search_config into the kernel parameters
+inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_f)
 {
-	// One atomic word is the whole lock state: bit b (b < 16) set = ring b is free; bit 16+b = the phase parity the
-	// next wait on ring b's mbarrier must observe.  A slot learns the parity from the very value its acquiring
-	// atomicCAS observed and hands the updated parity back with atomics before it sets the free bit again, so no
-	// plain shared-memory word is ever shared between slots.
-	uint32_t state;
-	uint32_t pad;
-	uint64_t bar[15];		// one mbarrier per ring
-	// latency mode (COOP): the owner warp publishes the hop's row count (kNone = quit) and |q|^2 here
-	uint32_t coop_n;
-	float	 coop_qn;
-};
-constexpr uint32_t kMaxRings = 15;
+	p.rings = cfg.rings;
+	p.ring_bytes = cfg.ring_bytes;
+	p.off_pool = cfg.off_pool;
+	p.off_priv = cfg.off_priv;
+	p.priv_bytes = cfg.priv_bytes;
+	p.off_pfbar = cfg.off_pfbar;
+	p.row_smem = cfg.row_smem;
+	p.row_bytes = row_f * 4u;
+	p.qt_stride = cfg.qt_stride;
+	p.off_qt = cfg.off_qt;
+	p.off_qtail = cfg.off_qtail;
+	p.off_pf = cfg.off_pf;
+	p.off_ring = cfg.off_ring;
+	p.off_res = cfg.off_res;
+	p.off_hopkey = cfg.off_hopkey;
+	p.off_acckey = cfg.off_acckey;
+	p.off_evict = cfg.off_evict;
+	p.off_hopid = cfg.off_hopid;
+}
 
 constexpr uint32_t kNone = 0xffffffffu;
 constexpr int	   kTPR = 4;		   // lanes cooperating on one row
@@ -233,7 +243,9 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 // and score one 8-row group of the hop at the same time, so a hop costs one DRAM round trip + one row
 // scoring instead of ceil(n/8) of them back to back.  Two named barriers bracket the shared phase; every
 // row is scored by the same score_row4 (same bits).
+#ifndef PGEMB_HOST_EMULATION  // tests/emu supplies the host version
 __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#endif
 
 template <int METRIC>
 __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char *ring, uint64_t *rbar, uint32_t &rpar, uint32_t warp,
@@ -272,7 +284,11 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 template <int METRIC, bool COOP>
 __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
+#ifdef PGEMB_HOST_EMULATION
+	unsigned char *smem = emu::dynamic_smem();
+#else
 	extern __shared__ __align__(128) unsigned char smem[];
+#endif
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t slot = COOP ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;

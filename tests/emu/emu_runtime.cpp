@@ -1,0 +1,109 @@
+// Scheduler and launcher of the host SIMT emulator (see fake_cuda/cuda_runtime.h).  Test infrastructure.
+#include <cuda_runtime.h>
+
+namespace emu {
+
+thread_local Warp *tl_warp = nullptr;
+dim3			   g_block_dim, g_grid_dim;
+pthread_mutex_t	   g_mbar_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static void lane_trampoline()
+{
+	Warp *w = tl_warp;
+	w->body();
+	w = tl_warp;
+	w->lane[w->cur].st = DONE;
+	// returning switches to uc_link (the warp's scheduler)
+}
+
+void run_warp(Warp &w)
+{
+	tl_warp = &w;
+	for (int i = 0; i < 32; i++)
+	{
+		Lane &l = w.lane[i];
+		l.stack = (char *) malloc(kLaneStack);
+		getcontext(&l.ctx);
+		l.ctx.uc_stack.ss_sp = l.stack;
+		l.ctx.uc_stack.ss_size = kLaneStack;
+		l.ctx.uc_link = &w.sched;
+		makecontext(&l.ctx, (void (*)()) lane_trampoline, 0);
+		l.st = RUNNABLE;
+	}
+	int rr = 0, last = -1;
+	for (;;)
+	{
+		int pick = -1;
+		for (int i = 0; i < 32; i++)
+		{
+			const int c = (rr + i) & 31;
+			if (w.lane[c].st == RUNNABLE)
+			{
+				pick = c;
+				break;
+			}
+		}
+		if (pick >= 0)
+		{
+			if (pick == last) sched_yield();  // a lone spinning lane: give the other warps' threads the core
+			last = pick;
+			w.cur = pick;
+			rr = pick + 1;
+			swapcontext(&w.sched, &w.lane[pick].ctx);
+			continue;
+		}
+		int live = 0;
+		for (int i = 0; i < 32; i++) live += (w.lane[i].st != DONE);
+		if (live == 0) break;
+		// every live lane waits at a collective: exchange and release
+		if (w.kind == K_CTA_BAR) pthread_barrier_wait(&w.cta->bars[w.bar_id & 15]);
+		for (int i = 0; i < 32; i++)
+		{
+			w.present[i] = (w.lane[i].st == AT_COLL);
+			w.snap[i] = w.lane[i].xchg;
+			if (w.lane[i].st == AT_COLL) w.lane[i].st = RUNNABLE;
+		}
+		rr = 0;
+		last = -1;
+	}
+	for (int i = 0; i < 32; i++) free(w.lane[i].stack);
+	tl_warp = nullptr;
+}
+
+void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std::function<void()> &fn)
+{
+	g_grid_dim = grid;
+	g_block_dim = dim3(block_threads);
+	const unsigned nwarps = (block_threads + 31) / 32;
+	for (unsigned by = 0; by < grid.y; by++)
+		for (unsigned bx = 0; bx < grid.x; bx++)
+		{
+			Cta cta;
+			cta.nwarps = nwarps;
+			cta.block_idx = dim3(bx, by);
+			for (auto &b : cta.bars) pthread_barrier_init(&b, nullptr, nwarps);
+			cta.dyn_smem = nullptr;
+			if (dyn_smem_bytes)
+			{
+				cta.dyn_smem = (unsigned char *) aligned_alloc(128, (dyn_smem_bytes + 127) / 128 * 128);
+				memset(cta.dyn_smem, 0xAA, dyn_smem_bytes);	// shared memory starts uninitialised on the device too
+			}
+			std::vector<std::thread> th;
+			std::vector<Warp *>		 warps(nwarps);
+			for (unsigned wi = 0; wi < nwarps; wi++)
+			{
+				Warp *w = new Warp();
+				warps[wi] = w;
+				w->cta = &cta;
+				w->body = fn;
+				for (int l = 0; l < 32; l++) w->lane[l].tid = dim3(wi * 32 + l);
+				th.emplace_back([w]() { run_warp(*w); });
+			}
+			for (auto &t : th) t.join();
+			for (auto *w : warps) delete w;
+			for (auto &b : cta.bars) pthread_barrier_destroy(&b);
+			free(cta.dyn_smem);
+		}
+}
+
+}  // namespace emu

@@ -1,0 +1,272 @@
+// Host stand-in for <cuda_runtime.h> (tests/emu): compiles the .cuh kernels with g++ and runs them on the CPU.
+//
+// Execution model -- a small SIMT emulator, enough for this repo's kernels:
+//   * a CTA is a group of OS threads, one per WARP; the 32 lanes of a warp are user-level fibers (ucontext) of that
+//     thread.  A lane runs until it reaches a warp collective (__syncwarp, __ballot_sync, __shfl*_sync,
+//     __match_any_sync), a CTA barrier (__syncthreads, bar.sync) or a spin-wait hook (mbarrier wait, __nanosleep); the
+//     warp's scheduler then runs the next lane.  When every live lane waits at a collective the values are exchanged
+//     and all lanes resume.  Warps of a CTA really run concurrently, so shared-memory locks and atomics between warps
+//     are exercised; CTAs of a grid run one after another.
+//   * shared memory: `__shared__` arrays become function-local statics, dynamic shared memory is a per-CTA buffer.
+//   * mbarrier + 1-D bulk TMA: the copy is performed synchronously by the issuing lane and accounted on the barrier
+//     (expect-tx / complete-tx / phase parity) -- one of the legal hardware schedules.
+//   * arithmetic: the _rn intrinsics are plain IEEE operations (compile with -ffp-contract=off, no fast-math).
+// It checks LOGIC (indexing, protocols, summation order), not memory-model races inside a warp and not speed.
+// Test infrastructure only; never part of the product build.
+#pragma once
+#define PGEMB_HOST_EMULATION 1
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <pthread.h>
+#include <sched.h>
+#include <thread>
+#include <ucontext.h>
+#include <vector>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct dim3
+{
+	unsigned x = 1, y = 1, z = 1;
+	dim3() {}
+	dim3(unsigned a, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+namespace emu {
+
+constexpr size_t kLaneStack = 192 * 1024;
+enum State { RUNNABLE, AT_COLL, DONE };
+enum Kind { K_WARP, K_CTA_BAR };
+
+struct Cta
+{
+	pthread_barrier_t bars[16];
+	unsigned		  nwarps = 0;
+	unsigned char	 *dyn_smem = nullptr;
+	dim3			  block_idx;
+};
+
+struct Lane
+{
+	ucontext_t ctx;
+	char	  *stack = nullptr;
+	State	   st = RUNNABLE;
+	uint64_t   xchg = 0;
+	dim3	   tid;
+};
+
+struct Warp
+{
+	ucontext_t			  sched;
+	Lane				  lane[32];
+	int					  cur = 0;
+	Cta					 *cta = nullptr;
+	int					  kind = K_WARP, bar_id = 0;
+	uint64_t			  snap[32];
+	bool				  present[32];
+	std::function<void()> body;
+};
+
+extern thread_local Warp *tl_warp;
+extern dim3				   g_block_dim, g_grid_dim;
+extern pthread_mutex_t	   g_mbar_mu;
+
+inline Warp &W() { return *tl_warp; }
+inline Lane &L() { return tl_warp->lane[tl_warp->cur]; }
+inline int	 lane_index() { return tl_warp->cur; }
+
+inline void collective(int kind, uint64_t v, int bar_id = 0)
+{
+	Warp &w = W();
+	Lane &l = w.lane[w.cur];
+	l.xchg = v;
+	l.st = AT_COLL;
+	w.kind = kind;
+	w.bar_id = bar_id;
+	swapcontext(&l.ctx, &w.sched);
+}
+// spin-wait hook: let the other lanes of the warp (and the other warps' threads) run
+inline void yield()
+{
+	Warp &w = W();
+	Lane &l = w.lane[w.cur];
+	swapcontext(&l.ctx, &w.sched);
+}
+inline unsigned char *dynamic_smem() { return W().cta->dyn_smem; }
+
+void run_warp(Warp &w);	 // scheduler loop (emu_runtime.cpp)
+
+// Run kernel body `fn` (called once per CUDA thread) over a grid; blocks are executed one after another.
+void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std::function<void()> &fn);
+
+}  // namespace emu
+
+#define threadIdx (emu::L().tid)
+#define blockIdx (emu::W().cta->block_idx)
+#define blockDim (emu::g_block_dim)
+#define gridDim (emu::g_grid_dim)
+
+// ---- barriers and warp collectives ------------------------------------------------------------------
+static inline void __syncthreads() { emu::collective(emu::K_CTA_BAR, 0, 0); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::collective(emu::K_WARP, 0); }
+static inline unsigned __ballot_sync(unsigned, int pred)
+{
+	emu::collective(emu::K_WARP, pred ? 1u : 0u);
+	const emu::Warp &w = emu::W();
+	unsigned		 r = 0;
+	for (int i = 0; i < 32; i++)
+		if (w.present[i] && w.snap[i]) r |= 1u << i;
+	return r;
+}
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32)
+{
+	uint64_t b = 0;
+	memcpy(&b, &v, sizeof(T));
+	emu::collective(emu::K_WARP, b);
+	const emu::Warp &w = emu::W();
+	const int		 base = w.cur / width * width;
+	T				 out;
+	memcpy(&out, &w.snap[base + ((src % width) + width) % width], sizeof(T));
+	return out;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32)
+{
+	uint64_t b = 0;
+	memcpy(&b, &v, sizeof(T));
+	emu::collective(emu::K_WARP, b);
+	const emu::Warp &w = emu::W();
+	int				 s = w.cur ^ lanemask;
+	if (s / width != w.cur / width) s = w.cur;
+	T out;
+	memcpy(&out, &w.snap[s], sizeof(T));
+	return out;
+}
+static inline unsigned __match_any_sync(unsigned, unsigned v)
+{
+	emu::collective(emu::K_WARP, v);
+	const emu::Warp &w = emu::W();
+	unsigned		 r = 0;
+	for (int i = 0; i < 32; i++)
+		if (w.present[i] && (unsigned) w.snap[i] == v) r |= 1u << i;
+	return r;
+}
+static inline void coop_bar(int id, uint32_t) { emu::collective(emu::K_CTA_BAR, 0, id); }
+
+// ---- bit tricks, conversions, arithmetic ------------------------------------------------------------
+static inline int	   __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int	   __ffs(unsigned v) { return __builtin_ffs((int) v); }
+static inline int	   __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float	   __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float	   __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline float	   __fadd_rn(float a, float b) { return a + b; }
+static inline float	   __fsub_rn(float a, float b) { return a - b; }
+static inline float	   __fmul_rn(float a, float b) { return a * b; }
+static inline float	   __fsqrt_rn(float a) { return sqrtf(a); }
+static inline double   __dsqrt_rn(double a) { return sqrt(a); }
+static inline double   __ddiv_rn(double a, double b) { return a / b; }
+static inline float	   __double2float_rn(double a) { return (float) a; }
+using std::max;
+using std::min;
+
+// ---- memory -----------------------------------------------------------------------------------------
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+static inline void					  __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void					  __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline void __nanosleep(unsigned)
+{
+	sched_yield();
+	emu::yield();
+}
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicXor(unsigned *p, unsigned v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
+{
+	unsigned e = cmp;
+	__atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+	return e;
+}
+static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t) p; }
+
+// ---- mbarrier + 1-D bulk TMA (host versions of the wrappers common.cuh guards out) --------------------
+// 64-bit barrier word: [0] phase parity, [1..15] pending arrivals, [16..30] arrival count, [32..63] tx bytes (signed)
+namespace emu {
+struct BarView { uint32_t w0; int32_t tx; };
+inline void bar_complete_if_done(BarView &v)
+{
+	if (((v.w0 >> 1) & 0x7fffu) == 0 && v.tx == 0)
+	{
+		const uint32_t init = (v.w0 >> 16) & 0x7fffu;
+		v.w0 = ((v.w0 & 1u) ^ 1u) | (init << 1) | (init << 16);
+	}
+}
+}  // namespace emu
+static inline uint32_t smem_u32(const void *) { return 0; }
+static inline void	   mbar_init(uint64_t *bar, uint32_t count)
+{
+	emu::BarView v{(count << 1) | (count << 16), 0};
+	memcpy(bar, &v, 8);
+}
+static inline void fence_mbar_init() {}
+static inline void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	pthread_mutex_lock(&emu::g_mbar_mu);
+	emu::BarView v;
+	memcpy(&v, bar, 8);
+	v.tx += (int32_t) bytes;
+	const uint32_t pend = ((v.w0 >> 1) & 0x7fffu) - 1u;
+	v.w0 = (v.w0 & ~(0x7fffu << 1)) | ((pend & 0x7fffu) << 1);
+	emu::bar_complete_if_done(v);
+	memcpy(bar, &v, 8);
+	pthread_mutex_unlock(&emu::g_mbar_mu);
+}
+static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+	pthread_mutex_lock(&emu::g_mbar_mu);
+	emu::BarView v;
+	memcpy(&v, bar, 8);
+	pthread_mutex_unlock(&emu::g_mbar_mu);
+	if ((v.w0 & 1u) != (parity & 1u)) return true;
+	emu::yield();
+	return false;
+}
+static inline void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	while (!mbar_try_wait(bar, parity)) {}
+}
+static inline uint64_t l2_policy_evict_first() { return 0; }
+static inline uint64_t l2_policy_evict_last() { return 0; }
+static inline void	   tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t)
+{
+	if ((bytes & 15u) || ((uintptr_t) dst & 15u) || ((uintptr_t) src & 15u))
+	{
+		fprintf(stderr, "emu: cp.async.bulk needs 16-byte aligned addresses and size (dst %p src %p bytes %u)\n", dst, src, bytes);
+		abort();
+	}
+	memcpy(dst, src, bytes);
+	pthread_mutex_lock(&emu::g_mbar_mu);
+	emu::BarView v;
+	memcpy(&v, bar, 8);
+	v.tx -= (int32_t) bytes;
+	emu::bar_complete_if_done(v);
+	memcpy(bar, &v, 8);
+	pthread_mutex_unlock(&emu::g_mbar_mu);
+}
+static inline uint32_t lanemask_lt() { return (1u << (emu::L().tid.x & 31u)) - 1u; }

@@ -1,0 +1,107 @@
+// pgemb::search_kernel (throughput and latency mode) on the host SIMT emulator (tests/emu).
+// The harness plays the part of capi.cu's launch_search: same make_search_config, same parameter block.
+#include <cuda_runtime.h>  // the stand-in in tests/emu/fake_cuda
+
+#include "../../pg_embedding_b200/csrc/search_kernel.cuh"
+
+using namespace pgemb;
+
+template <int METRIC, bool COOP> static void go(const SearchParams &p, unsigned grid, unsigned warps, size_t smem)
+{
+	emu::launch(dim3(grid), warps * 32, smem, [=]() { search_kernel<METRIC, COOP>(p); });
+}
+
+// returns 0 on success, >0 = make_search_config's code, -1 = bad metric; *error_out = the kernel's sticky error flag
+extern "C" int emu_search(int metric, int coop, const float *vectors, const uint32_t *links, const uint64_t *labels, const float *norms,
+						  uint32_t n_items, uint32_t dim, uint32_t row_f, uint32_t link_stride, uint32_t maxM, const float *queries,
+						  uint32_t nq, uint32_t ef, int raw_mode, uint64_t *labels_out, float *dists_out, uint32_t *ids_out,
+						  int32_t *n_out, uint32_t *stats_out, uint32_t want_warps, uint32_t want_rings, uint32_t grid, uint32_t vh_size,
+						  uint32_t visited_pairs, int *error_out)
+{
+	SearchShape sh;
+	sh.metric = metric;
+	sh.dim = dim;
+	sh.row_f = row_f;
+	sh.link_stride = link_stride;
+	sh.maxM = maxM;
+	sh.ef = ef;
+	sh.sm_count = grid;
+	SearchTuning tu;
+	tu.want_warps = (int) want_warps;
+	tu.want_rings = (int) want_rings;
+	tu.want_coop_warps = (int) want_warps;
+	SearchConfig cfg;
+	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
+	if (rc) return rc;
+	const uint32_t slots = coop ? grid : grid * cfg.warps;
+	const uint32_t vis_words = (n_items + 31) / 32 + 1;
+	const uint32_t vlog_cap = n_items < 32768 ? n_items + 1 : 32768;
+	std::vector<uint32_t> visited((size_t) slots * vis_words, 0u), vlog((size_t) slots * vlog_cap, 0u);
+	std::vector<uint32_t> vhash((size_t) slots * (vh_size ? vh_size : 1), 0xffffffffu);
+	std::vector<uint64_t> ovf((size_t) slots * ef, 0ull);
+	unsigned int counter = 0;
+	int			 err = 0;
+
+	SearchParams p;
+	memset(&p, 0, sizeof(p));
+	p.vectors = vectors;
+	p.links = links;
+	p.labels = labels;
+	p.norms = norms;
+	p.n_items = n_items;
+	p.dim = dim;
+	p.row_f = row_f;
+	p.link_stride = link_stride;
+	p.maxM = maxM;
+	p.entry = 0;
+	p.queries = queries;
+	p.nq = nq;
+	p.q_stride = dim;
+	p.ef = ef;
+	p.raw_mode = raw_mode ? 1u : 0u;
+	p.labels_out = labels_out;
+	p.dists_out = dists_out;
+	p.ids_out = ids_out;
+	p.n_out = n_out;
+	p.stats_out = stats_out;
+	p.visited = visited.data();
+	p.vlog = vlog.data();
+	p.ovf = ovf.data();
+	p.vhash = vhash.data();
+	p.vis_words = vis_words;
+	p.vlog_cap = vlog_cap;
+	p.vh_size = vh_size;
+	{
+		uint32_t lg = 0;
+		while ((1u << lg) < vh_size) lg++;
+		p.vh_shift = 32u - lg;
+	}
+	p.counter = &counter;
+	p.error_flag = &err;
+	p.prefetch_links = 1;
+#ifdef PGEMB_HAS_VISITED_PAIRS
+	p.visited_pairs = visited_pairs;
+#else
+	(void) visited_pairs;
+#endif
+	apply_config(p, cfg, row_f);
+	unsigned g = nq < grid ? nq : grid;
+	if (g == 0) g = 1;
+	switch (metric * 2 + (coop ? 1 : 0))
+	{
+		case 0: go<M_L2, false>(p, g, cfg.warps, cfg.smem); break;
+		case 1: go<M_L2, true>(p, g, cfg.warps, cfg.smem); break;
+		case 2: go<M_COS, false>(p, g, cfg.warps, cfg.smem); break;
+		case 3: go<M_COS, true>(p, g, cfg.warps, cfg.smem); break;
+		case 4: go<M_MAN, false>(p, g, cfg.warps, cfg.smem); break;
+		case 5: go<M_MAN, true>(p, g, cfg.warps, cfg.smem); break;
+		default: return -1;
+	}
+	// the visited sets must be left clean for the next launch
+	for (uint32_t v : visited)
+		if (v != 0u) err |= 0x100;
+	for (uint32_t v : vhash)
+		if (v != 0xffffffffu) err |= 0x200;
+	if (error_out) *error_out = err;
+	return 0;
+}
