@@ -284,11 +284,7 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 template <int METRIC, bool COOP>
 __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
-#ifdef PGEMB_HOST_EMULATION
-	unsigned char *smem = emu::dynamic_smem();
-#else
-	extern __shared__ __align__(128) unsigned char smem[];
-#endif
+	PGEMB_DYNAMIC_SMEM(smem, 128);
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t slot = COOP ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;
