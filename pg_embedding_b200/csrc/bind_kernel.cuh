@@ -24,7 +24,9 @@
 // sorting (target,source) pairs and letting the CTA of each segment head apply its segment sequentially
 // -- for n_new == 1 this is exactly one reference insert.
 #pragma once
+#ifndef PGEMB_HOST_EMULATION
 #include <cub/cub.cuh>
+#endif
 
 #include "common.cuh"
 #include "dist_exact.cuh"
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(kBindThreads) select_kernel(GraphView g, const
 															   const int32_t *__restrict__ cand_n, uint32_t ef,
 															   uint64_t *__restrict__ pairs /* [n_new][M] */)
 {
-	extern __shared__ __align__(16) unsigned char sm[];
+	PGEMB_DYNAMIC_SMEM(sm, 16);
 	uint64_t	  *cand = reinterpret_cast<uint64_t *>(sm);			// ef
 	uint64_t	  *kept = cand + ef;								// max(M,1)
 	uint32_t	  *ord = reinterpret_cast<uint32_t *>(kept + (g.M ? g.M : 1));	// ef
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(kBindThreads) select_kernel(GraphView g, const
 template <int METRIC>
 __global__ void __launch_bounds__(kBindThreads) backlink_kernel(GraphView g, const uint64_t *__restrict__ pairs_sorted, uint32_t n_pairs)
 {
-	extern __shared__ __align__(16) unsigned char sm[];
+	PGEMB_DYNAMIC_SMEM(sm, 16);
 	const uint32_t C1 = g.maxM + 1;
 	uint64_t	  *unsorted = reinterpret_cast<uint64_t *>(sm);	 // C1
 	uint64_t	  *cand = unsorted + C1;						 // C1

@@ -436,6 +436,7 @@ static int env_int(const char *name, int dflt)
 
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
+// shared-memory layout + slots/rings per CTA: search_config.h (shared with the host emulation harness in tests/emu)
 static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c, bool coop = false)
 {
 	SearchShape sh;

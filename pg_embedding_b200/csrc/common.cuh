@@ -6,6 +6,13 @@
 
 #include "../../include/pgemb_b200.h"
 
+// dynamic shared memory of the running CTA (the host emulation in tests/emu hands out a per-CTA buffer instead)
+#ifdef PGEMB_HOST_EMULATION
+#define PGEMB_DYNAMIC_SMEM(name, alignment) unsigned char *name = emu::dynamic_smem()
+#else
+#define PGEMB_DYNAMIC_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
+#endif
+
 namespace pgemb {
 
 constexpr int kWarp = 32;

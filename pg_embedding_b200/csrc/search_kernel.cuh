@@ -245,7 +245,7 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 // and score one 8-row group of the hop at the same time, so a hop costs one DRAM round trip + one row
 // scoring instead of ceil(n/8) of them back to back.  Two named barriers bracket the shared phase; every
 // row is scored by the same score_row4 (same bits).
-#ifndef PGEMB_HOST_EMULATION
+#ifndef PGEMB_HOST_EMULATION  // tests/emu supplies the host version
 __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif
 
@@ -286,11 +286,7 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 template <int METRIC, bool COOP>
 __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
-#ifdef PGEMB_HOST_EMULATION
-	unsigned char *smem = emu::dynamic_smem();
-#else
-	extern __shared__ __align__(128) unsigned char smem[];
-#endif
+	PGEMB_DYNAMIC_SMEM(smem, 128);
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
 	const uint32_t slot = COOP ? blockIdx.x : blockIdx.x * (blockDim.x >> 5) + warp;

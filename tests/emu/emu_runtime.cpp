@@ -57,10 +57,24 @@ void run_warp(Warp &w)
 		if (live == 0) break;
 		// every live lane waits at a collective: exchange and release
 		if (w.kind == K_CTA_BAR) pthread_barrier_wait(&w.cta->bars[w.bar_id & 15]);
+		unsigned cta_or = 0;
+		if (w.kind == K_CTA_OR)
+		{
+			// __syncthreads_or: OR over the warp, then over the CTA (two barriers: publish, then everybody has read)
+			unsigned mine = 0;
+			for (int i = 0; i < 32; i++)
+				if (w.lane[i].st == AT_COLL && w.lane[i].xchg) mine = 1;
+			const int ph = w.or_phase;
+			w.or_phase ^= 1;
+			if (mine) __atomic_fetch_or(&w.cta->or_acc[ph], 1u, __ATOMIC_SEQ_CST);
+			pthread_barrier_wait(&w.cta->bars[0]);
+			cta_or = __atomic_load_n(&w.cta->or_acc[ph], __ATOMIC_SEQ_CST);
+			if (pthread_barrier_wait(&w.cta->bars[0]) == PTHREAD_BARRIER_SERIAL_THREAD) __atomic_store_n(&w.cta->or_acc[ph], 0u, __ATOMIC_SEQ_CST);
+		}
 		for (int i = 0; i < 32; i++)
 		{
 			w.present[i] = (w.lane[i].st == AT_COLL);
-			w.snap[i] = w.lane[i].xchg;
+			w.snap[i] = (w.kind == K_CTA_OR) ? cta_or : w.lane[i].xchg;
 			if (w.lane[i].st == AT_COLL) w.lane[i].st = RUNNABLE;
 		}
 		rr = 0;

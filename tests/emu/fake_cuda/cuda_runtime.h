@@ -51,12 +51,13 @@ namespace emu {
 
 constexpr size_t kLaneStack = 192 * 1024;
 enum State { RUNNABLE, AT_COLL, DONE };
-enum Kind { K_WARP, K_CTA_BAR };
+enum Kind { K_WARP, K_CTA_BAR, K_CTA_OR };
 
 struct Cta
 {
 	pthread_barrier_t bars[16];
 	unsigned		  nwarps = 0;
+	unsigned		  or_acc[2] = {0, 0};  // __syncthreads_or accumulators, double-buffered by phase
 	unsigned char	 *dyn_smem = nullptr;
 	dim3			  block_idx;
 };
@@ -76,7 +77,7 @@ struct Warp
 	Lane				  lane[32];
 	int					  cur = 0;
 	Cta					 *cta = nullptr;
-	int					  kind = K_WARP, bar_id = 0;
+	int					  kind = K_WARP, bar_id = 0, or_phase = 0;
 	uint64_t			  snap[32];
 	bool				  present[32];
 	std::function<void()> body;
@@ -123,6 +124,11 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 
 // ---- barriers and warp collectives ------------------------------------------------------------------
 static inline void __syncthreads() { emu::collective(emu::K_CTA_BAR, 0, 0); }
+static inline int  __syncthreads_or(int pred)
+{
+	emu::collective(emu::K_CTA_OR, pred ? 1u : 0u, 0);
+	return (int) emu::W().snap[emu::W().cur];  // the scheduler stores the CTA-wide result in every lane's slot
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::collective(emu::K_WARP, 0); }
 static inline unsigned __ballot_sync(unsigned, int pred)
 {
@@ -156,6 +162,7 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lanemas
 	memcpy(&out, &w.snap[s], sizeof(T));
 	return out;
 }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 static inline unsigned __match_any_sync(unsigned, unsigned v)
 {
 	emu::collective(emu::K_WARP, v);
@@ -197,6 +204,12 @@ static inline void __nanosleep(unsigned)
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicXor(unsigned *p, unsigned v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicMin(unsigned *p, unsigned v)
+{
+	unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+	while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+	return old;
+}
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
 {
 	unsigned e = cmp;
@@ -204,6 +217,9 @@ static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
 	return e;
 }
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t) p; }
+// the few runtime calls that appear in headers shared with host code
+typedef int cudaError_t;
+static inline cudaError_t cudaFree(void *) { return 0; }
 
 // ---- mbarrier + 1-D bulk TMA (host versions of the wrappers common.cuh guards out) --------------------
 // 64-bit barrier word: [0] phase parity, [1..15] pending arrivals, [16..30] arrival count, [32..63] tx bytes (signed)

@@ -9,7 +9,19 @@ import subprocess
 import numpy as np
 import pytest
 
-from test_scan_tile_emulated import sqnorm_lane_order
+
+
+def sqnorm_lane_order(v):
+    """|v|^2 in the cosine lane order (4 lane-strided partial sums, (s0+s2)+(s1+s3), scalar tail): distfunc.c:141-142 as built."""
+    v = v.astype(np.float32)
+    main = v.size & ~3
+    s = np.zeros(4, np.float32)
+    for i in range(0, main, 4):
+        s = s + v[i:i + 4] * v[i:i + 4]
+    res = np.float32(np.float32(s[0] + s[2]) + np.float32(s[1] + s[3]))
+    for e in range(main, v.size):
+        res = np.float32(res + np.float32(v[e] * v[e]))
+    return res
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRIC_ID = {"l2": 0, "cosine": 1, "manhattan": 2}
@@ -57,7 +69,7 @@ CASES = [
     ("cosine", 16, 4, 20, 300, 0, 8, 8),
     ("manhattan", 33, 5, 20, 250, 0, 12, 6),  # dims % 4 != 0: padded rows, scalar tails
     ("l2", 40, 20, 24, 200, 0, 16, 5),       # maxM = 40: more than one 32-id chunk per link list, 5 row groups per hop
-    ("cosine", 24, 50, 16, 260, 0, 10, 4),   # maxM = 100: several 64-id iterations of the paired visited test
+    ("cosine", 24, 50, 16, 260, 0, 10, 4),   # maxM = 100: four 32-id chunks per link list, 13 row groups per hop
 ]
 
 
@@ -90,3 +102,39 @@ def test_search_kernel_emulated_matches_oracle(emu, oracle_mod, case, coop, pair
         k = int(got["n"][qi])
         dref = oracle_mod.dist_many("port", metric, q[qi], x[got["ids"][qi, :k]]) if k else np.zeros(0, np.float32)
         assert got["dists"][qi, :k].tobytes() == dref.tobytes()
+
+
+BIND_CASES = [
+    # metric, dims, m, efC, n, levels
+    ("l2", 3, 3, 8, 70, 3),          # ties + duplicates: equal-distance scan order of the heuristic, full lists re-pruned
+    ("cosine", 16, 4, 12, 60, 0),
+    ("manhattan", 9, 2, 6, 50, 0),   # M = 2, maxM = 4: lists fill quickly, re-prune path on most inserts
+]
+
+
+@pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
+@pytest.mark.parametrize("case", BIND_CASES, ids=[f"{c[0]}-d{c[1]}m{c[2]}" for c in BIND_CASES])
+def test_bind_kernels_emulated_match_oracle(emu, oracle_mod, case, coop):
+    """n x hnsw_bind_point on the emulator (traversal in raw mode + select_kernel + backlink_kernel per insert):
+    every link list must equal the oracle's after the same inserts."""
+    metric, dims, m, efc, n, levels = case
+    rng = np.random.default_rng(77 + dims)
+    x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
+    if metric == "cosine":
+        x = x + 1.0
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+    orc.build(x)
+    want = orc.links()
+    maxm = 2 * m
+    row_f = (dims + 3) & ~3
+    ls = (maxm + 1 + 3) & ~3
+    xv = np.zeros((n, row_f), np.float32); xv[:, :dims] = x
+    lk = np.zeros((n, ls), np.uint32)
+    norms = np.array([sqnorm_lane_order(x[i]) for i in range(n)], np.float32) if metric == "cosine" else np.zeros(n, np.float32)
+    err = C.c_int(0)
+    rc = emu.emu_bind_sequence(METRIC_ID[metric], coop, _p(xv, C.c_float), _p(lk, C.c_uint32), _p(norms, C.c_float), C.c_uint32(n), C.c_uint32(dims),
+                               C.c_uint32(row_f), C.c_uint32(ls), C.c_uint32(m), C.c_uint32(maxm), C.c_uint32(efc), C.c_uint32(0), C.c_uint32(n), C.byref(err))
+    assert rc == 0 and err.value == 0, (rc, err.value)
+    got = lk[:, :maxm + 1]
+    bad = np.flatnonzero((got != want).any(1))
+    assert bad.size == 0, f"link lists differ at nodes {bad[:8]}: {got[bad[0]]} vs {want[bad[0]]}"
