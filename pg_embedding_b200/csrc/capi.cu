@@ -452,6 +452,7 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	tu.want_warps = env_int("PGEMB_WARPS", 0);
 	tu.want_rings = env_int("PGEMB_RINGS", 0);
 	tu.want_coop_warps = env_int("PGEMB_COOP_WARPS", 0);
+	tu.smem_visited = env_int("PGEMB_SMEM_VISITED", 0);  // opt-in prototype: entries of the latency mode's shared-memory visited set
 	switch (make_search_config(sh, tu, coop, c))
 	{
 		case 0: return PGEMB_OK;

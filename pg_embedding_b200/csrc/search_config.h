@@ -27,6 +27,7 @@ struct SearchConfig
 	uint32_t off_pool = 0, off_ring = 0, off_priv = 0;
 	uint32_t off_qt = 0, off_qtail = 0, off_res = 0, off_hopkey = 0, off_acckey = 0, off_evict = 0, off_hopid = 0, off_pf = 0, off_pfbar = 0;
 	uint32_t ef = 0;
+	uint32_t off_vhs = 0, vhs_entries = 0;	// latency mode: visited hash set in shared memory
 };
 
 struct SearchShape
@@ -41,6 +42,7 @@ struct SearchTuning
 	int	   want_warps = 0;	   // overrides (0 = choose)
 	int	   want_rings = 0;
 	int	   want_coop_warps = 0;
+	int	   smem_visited = 0;	  // latency mode: entries (power of two) of the shared-memory visited set to try for, 0 = off
 };
 
 inline uint32_t cfg_align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
@@ -116,6 +118,18 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 		t.off_ring = pool_bytes;
 		t.off_priv = pool_bytes + R * t.ring_bytes;
 		t.smem = t.off_priv + t.priv_bytes;
+		if (tu.smem_visited > 0)
+		{
+			// whatever is left of the CTA's 227 KB, as a power-of-two table of u32 (never below 1024 entries)
+			uint32_t e = 1024;
+			while (e * 2u <= (uint32_t) tu.smem_visited && t.smem + e * 2u * 4u <= max_cta) e *= 2u;
+			if (t.smem + e * 4u <= max_cta)
+			{
+				t.off_vhs = t.smem;
+				t.vhs_entries = e;
+				t.smem += e * 4u;
+			}
+		}
 		t.row_smem = row_smem;
 		t.qt_stride = qt_stride;
 		t.ef = ef;

@@ -70,6 +70,7 @@ struct SearchParams
 	uint32_t	 *vhash;		 // [slots][vh_size]     open-addressing visited set, 0xffffffff = empty
 	uint32_t	  vis_words, vlog_cap;
 	uint32_t	  vh_size, vh_shift;  // vh_size = 2^k entries (0: bitmap only), hash = (id * 2654435761) >> vh_shift
+	uint32_t	  off_vhs, vhs_entries;	 // latency mode: the hash set lives in the CTA's shared memory (2^k entries, 0 = use vhash)
 	unsigned int *counter;		 // work-stealing query counter
 	const unsigned int *avail;	 // optional: number of queries whose data has landed (host API streams them in while the kernel runs)
 	int			 *error_flag;	 // sticky: 1 = bad link id / count, 2 = overflow buffer exceeded
@@ -88,6 +89,8 @@ struct SearchParams
 // copy the shared-memory layout chosen by make_search_config into the kernel parameters
 inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_f)
 {
+	p.off_vhs = cfg.off_vhs;
+	p.vhs_entries = cfg.vhs_entries;
 	p.rings = cfg.rings;
 	p.ring_bytes = cfg.ring_bytes;
 	p.off_pool = cfg.off_pool;
@@ -309,11 +312,15 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	const uint32_t ef = p.ef;
 	const int	   dim = (int) p.dim;
 	const int	   main_n = main_len<METRIC>(dim);
-	const uint32_t H = p.vh_size;
+	// latency mode keeps the open-addressing visited set in shared memory when the CTA has room for it: a hop's
+	// test-and-set round then costs shared-memory atomics instead of L2 round trips
+	const bool	   vh_shared = COOP && p.vhs_entries != 0u;
+	const uint32_t H = vh_shared ? p.vhs_entries : p.vh_size;
+	const uint32_t vh_shift = vh_shared ? (32u - (uint32_t) __popc(p.vhs_entries - 1u)) : p.vh_shift;
 	uint32_t	  *vis = p.visited + (size_t) slot * p.vis_words;
 	uint32_t	  *vlog = p.vlog + (size_t) slot * p.vlog_cap;
 	uint64_t	  *ovf = p.ovf + (size_t) slot * ef;
-	uint32_t	  *vh = p.vhash + (size_t) slot * H;
+	uint32_t	  *vh = vh_shared ? reinterpret_cast<uint32_t *>(smem + p.off_vhs) : p.vhash + (size_t) slot * H;
 	const uint64_t pol_stream = l2_policy_evict_first();
 	const uint64_t pol_keep = l2_policy_evict_last();
 	constexpr uint32_t kEmpty = 0xffffffffu;
@@ -326,6 +333,8 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			mbar_init(&pool->bar[b], 1);
 		}
 	}
+	if (vh_shared)
+		for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) vh[i] = 0xffffffffu;
 	if (lane == 0 && (!COOP || warp == 0)) mbar_init(pf_bar, 1);
 	fence_mbar_init();
 	__syncthreads();		   // the only CTA-wide barrier: from here on the slots run independently
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				hop_id[0] = p.entry;
 				if (vmode == 0)
 				{
-					const uint32_t h = (p.entry * 2654435761u) >> p.vh_shift;
+					const uint32_t h = (p.entry * 2654435761u) >> vh_shift;
 					vh[h] = p.entry;
 					vlog[0] = h;
 				}
@@ -789,7 +798,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				for (uint32_t i = lane; i < logn; i += 32)
 				{
 					const uint32_t pos = vlog[i];
-					const uint32_t vid = __ldcg(&vh[pos]);	// written by L2 atomics: never read through L1
+					const uint32_t vid = vh_shared ? *reinterpret_cast<volatile uint32_t *>(&vh[pos]) : __ldcg(&vh[pos]);  // global: written by L2 atomics, never read through L1
 					vh[pos] = kEmpty;
 					atomicOr(&vis[vid >> 5], 1u << (vid & 31));
 					vlog[i] = vid;
@@ -814,7 +823,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					uint32_t lA = idA, lB = idB;
 					if (vmode == 0)
 					{
-						uint32_t hA = (idA * 2654435761u) >> p.vh_shift, hB = (idB * 2654435761u) >> p.vh_shift;
+						uint32_t hA = (idA * 2654435761u) >> vh_shift, hB = (idB * 2654435761u) >> vh_shift;
 						bool	 pA = vA, pB = vB;	// still probing
 						while (pA || pB)
 						{
@@ -883,7 +892,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				{
 					if (first)
 					{
-						uint32_t h = (id * 2654435761u) >> p.vh_shift;
+						uint32_t h = (id * 2654435761u) >> vh_shift;
 						for (;;)
 						{
 							const uint32_t old = atomicCAS(&vh[h], kEmpty, id);

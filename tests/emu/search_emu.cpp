@@ -7,6 +7,12 @@
 
 using namespace pgemb;
 
+extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const uint32_t *links, const uint64_t *labels, const float *norms,
+							 uint32_t n_items, uint32_t dim, uint32_t row_f, uint32_t link_stride, uint32_t maxM, const float *queries,
+							 uint32_t nq, uint32_t ef, int raw_mode, uint64_t *labels_out, float *dists_out, uint32_t *ids_out,
+							 int32_t *n_out, uint32_t *stats_out, uint32_t want_warps, uint32_t want_rings, uint32_t grid, uint32_t vh_size,
+							 uint32_t visited_pairs, uint32_t smem_visited, int *error_out);
+
 template <int METRIC, bool COOP> static void go(const SearchParams &p, unsigned grid, unsigned warps, size_t smem)
 {
 	emu::launch(dim3(grid), warps * 32, smem, [=]() { search_kernel<METRIC, COOP>(p); });
@@ -18,6 +24,16 @@ extern "C" int emu_search(int metric, int coop, const float *vectors, const uint
 						  uint32_t nq, uint32_t ef, int raw_mode, uint64_t *labels_out, float *dists_out, uint32_t *ids_out,
 						  int32_t *n_out, uint32_t *stats_out, uint32_t want_warps, uint32_t want_rings, uint32_t grid, uint32_t vh_size,
 						  uint32_t visited_pairs, int *error_out)
+{
+	return emu_search_ex(metric, coop, vectors, links, labels, norms, n_items, dim, row_f, link_stride, maxM, queries, nq, ef, raw_mode, labels_out,
+						 dists_out, ids_out, n_out, stats_out, want_warps, want_rings, grid, vh_size, visited_pairs, 0, error_out);
+}
+
+extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const uint32_t *links, const uint64_t *labels, const float *norms,
+							 uint32_t n_items, uint32_t dim, uint32_t row_f, uint32_t link_stride, uint32_t maxM, const float *queries,
+							 uint32_t nq, uint32_t ef, int raw_mode, uint64_t *labels_out, float *dists_out, uint32_t *ids_out,
+							 int32_t *n_out, uint32_t *stats_out, uint32_t want_warps, uint32_t want_rings, uint32_t grid, uint32_t vh_size,
+							 uint32_t visited_pairs, uint32_t smem_visited, int *error_out)
 {
 	SearchShape sh;
 	sh.metric = metric;
@@ -31,9 +47,11 @@ extern "C" int emu_search(int metric, int coop, const float *vectors, const uint
 	tu.want_warps = (int) want_warps;
 	tu.want_rings = (int) want_rings;
 	tu.want_coop_warps = (int) want_warps;
+	tu.smem_visited = (int) smem_visited;
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
 	if (rc) return rc;
+	if (coop && smem_visited && cfg.vhs_entries == 0) return 77;  // the test asked for the shared-memory set
 	const uint32_t slots = coop ? grid : grid * cfg.warps;
 	const uint32_t vis_words = (n_items + 31) / 32 + 1;
 	const uint32_t vlog_cap = n_items < 32768 ? n_items + 1 : 32768;

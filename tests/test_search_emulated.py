@@ -40,10 +40,11 @@ def emu(tmp_path_factory):
     assert res.returncode == 0, res.stderr
     lib = C.CDLL(out)
     lib.emu_search.restype = C.c_int
+    lib.emu_search_ex.restype = C.c_int
     return lib
 
 
-def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0):
+def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0):
     n, dim = x.shape
     row_f = (dim + 3) & ~3
     ls = (maxm + 1 + 3) & ~3
@@ -54,10 +55,10 @@ def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid
     lab = np.zeros((nq, ef), np.uint64); dd = np.zeros((nq, ef), np.float32); ids = np.zeros((nq, ef), np.uint32)
     nn = np.zeros(nq, np.int32); st = np.zeros((nq, 4), np.uint32)
     err = C.c_int(0)
-    rc = lib.emu_search(METRIC_ID[metric], coop, _p(xv, C.c_float), _p(lk, C.c_uint32), _p(labels, C.c_uint64), _p(norms, C.c_float),
+    rc = lib.emu_search_ex(METRIC_ID[metric], coop, _p(xv, C.c_float), _p(lk, C.c_uint32), _p(labels, C.c_uint64), _p(norms, C.c_float),
                         C.c_uint32(n), C.c_uint32(dim), C.c_uint32(row_f), C.c_uint32(ls), C.c_uint32(maxm), _p(np.ascontiguousarray(q), C.c_float),
                         C.c_uint32(nq), C.c_uint32(ef), 0, _p(lab, C.c_uint64), _p(dd, C.c_float), _p(ids, C.c_uint32), _p(nn, C.c_int32),
-                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.byref(err))
+                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited), C.byref(err))
     assert rc == 0, rc
     assert err.value == 0, hex(err.value)
     return dict(labels=lab, dists=dd, ids=ids, n=nn, stats=st)
@@ -138,3 +139,21 @@ def test_bind_kernels_emulated_match_oracle(emu, oracle_mod, case, coop):
     got = lk[:, :maxm + 1]
     bad = np.flatnonzero((got != want).any(1))
     assert bad.size == 0, f"link lists differ at nodes {bad[:8]}: {got[bad[0]]} vs {want[bad[0]]}"
+
+
+@pytest.mark.parametrize("n,ef", [(300, 12), (1500, 220)], ids=["small", "migrates-to-bitmap"])
+def test_latency_mode_shared_memory_visited_set(emu, oracle_mod, n, ef):
+    """Prototype (PGEMB_SMEM_VISITED): in latency mode the open-addressing visited set lives in the CTA's shared memory.
+    The 1500-node case visits more than half of the 1024-entry table, so it also crosses the migration to the bitmap."""
+    rng = np.random.default_rng(n)
+    dims, m, efc = 12, 6, 24
+    x = rng.standard_normal((n, dims)).astype(np.float32)
+    q = rng.standard_normal((3, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.build(x)
+    want = orc.search_many(q, ef, want_counters=True)
+    got = run_emu(emu, "l2", 1, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=2, rings=2, grid=2, vh=64, smem_visited=1024)
+    assert got["labels"].tobytes() == want["labels"].tobytes()
+    assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+    if n >= 1500:
+        assert int(want["counters"][:, 0].max()) > 512, "case too small to cross the half-full migration"

@@ -23,6 +23,8 @@ PY
 say "latency (both kernel modes), default and VISITED_PAIRS"
 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+say "latency with the shared-memory visited set (PGEMB_SMEM_VISITED=4096)"
+PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
