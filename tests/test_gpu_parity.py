@@ -198,11 +198,14 @@ def test_search_identical_to_oracle(pg, oracle_mod, metric, cfg):
     idx.close()
 
 
+@pytest.mark.parametrize("flags", [{"PGEMB_VISITED_PAIRS": "1"}, {"PGEMB_SMEM_VISITED": "4096"}, {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "1024"}],
+                         ids=["pairs", "smem-visited", "both"])
 @pytest.mark.parametrize("cfg", [SEARCH_CFGS[0], SEARCH_CFGS[5], SEARCH_CFGS[6], SEARCH_CFGS[7]], ids=lambda c: f"d{c[0]}m{c[1]}")
-def test_visited_pairs_mode(pg, oracle_mod, cfg, monkeypatch):
+def test_visited_pairs_mode(pg, oracle_mod, cfg, flags, monkeypatch):
     """PGEMB_VISITED_PAIRS=1: both 32-id halves of a link list are test-and-set concurrently.  Same results, same
     traversal counters; a graph whose lists repeat an id must be detected and served by the ordered path."""
-    monkeypatch.setenv("PGEMB_VISITED_PAIRS", "1")
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
     dims, m, efc, n, kw, efs = cfg
     rng = np.random.default_rng(4242 + dims)
     x = _data(rng, n, dims, **kw)
