@@ -23,6 +23,9 @@ def sqnorm_lane_order(v):
         res = np.float32(res + np.float32(v[e] * v[e]))
     return res
 
+# the emulated CTAs are real threads: a protocol bug could hang them -- fail the run instead of blocking it
+pytestmark = pytest.mark.timeout(900, method="thread")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRIC_ID = {"l2": 0, "cosine": 1, "manhattan": 2}
 
