@@ -141,3 +141,24 @@ def test_error_paths(pg):
     with pytest.raises(Exception):
         pg.HnswIndex(0, 2, 4, 4, "l2", capacity=3)        # dims must be given (embedding.c:219-221)
     idx.close()
+
+
+@pytest.mark.parametrize("env", [{"PGEMB_STREAM_QUERIES": "0"}, {"CUDA_LAUNCH_BLOCKING": "1"}, {"PGEMB_STREAM_QUERIES": "1"}],
+                         ids=["copy-then-launch", "launch-blocking", "streamed"])
+def test_host_pointer_search_both_copy_orders(pg, G, oracle_mod, env, monkeypatch):
+    """pgemb_search_batch copies the batch before the launch under serialising tools and streams it in otherwise; a batch
+    larger than one 4096-query chunk takes several chunks either way.  Same results."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(12)
+    dims, m, efc, n = 5, 3, 8, 120
+    x = rng.standard_normal((n, dims)).astype(np.float32)
+    q = rng.standard_normal((4200, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.build(x)
+    idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    idx.append(x, orc.labels(), orc.links())
+    out = idx.search_batch(q, 4)
+    want = orc.search_many(q, 4, nthreads=4)
+    assert out["labels"].tobytes() == want["labels"].tobytes() and out["n"].tolist() == want["n"].tolist()
+    idx.close()
