@@ -59,7 +59,12 @@ def load() -> C.CDLL:
         raise ImportError(
             f"{LIB_PATH} is missing: build the CUDA extension first (python -m pg_embedding_b200.build). "
             "There is no CPU fallback for the pg_embedding hot path.")
-    lib = C.CDLL(LIB_PATH)
+    _lib = _bind(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _bind(lib: C.CDLL) -> C.CDLL:
+    """Attach the prototypes of include/pgemb_b200.h to a loaded library."""
     vp, sz = C.c_void_p, C.c_size_t
     f32p, u64p, u32p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
     mp = C.POINTER(HnswMetadata)
@@ -106,7 +111,6 @@ def load() -> C.CDLL:
     lib.hnsw_init_dist_func.restype = None
     lib.hnsw_is_deleted.argtypes = [C.c_uint64]
     lib.hnsw_is_deleted.restype = C.c_bool
-    _lib = lib
     return lib
 
 

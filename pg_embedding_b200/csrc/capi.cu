@@ -237,7 +237,7 @@ static pgemb_status compute_norms(pgemb_index *idx, size_t first, size_t n, cuda
 	if (idx->meta.dist_func != DIST_COSINE || n == 0) return PGEMB_OK;
 	const uint32_t threads = 128;
 	const uint32_t blocks = (uint32_t) ((n * 4 + threads - 1) / threads);
-	norms_kernel<<<blocks, threads, 0, s>>>(idx->d_vectors, idx->row_f, (uint32_t) idx->meta.dim, (uint32_t) first, (uint32_t) n,
+	PGEMB_LAUNCH(norms_kernel, blocks, threads, 0, s, idx->d_vectors, idx->row_f, (uint32_t) idx->meta.dim, (uint32_t) first, (uint32_t) n,
 											idx->d_norms);
 	g_launches++;
 	CU_TRY(cudaGetLastError());
@@ -322,7 +322,7 @@ extern "C" pgemb_status pgemb_index_append_records(pgemb_index *idx, size_t n, c
 		CU_TRY(cudaMemcpyAsync(idx->d_stage, (const char *) records + done * record_stride, m * record_stride, cudaMemcpyHostToDevice,
 							   idx->stream));
 		const uint32_t threads = 128, blocks = (uint32_t) ((m * 32 + threads - 1) / threads);
-		records_unpack_kernel<<<blocks, threads, 0, idx->stream>>>((const unsigned char *) idx->d_stage, record_stride, (uint32_t) m,
+		PGEMB_LAUNCH(records_unpack_kernel, blocks, threads, 0, idx->stream, (const unsigned char *) idx->d_stage, record_stride, (uint32_t) m,
 																   (uint32_t) (idx->n + done), (uint32_t) idx->meta.dim,
 																   (uint32_t) idx->meta.maxM, idx->row_f, idx->link_stride,
 																   idx->d_vectors, idx->d_links, idx->d_labels);
@@ -355,7 +355,7 @@ extern "C" pgemb_status pgemb_index_export_records(const pgemb_index *cidx, size
 		if (st) return st;
 		CU_TRY(cudaMemsetAsync(idx->d_stage, 0, m * record_stride, idx->stream));
 		const uint32_t threads = 128, blocks = (uint32_t) ((m * 32 + threads - 1) / threads);
-		records_pack_kernel<<<blocks, threads, 0, idx->stream>>>((unsigned char *) idx->d_stage, record_stride, (uint32_t) m,
+		PGEMB_LAUNCH(records_pack_kernel, blocks, threads, 0, idx->stream, (unsigned char *) idx->d_stage, record_stride, (uint32_t) m,
 																 (uint32_t) (first + done), (uint32_t) idx->meta.dim,
 																 (uint32_t) idx->meta.maxM, idx->row_f, idx->link_stride, idx->d_vectors,
 																 idx->d_links, idx->d_labels);
@@ -607,7 +607,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 			const uint32_t nn = (uint32_t) idx->n;
 			int			   dup = 0;
 			CU_TRY(cudaMemsetAsync(idx->d_counter + 3, 0, sizeof(int), s));
-			if (nn) links_distinct_kernel<<<(nn + 3) / 4, 128, 0, s>>>(idx->d_links, idx->link_stride, (uint32_t) idx->meta.maxM, 0u, nn, (int *) (idx->d_counter + 3));
+			if (nn) PGEMB_LAUNCH(links_distinct_kernel, (nn + 3) / 4, 128, 0, s, idx->d_links, idx->link_stride, (uint32_t) idx->meta.maxM, 0u, nn, (int *) (idx->d_counter + 3));
 			g_launches++;
 			CU_TRY(cudaMemcpyAsync(&dup, idx->d_counter + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
 			CU_TRY(cudaStreamSynchronize(s));
@@ -635,7 +635,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	// small batches are spread over all SMs (the slots steal queries from one counter), not packed into few CTAs
 	uint32_t grid = (uint32_t) (nq < (size_t) idx->sm_count ? nq : (size_t) idx->sm_count);
 	if (time_it) CU_TRY(cudaEventRecord(idx->ev0, s));
-	fn<<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
+	PGEMB_LAUNCH(fn, grid, cfg.warps * 32, cfg.smem, s, p);
 	g_launches++;
 	CU_TRY(cudaGetLastError());
 	if (time_it)
@@ -790,9 +790,9 @@ static pgemb_status launch_pairs(int metric, const float *d_a, const float *d_b,
 	const uint32_t blocks = (uint32_t) (((size_t) n * lanes + threads - 1) / threads);
 	switch (metric)
 	{
-		case DIST_L2: dist_pairs_kernel<M_L2><<<blocks, threads, 0, s>>>(d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
-		case DIST_COSINE: dist_pairs_kernel<M_COS><<<blocks, threads, 0, s>>>(d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
-		case DIST_MANHATTAN: dist_pairs_kernel<M_MAN><<<blocks, threads, 0, s>>>(d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
+		case DIST_L2: PGEMB_LAUNCH(dist_pairs_kernel<M_L2>, blocks, threads, 0, s, d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
+		case DIST_COSINE: PGEMB_LAUNCH(dist_pairs_kernel<M_COS>, blocks, threads, 0, s, d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
+		case DIST_MANHATTAN: PGEMB_LAUNCH(dist_pairs_kernel<M_MAN>, blocks, threads, 0, s, d_a, d_b, dim, dim, dim, n, broadcast_a, d_out); break;
 		default: return fail(PGEMB_ERR_ARG, "unknown distance function");
 	}
 	g_launches++;
@@ -849,7 +849,7 @@ extern "C" pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coo
 	const uint32_t threads = 128, lanes = (metric == DIST_L2) ? 8 : 4;
 	const uint32_t blocks = (uint32_t) ((nq * k * lanes + threads - 1) / threads);
 #define GATHER(MM)                                                                                                              \
-	dist_gather_kernel<MM><<<blocks, threads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, (uint32_t) idx->n, d_q, \
+	PGEMB_LAUNCH(dist_gather_kernel<MM>, blocks, threads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, (uint32_t) idx->n, d_q, \
 													  (uint32_t) dim, (uint32_t) nq, (uint32_t) k, d_i, d_o)
 	if (metric == DIST_L2) GATHER(M_L2);
 	else if (metric == DIST_COSINE) GATHER(M_COS);
@@ -897,7 +897,7 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	const bool tiled = env_int("PGEMB_SCAN_TILED", 0) != 0;
 	if (tiled && metric == DIST_COSINE)
 	{
-		norms_kernel<<<(uint32_t) ((nq * 4 + 127) / 128), 128, 0, s>>>(d_q, (uint32_t) dim, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
+		PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nq * 4 + 127) / 128), 128, 0, s, d_q, (uint32_t) dim, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
 		g_launches++;
 		CU_TRY(cudaGetLastError());
 	}
@@ -907,11 +907,10 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 		const uint32_t threads = 128;
 		const uint32_t blocks = (uint32_t) ((nq * nr * lanes + threads - 1) / threads);
 #define SCAN_DIST(MM)                                                                                                              \
-	scan_dist_kernel<MM><<<blocks, threads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, \
+	PGEMB_LAUNCH(scan_dist_kernel<MM>, blocks, threads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, \
 													(uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
 #define SCAN_TILE(MM)                                                                                                              \
-	scan_tile_kernel<MM><<<dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), \
-						   kScanThreads, 0, s>>>(idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, d_qn,  \
+	PGEMB_LAUNCH(scan_tile_kernel<MM>, dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), kScanThreads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, d_qn,  \
 												 (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
 		if (tiled)
 		{
@@ -924,7 +923,7 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 		else SCAN_DIST(M_MAN);
 #undef SCAN_TILE
 #undef SCAN_DIST
-		scan_select_kernel<<<(uint32_t) ((nq + 3) / 4), 128, 0, s>>>(d_dist, idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k,
+		PGEMB_LAUNCH(scan_select_kernel, (uint32_t) ((nq + 3) / 4), 128, 0, s, d_dist, idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k,
 																	 d_td, d_tl, d_tn, d_sd, d_sl);
 		g_launches += 2;
 		CU_TRY(cudaGetLastError());
@@ -1087,7 +1086,7 @@ static pgemb_status launch_connect(pgemb_index *idx, const uint32_t *d_new_ids, 
 #define LAUNCH_SELECT(MM)                                                                                                        \
 	do {                                                                                                                         \
 		if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
-		select_kernel<MM><<<(uint32_t) count, kBindThreads, sel_smem, s>>>(g, d_new_ids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) ef, w.d_pairs); \
+		PGEMB_LAUNCH(select_kernel<MM>, (uint32_t) count, kBindThreads, sel_smem, s, g, d_new_ids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) ef, w.d_pairs); \
 	} while (0)
 	if (metric == DIST_L2) LAUNCH_SELECT(M_L2);
 	else if (metric == DIST_COSINE) LAUNCH_SELECT(M_COS);
@@ -1107,7 +1106,7 @@ static pgemb_status launch_connect(pgemb_index *idx, const uint32_t *d_new_ids, 
 #define LAUNCH_BACK(MM)                                                                                                          \
 	do {                                                                                                                         \
 		if (bl_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(backlink_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bl_smem)); \
-		backlink_kernel<MM><<<(uint32_t) n_pairs, kBindThreads, bl_smem, s>>>(g, sorted, (uint32_t) n_pairs);                      \
+		PGEMB_LAUNCH(backlink_kernel<MM>, (uint32_t) n_pairs, kBindThreads, bl_smem, s, g, sorted, (uint32_t) n_pairs);                      \
 	} while (0)
 	if (metric == DIST_L2) LAUNCH_BACK(M_L2);
 	else if (metric == DIST_COSINE) LAUNCH_BACK(M_COS);
@@ -1200,7 +1199,7 @@ extern "C" pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t 
 			pos = 1;  // node 0 has nothing to connect to (hnswalg.cpp:227-228)
 			continue;
 		}
-		iota_kernel<<<(uint32_t) ((B + 255) / 256), 256, 0, s>>>(w.d_qids, (uint32_t) pos, (uint32_t) B);
+		PGEMB_LAUNCH(iota_kernel, (uint32_t) ((B + 255) / 256), 256, 0, s, w.d_qids, (uint32_t) pos, (uint32_t) B);
 		g_launches++;
 		st = launch_search(idx, B, nullptr, 0, w.d_qids, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n, nullptr, s,
 						   false);
@@ -1267,7 +1266,7 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 		}
 		if (B > batch_max) B = batch_max;
 		if (B > end - pos) B = end - pos;
-		iota_kernel<<<(uint32_t) ((B + 255) / 256), 256, 0, s>>>(w.d_qids, (uint32_t) pos, (uint32_t) B);
+		PGEMB_LAUNCH(iota_kernel, (uint32_t) ((B + 255) / 256), 256, 0, s, w.d_qids, (uint32_t) pos, (uint32_t) B);
 		g_launches++;
 		st = launch_search(idx, B, nullptr, 0, w.d_qids, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n, nullptr, s,
 						   false, nullptr, w.d_exp, ecap, w.d_exp_n);
@@ -1281,7 +1280,7 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 #define LAUNCH_SELECT_X(MM)                                                                                                     \
 	do {                                                                                                                         \
 		if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
-		select_kernel<MM><<<(uint32_t) B, kBindThreads, sel_smem, s>>>(g, w.d_qids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) efc, w.d_pairs); \
+		PGEMB_LAUNCH(select_kernel<MM>, (uint32_t) B, kBindThreads, sel_smem, s, g, w.d_qids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) efc, w.d_pairs); \
 	} while (0)
 		if (metric == DIST_L2) LAUNCH_SELECT_X(M_L2);
 		else if (metric == DIST_COSINE) LAUNCH_SELECT_X(M_COS);
@@ -1294,9 +1293,9 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 		{
 			uint32_t hfirst = (uint32_t) B;
 			CU_TRY(cudaMemcpyAsync(w.d_first, &hfirst, 4, cudaMemcpyHostToDevice, s));
-			stamp_targets_kernel<<<(n_pairs_all + 255) / 256, 256, 0, s>>>(w.d_pairs, n_pairs_all, w.d_stamp);
-			validate_kernel<<<(uint32_t) ((B * 32 + 255) / 256), 256, 0, s>>>(w.d_exp, w.d_exp_n, ecap, w.d_qids, (uint32_t) B, w.d_stamp, w.d_first);
-			clear_stamps_kernel<<<(n_pairs_all + 255) / 256, 256, 0, s>>>(w.d_pairs, n_pairs_all, w.d_stamp);
+			PGEMB_LAUNCH(stamp_targets_kernel, (n_pairs_all + 255) / 256, 256, 0, s, w.d_pairs, n_pairs_all, w.d_stamp);
+			PGEMB_LAUNCH(validate_kernel, (uint32_t) ((B * 32 + 255) / 256), 256, 0, s, w.d_exp, w.d_exp_n, ecap, w.d_qids, (uint32_t) B, w.d_stamp, w.d_first);
+			PGEMB_LAUNCH(clear_stamps_kernel, (n_pairs_all + 255) / 256, 256, 0, s, w.d_pairs, n_pairs_all, w.d_stamp);
 			g_launches += 3;
 			CU_TRY(cudaMemcpyAsync(&hfirst, w.d_first, 4, cudaMemcpyDeviceToHost, s));
 			CU_TRY(cudaStreamSynchronize(s));
@@ -1304,7 +1303,7 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 			if (acc < 1) acc = 1;
 			if (acc < B)
 			{
-				zero_links_kernel<<<(uint32_t) (B - acc), 64, 0, s>>>(idx->d_links, idx->link_stride, w.d_qids + acc, (uint32_t) (B - acc));
+				PGEMB_LAUNCH(zero_links_kernel, (uint32_t) (B - acc), 64, 0, s, idx->d_links, idx->link_stride, w.d_qids + acc, (uint32_t) (B - acc));
 				g_launches++;
 			}
 		}
@@ -1323,7 +1322,7 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 #define LAUNCH_BACK_X(MM)                                                                                                        \
 	do {                                                                                                                         \
 		if (bl_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(backlink_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bl_smem)); \
-		backlink_kernel<MM><<<n_pairs, kBindThreads, bl_smem, s>>>(g, sorted, n_pairs);                                          \
+		PGEMB_LAUNCH(backlink_kernel<MM>, n_pairs, kBindThreads, bl_smem, s, g, sorted, n_pairs);                                          \
 	} while (0)
 		if (metric == DIST_L2) LAUNCH_BACK_X(M_L2);
 		else if (metric == DIST_COSINE) LAUNCH_BACK_X(M_COS);
@@ -1362,7 +1361,7 @@ extern "C" pgemb_status pgemb_merge_topk_device(size_t nq, size_t n_shards, size
 	if (n_shards == 0 || k == 0) return fail(PGEMB_ERR_ARG, "n_shards and k must be > 0");
 	const uint32_t threads = 128;
 	const uint32_t blocks = (uint32_t) ((nq * 32 + threads - 1) / threads);
-	merge_topk_kernel<<<blocks, threads, 0, (cudaStream_t) stream>>>((uint32_t) nq, (uint32_t) n_shards, (uint32_t) k, d_dists_in,
+	PGEMB_LAUNCH(merge_topk_kernel, blocks, threads, 0, (cudaStream_t) stream, (uint32_t) nq, (uint32_t) n_shards, (uint32_t) k, d_dists_in,
 																	 d_labels_in, d_n_in, d_dists_out, d_labels_out, d_n_out);
 	g_launches++;
 	CU_TRY(cudaGetLastError());

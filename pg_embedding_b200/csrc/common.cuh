@@ -13,6 +13,14 @@
 #define PGEMB_DYNAMIC_SMEM(name, alignment) extern __shared__ __align__(alignment) unsigned char name[]
 #endif
 
+// kernel launch (under the host emulation a launch runs the grid on the emulator, synchronously)
+#ifdef PGEMB_HOST_EMULATION
+#define PGEMB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+	emu::launch(dim3(grid), (unsigned) (block), (size_t) (smem), [=]() { kernel(__VA_ARGS__); })
+#else
+#define PGEMB_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace pgemb {
 
 constexpr int kWarp = 32;

@@ -217,9 +217,9 @@ static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
 	return e;
 }
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t) p; }
-// the few runtime calls that appear in headers shared with host code
+// (the runtime API the host code uses is emulated at the end of this header)
 typedef int cudaError_t;
-static inline cudaError_t cudaFree(void *) { return 0; }
+static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 
 // ---- mbarrier + 1-D bulk TMA (host versions of the wrappers common.cuh guards out) --------------------
 // 64-bit barrier word: [0] phase parity, [1..15] pending arrivals, [16..30] arrival count, [32..63] tx bytes (signed)
@@ -286,3 +286,90 @@ static inline void	   tma_load_1d(void *dst, const void *src, uint32_t bytes, ui
 	pthread_mutex_unlock(&emu::g_mbar_mu);
 }
 static inline uint32_t lanemask_lt() { return (1u << (emu::L().tid.x & 31u)) - 1u; }
+
+// ---- the part of the CUDA runtime API capi.cu uses ---------------------------------------------------------
+// Device memory is host memory, streams execute in call order (every "async" call completes before it returns),
+// events are wall-clock time stamps.  Enough to run the library's host logic (workspaces, build orchestration,
+// staging, error paths) over the emulated kernels.
+#include <chrono>
+enum cudaErrorEmu { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaLimit { cudaLimitPersistingL2CacheSize = 6 };
+enum cudaStreamAttrID { cudaStreamAttributeAccessPolicyWindow = 1 };
+enum cudaAccessProperty { cudaAccessPropertyNormal = 0, cudaAccessPropertyStreaming = 1, cudaAccessPropertyPersisting = 2 };
+struct cudaAccessPolicyWindow { void *base_ptr; size_t num_bytes; float hitRatio; cudaAccessProperty hitProp, missProp; };
+union cudaStreamAttrValue { cudaAccessPolicyWindow accessPolicyWindow; int pad[16]; };
+struct cudaDeviceProp { int multiProcessorCount; int persistingL2CacheMaxSize; int accessPolicyMaxWindowSize; };
+struct EmuStream { int id; };
+struct EmuEvent { double t_ms; };
+typedef EmuStream *cudaStream_t;
+typedef EmuEvent  *cudaEvent_t;
+
+static inline const char *cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : (e == 2 ? "out of memory" : "invalid value"); }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
+{
+	const char *v = getenv("PGEMB_EMU_SMS");
+	p->multiProcessorCount = (v && *v) ? atoi(v) : 2;
+	p->persistingL2CacheMaxSize = 0;
+	p->accessPolicyMaxWindowSize = 0;
+	return cudaSuccess;
+}
+template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t bytes)
+{
+	*p = (T *) aligned_alloc(256, (bytes + 255) / 256 * 256 + 256);
+	if (*p) memset((void *) *p, 0xCD, bytes);  // device memory is not zeroed
+	return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+template <typename T> static inline cudaError_t cudaMallocHost(T **p, size_t bytes) { return cudaMalloc(p, bytes); }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t = nullptr)
+{
+	for (size_t r = 0; r < h; r++) memmove((char *) d + r * dp, (const char *) s + r * sp, w);
+	return cudaSuccess;
+}
+static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = new EmuStream{1}; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaStreamSetAttribute(cudaStream_t, cudaStreamAttrID, const cudaStreamAttrValue *) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new EmuEvent{0.0}; return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr)
+{
+	e->t_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+	return cudaSuccess;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float) (b->t_ms - a->t_ms); return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
+
+namespace cub {
+struct DeviceRadixSort
+{
+	template <typename K>
+	static cudaError_t SortKeys(void *tmp, size_t &bytes, const K *in, K *out, int n, int = 0, int = sizeof(K) * 8, cudaStream_t = nullptr)
+	{
+		if (!tmp)
+		{
+			bytes = 16;
+			return cudaSuccess;
+		}
+		std::copy(in, in + n, out);
+		std::sort(out, out + n);
+		return cudaSuccess;
+	}
+};
+}  // namespace cub

@@ -1,0 +1,195 @@
+"""The WHOLE library on the host: capi.cu (the C ABI: workspaces, staging, build orchestration, error paths) compiled by
+g++ against tests/emu's stand-in CUDA runtime, its kernels run by the SIMT emulator.  The bodies of the GPU parity tests
+(tests/test_gpu_parity.py) are reused on their small configurations, so the same assertions that gate the B200 run
+also exercise the host logic here -- bit-exact against the oracle -- without a GPU.
+
+This is test infrastructure, not a fallback: the emulated library is built into a temporary directory by this module's
+fixture and is the only thing that ever loads it; `pg_embedding_b200._lib.load()` knows nothing about it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.timeout(1800, method="thread")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libpgemb_emulated.so")
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+           "-I", os.path.join(ROOT, "tests", "emu", "fake_cuda"), "-I", os.path.join(ROOT, "include"), "-o", out,
+           os.path.join(ROOT, "pg_embedding_b200", "csrc", "capi.cu"), os.path.join(ROOT, "tests", "emu", "emu_runtime.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-4000:]
+    from pg_embedding_b200 import _lib
+    return _lib._bind(C.CDLL(out))
+
+
+@pytest.fixture()
+def pg(emu_lib, monkeypatch):
+    """pg_embedding_b200 with its library handle swapped for the emulated build (restored after each test)."""
+    import pg_embedding_b200 as pkg
+    from pg_embedding_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", emu_lib)
+    monkeypatch.setenv("PGEMB_EMU_SMS", "2")
+    assert pkg.device_count() == 1
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def G():
+    import test_gpu_parity as g     # the GPU parity tests: bodies reused below
+    return g
+
+
+def test_kats(pg, G):
+    for case in G.GOLD:
+        G.test_kat_regress(pg, case)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
+def test_distance_entry_points(pg, G, oracle_mod, metric):
+    rng = np.random.default_rng(1)
+    for dim in (1, 3, 16, 33, 129):
+        a = rng.standard_normal((7, dim)).astype(np.float32)
+        b = rng.standard_normal((7, dim)).astype(np.float32)
+        assert pg.dist_batch(metric, a, b).tobytes() == oracle_mod.dist_many("port", metric, a, b).tobytes()
+        assert pg.dist_batch(metric, a[0], b).tobytes() == oracle_mod.dist_many("port", metric, a[0], b).tobytes()
+    G.test_sql_distance_functions(pg, oracle_mod)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
+@pytest.mark.parametrize("ci", [0, 1, 3], ids=["ties", "duplicates", "padded"])
+def test_search_through_the_abi(pg, G, oracle_mod, metric, ci):
+    G.test_search_identical_to_oracle(pg, oracle_mod, metric, G.SEARCH_CFGS[ci])
+
+
+def test_empty_and_tiny(pg, G, oracle_mod):
+    G.test_search_empty_and_tiny(pg, oracle_mod)
+
+
+@pytest.mark.parametrize("metric,ci", [("l2", 0), ("cosine", 0), ("manhattan", 1)], ids=["ties-l2", "ties-cosine", "duplicates-manhattan"])
+def test_inserts_through_the_abi(pg, G, oracle_mod, metric, ci):
+    G.test_bind_links_identical_to_oracle(pg, oracle_mod, metric, G.BIND_CFGS[ci])
+
+
+def test_record_layout(pg, G, oracle_mod):
+    G.test_record_layout_roundtrip(pg, oracle_mod, 3, 3)
+    G.test_record_layout_roundtrip(pg, oracle_mod, 33, 5)
+
+
+def test_exact_parallel_build_orchestration(pg, oracle_mod):
+    """pgemb_build_exact: speculative batches, stamp/validate kernels, prefix acceptance, restart -- must equal n sequential inserts."""
+    rng = np.random.default_rng(5)
+    for metric, dims, m, efc, n, levels in (("l2", 4, 3, 10, 180, 3), ("cosine", 12, 4, 16, 200, 0)):
+        x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
+        if metric == "cosine":
+            x = x + 1.0
+        orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x)
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+        idx.append(x)
+        _, st = idx.build_exact(0, n, 64)
+        assert idx.links().tobytes() == orc.links().tobytes(), metric
+        assert st["batches"] < n - 1, "no batch ever accepted more than one insert"
+        idx.close()
+
+
+def test_bulk_build_orchestration(pg, oracle_mod):
+    """pgemb_build_bulk: batch_max = 1 is the sequential build; larger batches give a valid graph (sorted back-link pairs,
+    per-target serialisation) that the traversal searches with the reference's results on that same graph."""
+    rng = np.random.default_rng(6)
+    dims, m, efc, n = 8, 4, 16, 400
+    x = rng.standard_normal((n, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.build(x)
+    a = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    a.build(x, batch_max=1)
+    assert a.links().tobytes() == orc.links().tobytes()
+    a.close()
+    b = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    b.build(x, batch_max=32)
+    links = b.links()
+    cnt = links[:, 0]
+    assert cnt.max() <= 2 * m and (cnt[1:] > 0).all()
+    for i in range(n):
+        ids = links[i, 1:1 + cnt[i]]
+        assert (ids < n).all() and (ids != i).all() and len(set(ids.tolist())) == len(ids)
+    chk = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    chk.load_graph(x, links, b.labels())
+    q = rng.standard_normal((20, dims)).astype(np.float32)
+    assert b.search_batch(q, 10)["labels"].tobytes() == chk.search_many(q, 10)["labels"].tobytes()
+    b.close()
+
+
+def test_scan_and_merge(pg, G, oracle_mod):
+    G.test_scan_topk_regress_seqscan(pg)
+    G.test_scan_doubles_efsearch(pg, oracle_mod)
+
+
+def test_error_paths(pg):
+    from pg_embedding_b200._lib import PgembError
+    idx = pg.HnswIndex(4, 2, 4, 4, "l2", capacity=3)
+    idx.append(np.zeros((3, 4), np.float32))
+    with pytest.raises(PgembError):
+        idx.append(np.zeros((1, 4), np.float32))          # capacity exceeded
+    with pytest.raises(PgembError):
+        idx.links(2, 5)                                   # range beyond the index
+    with pytest.raises(Exception):
+        pg.HnswIndex(0, 2, 4, 4, "l2", capacity=3)        # dims must be given (embedding.c:219-221)
+    idx.close()
+
+
+@pytest.mark.parametrize("env", [{"PGEMB_STREAM_QUERIES": "0"}, {"CUDA_LAUNCH_BLOCKING": "1"}, {"PGEMB_STREAM_QUERIES": "1"}],
+                         ids=["copy-then-launch", "launch-blocking", "streamed"])
+def test_host_pointer_search_both_copy_orders(pg, G, oracle_mod, env, monkeypatch):
+    """pgemb_search_batch copies the batch before the launch under serialising tools and streams it in otherwise; a batch
+    larger than one 4096-query chunk takes several chunks either way.  Same results."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(12)
+    dims, m, efc, n = 5, 3, 8, 120
+    x = rng.standard_normal((n, dims)).astype(np.float32)
+    q = rng.standard_normal((4200, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.build(x)
+    idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    idx.append(x, orc.labels(), orc.links())
+    out = idx.search_batch(q, 4)
+    want = orc.search_many(q, 4, nthreads=4)
+    assert out["labels"].tobytes() == want["labels"].tobytes() and out["n"].tolist() == want["n"].tolist()
+    idx.close()
+
+
+# ---- prototype flags (branch r2-prototypes) through the whole emulated library ------------------------------------
+@pytest.mark.parametrize("flags", [{"PGEMB_VISITED_PAIRS": "1"}, {"PGEMB_SMEM_VISITED": "1024"}, {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "2048"}],
+                         ids=["pairs", "smem-visited", "both"])
+def test_prototype_traversal_flags(pg, G, oracle_mod, flags, monkeypatch):
+    G.test_visited_pairs_mode(pg, oracle_mod, G.SEARCH_CFGS[0], flags, monkeypatch)       # incl. the repeated-id fallback
+    for k, v in flags.items():
+        monkeypatch.setenv(k, v)
+    G.test_search_identical_to_oracle(pg, oracle_mod, "cosine", G.SEARCH_CFGS[3])
+    G.test_bind_links_identical_to_oracle(pg, oracle_mod, "l2", G.BIND_CFGS[0])
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
+def test_prototype_tiled_scan(pg, G, oracle_mod, metric, monkeypatch):
+    monkeypatch.setenv("PGEMB_SCAN_TILED", "1")
+    G.test_scan_topk_regress_seqscan(pg)
+    rng = np.random.default_rng(3)
+    for dims, n, k in ((33, 700, 20), (100, 300, 5)):
+        x = rng.standard_normal((n, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        q = rng.standard_normal((37, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        labels = rng.permutation(n).astype(np.uint64) + np.uint64(9)
+        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
+        idx.append(x, labels)
+        out = idx.scan_topk(q, k)
+        for i in range(q.shape[0]):
+            d = oracle_mod.dist_many("port", metric, q[i], x)
+            order = sorted((float(d[j]), int(labels[j])) for j in range(n))[:k]
+            assert out["labels"][i].tolist() == [o[1] for o in order], (metric, dims, i)
+            assert out["dists"][i].tobytes() == np.array([o[0] for o in order], np.float32).tobytes()
+        idx.close()

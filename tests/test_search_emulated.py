@@ -23,6 +23,9 @@ def sqnorm_lane_order(v):
         res = np.float32(res + np.float32(v[e] * v[e]))
     return res
 
+# the emulated CTAs are real threads: a protocol bug could hang them -- fail the run instead of blocking it
+pytestmark = pytest.mark.timeout(900, method="thread")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRIC_ID = {"l2": 0, "cosine": 1, "manhattan": 2}
 
@@ -157,3 +160,44 @@ def test_latency_mode_shared_memory_visited_set(emu, oracle_mod, n, ef):
     assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
     if n >= 1500:
         assert int(want["counters"][:, 0].max()) > 512, "case too small to cross the half-full migration"
+
+
+def test_fuzz_traversal_emulated(emu, oracle_mod):
+    """300 seeded random configurations (metric, dims, m, ef, graph size, ties/duplicates, deleted labels, kernel mode,
+    slots/rings/CTAs, visited-table size): labels, counts and traversal counters must equal the oracle's every time."""
+    for seed in range(300):
+        rng = np.random.default_rng(9000 + seed)
+        metric = ["l2", "cosine", "manhattan"][rng.integers(0, 3)]
+        dims = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 33, 48]))
+        m = int(rng.choice([1, 2, 3, 4, 6, 9, 17]))
+        efc = int(rng.choice([1, 2, 5, 8, 16, 30]))
+        n = int(rng.choice([1, 2, 3, 10, 40, 90, 180]))
+        levels = int(rng.choice([0, 0, 2, 3, 5]))
+        ef = int(rng.choice([1, 2, 3, 5, 9, 16, 40]))
+        nq = int(rng.choice([1, 3, 7]))
+        coop = int(rng.integers(0, 2))
+        warps, rings, grid = int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 2, 3])), int(rng.choice([1, 2, 3]))
+        vh = int(rng.choice([0, 16, 64, 256]))
+        if levels:
+            x = rng.integers(0, levels, (n, dims)).astype(np.float32); q = rng.integers(0, levels, (nq, dims)).astype(np.float32)
+        else:
+            x = rng.standard_normal((n, dims)).astype(np.float32); q = rng.standard_normal((nq, dims)).astype(np.float32)
+        if metric == "cosine":
+            x, q = x + 1.0, q + 1.0
+        if rng.random() < 0.3 and n > 3:
+            k = max(1, n // 4)
+            x[rng.integers(0, n, k)] = x[rng.integers(0, n, k)]
+        labels = (rng.permutation(n).astype(np.uint64) << np.uint64(8)) | np.uint64(1)
+        orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x, labels)
+        for i in range(0, n, 5):
+            if rng.random() < 0.5:
+                orc.mark_deleted(i)
+        want = orc.search_many(q, ef, want_counters=True)
+        pairs, sv = int(rng.integers(0, 2)), int(rng.choice([0, 1024]))
+        got = run_emu(emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh, pairs=pairs, smem_visited=sv if coop else 0)
+        what = (seed, pairs, sv, metric, dims, m, efc, n, levels, ef, nq, coop, warps, rings, grid, vh)
+        assert got["n"].tolist() == want["n"].tolist(), what
+        assert got["labels"].tobytes() == want["labels"].tobytes(), what
+        assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), what
+        orc.close()
