@@ -447,6 +447,8 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	sh.maxM = (uint32_t) idx->meta.maxM;
 	sh.ef = ef;
 	sh.sm_count = (uint32_t) idx->sm_count;
+	// opt-in prototype: 8 lanes per row (4-row rings) for long L2 rows
+	sh.tpr = (sh.metric == DIST_L2 && env_int("PGEMB_L2_TPR8", 0) != 0 && idx->row_f * 4u >= (uint32_t) env_int("PGEMB_L2_TPR8_MIN_BYTES", 4096)) ? 8u : 4u;
 	SearchTuning tu;
 	tu.duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
 	tu.want_warps = env_int("PGEMB_WARPS", 0);
@@ -463,8 +465,9 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 
 typedef void (*search_fn_t)(const SearchParams);
 
-static search_fn_t pick_search_kernel(int metric, bool coop)
+static search_fn_t pick_search_kernel(int metric, bool coop, uint32_t tpr)
 {
+	if (metric == DIST_L2 && tpr == 8) return coop ? search_kernel<M_L2, true, 8> : search_kernel<M_L2, false, 8>;
 	switch (metric)
 	{
 		case DIST_L2: return coop ? search_kernel<M_L2, true> : search_kernel<M_L2, false>;
@@ -544,7 +547,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	SearchConfig cfg;
 	st = make_config(idx, (uint32_t) ef, &cfg, coop);
 	if (st) return st;
-	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, coop);
+	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, coop, cfg.tpr);
 	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for this metric");
 	CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.smem));
 	int occ = 0;

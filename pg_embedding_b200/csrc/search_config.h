@@ -27,6 +27,7 @@ struct SearchConfig
 	uint32_t off_pool = 0, off_ring = 0, off_priv = 0;
 	uint32_t off_qt = 0, off_qtail = 0, off_res = 0, off_hopkey = 0, off_acckey = 0, off_evict = 0, off_hopid = 0, off_pf = 0, off_pfbar = 0;
 	uint32_t ef = 0;
+	uint32_t tpr = 4;
 	uint32_t off_vhs = 0, vhs_entries = 0;	// latency mode: visited hash set in shared memory
 };
 
@@ -34,6 +35,7 @@ struct SearchShape
 {
 	int		 metric = 0;  // DIST_L2 = 0, DIST_COSINE = 1, DIST_MANHATTAN = 2
 	uint32_t dim = 0, row_f = 0, link_stride = 0, maxM = 0, ef = 0, sm_count = 0;
+	uint32_t tpr = 4;  // lanes per row: 4, or 8 (L2 only: a ring then holds 4 rows)
 };
 
 struct SearchTuning
@@ -64,13 +66,18 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 	// lane-major transposed query: per lane-thread a run of floats padded so that the four runs start
 	// 16 bytes apart modulo 128 (conflict-free LDS.128)
 	const uint32_t dim = sh.dim;
-	const uint32_t run = (metric == 0) ? ((dim & ~15u) >> 2) : ((dim & ~3u) >> 2);
-	const uint32_t qt_stride = cfg_align_up(run ? run : 1, 32) + 4u;
+	const uint32_t tpr = (metric == 0 && sh.tpr == 8) ? 8u : 4u;
+	const uint32_t rows_per_ring = 32u / tpr;
+	// floats per lane run: 4 lanes x dim/4 (two L2 chains interleaved per lane), or 8 lanes x dim/8
+	const uint32_t run = (metric == 0) ? ((dim & ~15u) >> (tpr == 8 ? 3 : 2)) : ((dim & ~3u) >> 2);
+	// runs start 16 bytes apart modulo 128 (LDS.128, 4 lanes) or 8 bytes apart (LDS.64, 8 lanes): conflict-free
+	const uint32_t qt_stride = cfg_align_up(run ? run : 1, 32) + (tpr == 8 ? 2u : 4u);
 
 	SearchConfig t;
+	t.tpr = tpr;
 	// ---- a slot's private block ----
 	uint32_t off = 0;
-	t.off_qt = off;			off = cfg_align_up(off + 4u * qt_stride * 4u, 16);
+	t.off_qt = off;			off = cfg_align_up(off + tpr * qt_stride * 4u, 16);
 	t.off_qtail = off;		off = cfg_align_up(off + 16u * 4u, 16);
 	t.off_res = off;		off += 2u * ef * 8u;
 	t.off_hopkey = off;		off += hopcap * 8u;
@@ -80,7 +87,7 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 	t.off_pf = off;			off = cfg_align_up(off + sh.link_stride * 4u, 8);
 	t.off_pfbar = off;		off += 8u;
 	t.priv_bytes = cfg_align_up(off, 128);
-	t.ring_bytes = cfg_align_up(8u * row_smem, 128);
+	t.ring_bytes = cfg_align_up(rows_per_ring * row_smem, 128);
 	const uint32_t pool_bytes = cfg_align_up((uint32_t) sizeof(RingPool), 128);
 	// ---- how many slots (warps) and rings per CTA (= per SM) ----
 	// A slot holds a ring for about `duty` of a hop; throughput ~ min(W / T_hop, R / (duty * T_hop)).
@@ -106,7 +113,7 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 	{
 		// latency mode: one slot per CTA, every warp owns a ring; no more warps than a full hop has row groups
 		uint32_t	   R = (max_cta - pool_bytes - t.priv_bytes) / t.ring_bytes;
-		const uint32_t groups = (hopcap + 7u) / 8u;
+		const uint32_t groups = (hopcap + rows_per_ring - 1u) / rows_per_ring;
 		if (R > groups) R = groups;
 		if (R > kMaxRings) R = kMaxRings;
 		const int wantC = tu.want_coop_warps;

@@ -112,8 +112,6 @@ inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_
 }
 
 constexpr uint32_t kNone = 0xffffffffu;
-constexpr int	   kTPR = 4;		   // lanes cooperating on one row
-constexpr int	   kRows = 32 / kTPR;  // rows per stage
 
 // ---- 4 lanes per row, query pre-transposed -----------------------------------------------------------
 // The query is stored lane-major in shared memory (qT): thread `sub` finds the values of ITS accumulator
@@ -241,6 +239,39 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 	}
 }
 
+// ---- L2 with 8 lanes per row: every lane owns ONE of the reference's eight accumulator lanes -----------------
+// Used for long rows (1536-d: 6 KB): a ring then holds 4 rows instead of 8, so twice as many rings fit and the
+// slots/rings balance of the 768-d configuration is kept.  qT8[sub*QS + 2b + {0,1}] = { q[16b+sub], q[16b+8+sub] }.
+__device__ __forceinline__ float score_row8_l2(const float *__restrict__ qts, const float *__restrict__ rowp, int sub, int main_n,
+												const float *__restrict__ q_tail, int dim)
+{
+	float		 S = 0.f;
+	const int	 nb = main_n >> 4;
+	const float *vp = rowp + sub;
+#pragma unroll 4
+	for (int b = 0; b < nb; b++)
+	{
+		const float2 qq = *reinterpret_cast<const float2 *>(qts + 2 * b);
+		const float	 d0 = __fsub_rn(qq.x, vp[16 * b]), d1 = __fsub_rn(qq.y, vp[16 * b + 8]);
+		S = __fadd_rn(S, __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
+	}
+	float full[8];
+#pragma unroll
+	for (int l = 0; l < 8; l++) full[l] = __shfl_sync(kFull, S, l, 8);
+	float res = hsum4(__fadd_rn(full[0], full[4]), __fadd_rn(full[1], full[5]), __fadd_rn(full[2], full[6]), __fadd_rn(full[3], full[7]));
+	res = l2_tail_exact(res, q_tail, rowp + main_n, dim - main_n);
+	return __fsqrt_rn(res);
+}
+
+template <int METRIC, int TPR>
+__device__ __forceinline__ float score_row(const float *__restrict__ qts, const float *__restrict__ rowp, int sub, int main_n,
+										   const float *__restrict__ q_tail, int dim, float qn, float vn)
+{
+	static_assert(TPR == 4 || (TPR == 8 && METRIC == M_L2), "8 lanes per row exist for L2 only (8 accumulator lanes)");
+	if (TPR == 8) return score_row8_l2(qts, rowp, sub, main_n, q_tail, dim);
+	return score_row4<METRIC>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
+}
+
 // ---- latency mode (COOP) -------------------------------------------------------------------------------
 // With fewer queries than SMs a query has a whole SM to itself, and the per-hop latency -- not bytes in
 // flight -- is what a caller of hnsw_search() waits for.  The CTA then runs ONE slot: warp 0 owns the
@@ -252,14 +283,15 @@ __device__ __forceinline__ float score_row4(const float *__restrict__ qts, const
 __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif
 
-template <int METRIC>
+template <int METRIC, int TPR>
 __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char *ring, uint64_t *rbar, uint32_t &rpar, uint32_t warp,
 											uint32_t nwarps, uint32_t n, const uint32_t *hop_id, uint64_t *hop_key, const float *qT,
 											const float *q_tail, float qn, int main_n, uint64_t pol_stream)
 {
 	const uint32_t lane = threadIdx.x & 31;
-	const int	   row_in_stage = lane / kTPR;
-	const int	   sub = lane % kTPR;
+	constexpr int  kRows = 32 / TPR;
+	const int	   row_in_stage = lane / TPR;
+	const int	   sub = lane % TPR;
 	const uint32_t G = (n + kRows - 1) / kRows;
 	const float	  *qts = qT + sub * p.qt_stride;
 	for (uint32_t g = warp; g < G; g += nwarps)
@@ -280,15 +312,16 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 		mbar_wait(rbar, rpar);
 		rpar ^= 1u;
 		const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
-		const float	 d = score_row4<METRIC>(qts, rowp, sub, main_n, q_tail, (int) p.dim, qn, vn);
+		const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, (int) p.dim, qn, vn);
 		if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
 		__syncwarp();
 	}
 }
 
-template <int METRIC, bool COOP>
+template <int METRIC, bool COOP, int TPR = 4>
 __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
+	constexpr int kRows = 32 / TPR;	 // rows per ring
 	PGEMB_DYNAMIC_SMEM(smem, 128);
 	const uint32_t lane = threadIdx.x & 31;
 	const uint32_t warp = threadIdx.x >> 5;
@@ -307,8 +340,8 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	uint64_t	  *pf_bar = reinterpret_cast<uint64_t *>(priv + p.off_pfbar);
 
 	const uint32_t lt = lanemask_lt();
-	const int	   row_in_stage = lane / kTPR;
-	const int	   sub = lane % kTPR;
+	const int	   row_in_stage = lane / TPR;
+	const int	   sub = lane % TPR;
 	const uint32_t ef = p.ef;
 	const int	   dim = (int) p.dim;
 	const int	   main_n = main_len<METRIC>(dim);
@@ -349,7 +382,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 			const uint32_t hn = *reinterpret_cast<volatile uint32_t *>(&pool->coop_n);
 			if (hn == kNone) break;
 			const float hq = *reinterpret_cast<volatile float *>(&pool->coop_qn);
-			coop_gather<METRIC>(p, my_ring, &pool->bar[warp], coop_par, warp, blockDim.x >> 5, hn, hop_id, hop_key, qT, q_tail, hq, main_n, pol_stream);
+			coop_gather<METRIC, TPR>(p, my_ring, &pool->bar[warp], coop_par, warp, blockDim.x >> 5, hn, hop_id, hop_key, qT, q_tail, hq, main_n, pol_stream);
 			coop_bar(2, blockDim.x);
 		}
 		return;
@@ -407,6 +440,11 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 						continue;
 					if (e >= main_n)
 						q_tail[e - main_n] = v;
+					else if (METRIC == M_L2 && TPR == 8)
+					{
+						const int b = e >> 4, o = e & 15;
+						qT[(o & 7) * p.qt_stride + 2 * b + (o >> 3)] = v;
+					}
 					else if (METRIC == M_L2)
 					{
 						const int b = e >> 4, o = e & 15, l = o & 7;
@@ -474,7 +512,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					if (lane == 0) pool->coop_n = n;
 					__syncwarp();
 					coop_bar(1, blockDim.x);
-					coop_gather<METRIC>(p, ring_base, &pool->bar[0], coop_par, 0, blockDim.x >> 5, n, hop_id, hop_key, qT, q_tail, qn, main_n, pol_stream);
+					coop_gather<METRIC, TPR>(p, ring_base, &pool->bar[0], coop_par, 0, blockDim.x >> 5, n, hop_id, hop_key, qT, q_tail, qn, main_n, pol_stream);
 					coop_bar(2, blockDim.x);
 				}
 				else
@@ -529,7 +567,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					mbar_wait(rbar, rpar);
 					rpar ^= 1u;
 					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
-					const float	 d = score_row4<METRIC>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
+					const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
 					if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
 					__syncwarp();
 					if (g + 1 < G) issue(g + 1);

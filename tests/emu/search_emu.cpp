@@ -13,9 +13,9 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 							 int32_t *n_out, uint32_t *stats_out, uint32_t want_warps, uint32_t want_rings, uint32_t grid, uint32_t vh_size,
 							 uint32_t visited_pairs, uint32_t smem_visited, int *error_out);
 
-template <int METRIC, bool COOP> static void go(const SearchParams &p, unsigned grid, unsigned warps, size_t smem)
+template <int METRIC, bool COOP, int TPR = 4> static void go(const SearchParams &p, unsigned grid, unsigned warps, size_t smem)
 {
-	emu::launch(dim3(grid), warps * 32, smem, [=]() { search_kernel<METRIC, COOP>(p); });
+	emu::launch(dim3(grid), warps * 32, smem, [=]() { search_kernel<METRIC, COOP, TPR>(p); });
 }
 
 // returns 0 on success, >0 = make_search_config's code, -1 = bad metric; *error_out = the kernel's sticky error flag
@@ -47,6 +47,8 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	tu.want_warps = (int) want_warps;
 	tu.want_rings = (int) want_rings;
 	tu.want_coop_warps = (int) want_warps;
+	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;
+	smem_visited &= 0x7fffffffu;
 	tu.smem_visited = (int) smem_visited;
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
@@ -106,6 +108,11 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	apply_config(p, cfg, row_f);
 	unsigned g = nq < grid ? nq : grid;
 	if (g == 0) g = 1;
+	if (cfg.tpr == 8)
+	{
+		if (coop) go<M_L2, true, 8>(p, g, cfg.warps, cfg.smem); else go<M_L2, false, 8>(p, g, cfg.warps, cfg.smem);
+	}
+	else
 	switch (metric * 2 + (coop ? 1 : 0))
 	{
 		case 0: go<M_L2, false>(p, g, cfg.warps, cfg.smem); break;

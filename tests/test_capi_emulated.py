@@ -193,3 +193,10 @@ def test_prototype_tiled_scan(pg, G, oracle_mod, metric, monkeypatch):
             assert out["labels"][i].tolist() == [o[1] for o in order], (metric, dims, i)
             assert out["dists"][i].tobytes() == np.array([o[0] for o in order], np.float32).tobytes()
         idx.close()
+
+
+def test_prototype_l2_eight_lanes(pg, G, oracle_mod, monkeypatch):
+    monkeypatch.setenv("PGEMB_L2_TPR8", "1")
+    monkeypatch.setenv("PGEMB_L2_TPR8_MIN_BYTES", "0")     # the small test rows too
+    G.test_search_identical_to_oracle(pg, oracle_mod, "l2", G.SEARCH_CFGS[3])
+    G.test_bind_links_identical_to_oracle(pg, oracle_mod, "l2", G.BIND_CFGS[0])

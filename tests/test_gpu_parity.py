@@ -232,6 +232,15 @@ def test_visited_pairs_mode(pg, oracle_mod, cfg, flags, monkeypatch):
         idx.close()
 
 
+def test_l2_eight_lanes_per_row(pg, oracle_mod, monkeypatch):
+    """PGEMB_L2_TPR8=1 (prototype): long L2 rows scored by 8 lanes per row, rings of 4 rows."""
+    monkeypatch.setenv("PGEMB_L2_TPR8", "1")
+    monkeypatch.setenv("PGEMB_L2_TPR8_MIN_BYTES", "0")
+    for cfg in (SEARCH_CFGS[3], SEARCH_CFGS[4], SEARCH_CFGS[7]):
+        test_search_identical_to_oracle(pg, oracle_mod, "l2", cfg)
+    test_bind_links_identical_to_oracle(pg, oracle_mod, "l2", BIND_CFGS[4])
+
+
 def test_search_empty_and_tiny(pg, oracle_mod):
     idx = pg.HnswIndex(4, 3, 8, 8, "l2", capacity=8)
     out = idx.search_batch(np.zeros((3, 4), np.float32), 8)

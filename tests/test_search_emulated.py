@@ -47,7 +47,7 @@ def emu(tmp_path_factory):
     return lib
 
 
-def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0):
+def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0, tpr8=False):
     n, dim = x.shape
     row_f = (dim + 3) & ~3
     ls = (maxm + 1 + 3) & ~3
@@ -61,7 +61,7 @@ def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid
     rc = lib.emu_search_ex(METRIC_ID[metric], coop, _p(xv, C.c_float), _p(lk, C.c_uint32), _p(labels, C.c_uint64), _p(norms, C.c_float),
                         C.c_uint32(n), C.c_uint32(dim), C.c_uint32(row_f), C.c_uint32(ls), C.c_uint32(maxm), _p(np.ascontiguousarray(q), C.c_float),
                         C.c_uint32(nq), C.c_uint32(ef), 0, _p(lab, C.c_uint64), _p(dd, C.c_float), _p(ids, C.c_uint32), _p(nn, C.c_int32),
-                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited), C.byref(err))
+                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited | (0x80000000 if tpr8 else 0)), C.byref(err))
     assert rc == 0, rc
     assert err.value == 0, hex(err.value)
     return dict(labels=lab, dists=dd, ids=ids, n=nn, stats=st)
@@ -201,3 +201,22 @@ def test_fuzz_traversal_emulated(emu, oracle_mod):
         assert got["labels"].tobytes() == want["labels"].tobytes(), what
         assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), what
         orc.close()
+
+
+@pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
+@pytest.mark.parametrize("dims,m,n,levels", [(3, 3, 120, 3), (40, 20, 200, 0), (100, 6, 150, 0), (16, 4, 90, 2)])
+def test_l2_eight_lanes_per_row(emu, oracle_mod, dims, m, n, levels, coop):
+    """Prototype (PGEMB_L2_TPR8): L2 rows scored by 8 lanes, one reference accumulator lane each, rings of 4 rows."""
+    rng = np.random.default_rng(dims * 3 + n)
+    x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
+    q = rng.integers(0, levels, (5, dims)).astype(np.float32) if levels else rng.standard_normal((5, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, 16, 64, "l2", capacity=n)
+    orc.build(x)
+    for ef in (3, 24):
+        want = orc.search_many(q, ef, want_counters=True)
+        got = run_emu(emu, "l2", coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=3, rings=2, grid=2, vh=64, tpr8=True)
+        assert got["labels"].tobytes() == want["labels"].tobytes()
+        assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+        for qi in range(q.shape[0]):
+            k = int(got["n"][qi])
+            assert got["dists"][qi, :k].tobytes() == oracle_mod.dist_many("port", "l2", q[qi], x[got["ids"][qi, :k]]).tobytes()

@@ -25,6 +25,9 @@ timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "latency with the shared-memory visited set (PGEMB_SMEM_VISITED=4096)"
 PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+say "1536-d L2 (configs[3] row shape): 4 lanes/row vs 8 lanes/row"
+timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
+PGEMB_L2_TPR8=1 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
 say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
