@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpgemb_b200.so")
+# PGEMB_LIB_VARIANT=proto loads the same sources built with -DPGEMB_PROTO (opt-in prototypes not yet measured on a
+# B200; build.py).  Anything else is the product library.
+VARIANT = os.environ.get("PGEMB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(HERE, "libpgemb_b200_proto.so" if VARIANT == "proto" else "libpgemb_b200.so")
 
 PGEMB_OK = 0
 

@@ -14,6 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpgemb_b200.so")
+# same sources with -DPGEMB_PROTO: the opt-in prototypes that have not been measured on a B200 yet.
+# Only loaded when PGEMB_LIB_VARIANT=proto (tests and tools/gpu_r2_first.sh); the product library above never contains them.
+OUT_PROTO = os.path.join(HERE, "libpgemb_b200_proto.so")
 SOURCES = ["capi.cu"]
 HEADERS = ["common.cuh", "dist_exact.cuh", "search_kernel.cuh", "aux_kernels.cuh", "bind_kernel.cuh", "scan_tile_kernel.cuh", "search_config.h",
            os.path.join("..", "..", "include", "pgemb_b200.h")]
@@ -26,31 +29,39 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
-    if not os.path.isfile(OUT):
+def needs_build(out: str = OUT) -> bool:
+    if not os.path.isfile(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return OUT
-    cmd = [
+def _cmd(out: str, proto: bool, verbose: bool) -> list:
+    return [
         nvcc_path(), "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-fmad=false",  # exact kernels use explicit _rn intrinsics; never contract anything else either
         "-Xptxas", "-v" if verbose else "-warn-spills",
         "-I", os.path.join(HERE, "..", "include"),
-        "-o", OUT,
-    ] + [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + "\n" + res.stderr)
-    if verbose:
-        print(res.stdout)
-        print(res.stderr)
+        "-o", out,
+    ] + (["-DPGEMB_PROTO"] if proto else []) + [os.path.join(CSRC, f) for f in SOURCES]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Build the product library and the prototype variant (both in-tree); returns the product library's path."""
+    jobs = []
+    for out, proto in ((OUT, False), (OUT_PROTO, True)):
+        if force or needs_build(out):
+            cmd = _cmd(out, proto, verbose)
+            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for cmd, pr in jobs:
+        so, se = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + so + "\n" + se)
+        if verbose:
+            print(so)
+            print(se)
     return OUT
 
 

@@ -22,6 +22,7 @@ __global__ void norms_kernel(const float *__restrict__ vectors, uint32_t row_f, 
 	if (row < n && sub == 0) norms[first + row] = s;
 }
 
+#ifdef PGEMB_PROTO
 // ---- invariant check for caller-provided link lists: are the ids of every list distinct? ----------------
 // (Lists written by the bind kernels always are; the traversal may then test-and-set both halves of a list
 // concurrently, search_kernel.cuh `visited_pairs`.)  One warp per node; sets *dup_flag if any list repeats an id.
@@ -42,6 +43,7 @@ __global__ void links_distinct_kernel(const uint32_t *__restrict__ links, uint32
 	}
 	if (dup) *dup_flag = 1;
 }
+#endif
 
 // ---- pair distances: out[i] = dist(a[i] | a[0], b[i]); LANES threads per pair, scalar loads --------
 template <int METRIC>

@@ -18,7 +18,9 @@
 #include "aux_kernels.cuh"
 #include "bind_kernel.cuh"
 #include "common.cuh"
+#ifdef PGEMB_PROTO
 #include "scan_tile_kernel.cuh"
+#endif
 #include "search_kernel.cuh"
 
 using namespace pgemb;
@@ -43,7 +45,11 @@ static pgemb_status fail(pgemb_status st, const std::string &msg)
 	} while (0)
 
 extern "C" const char *pgemb_last_error(void) { return g_last_error.c_str(); }
+#ifdef PGEMB_PROTO
+extern "C" const char *pgemb_version(void) { return "pg_embedding_b200 0.1 (sm_100a) +proto"; }
+#else
 extern "C" const char *pgemb_version(void) { return "pg_embedding_b200 0.1 (sm_100a)"; }
+#endif
 extern "C" uint64_t	   pgemb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int pgemb_device_count(void)
@@ -447,14 +453,18 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	sh.maxM = (uint32_t) idx->meta.maxM;
 	sh.ef = ef;
 	sh.sm_count = (uint32_t) idx->sm_count;
+#ifdef PGEMB_PROTO
 	// opt-in prototype: 8 lanes per row (4-row rings) for long L2 rows
 	sh.tpr = (sh.metric == DIST_L2 && env_int("PGEMB_L2_TPR8", 0) != 0 && idx->row_f * 4u >= (uint32_t) env_int("PGEMB_L2_TPR8_MIN_BYTES", 4096)) ? 8u : 4u;
+#endif
 	SearchTuning tu;
 	tu.duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
 	tu.want_warps = env_int("PGEMB_WARPS", 0);
 	tu.want_rings = env_int("PGEMB_RINGS", 0);
 	tu.want_coop_warps = env_int("PGEMB_COOP_WARPS", 0);
+#ifdef PGEMB_PROTO
 	tu.smem_visited = env_int("PGEMB_SMEM_VISITED", 0);  // opt-in prototype: entries of the latency mode's shared-memory visited set
+#endif
 	switch (make_search_config(sh, tu, coop, c))
 	{
 		case 0: return PGEMB_OK;
@@ -467,7 +477,11 @@ typedef void (*search_fn_t)(const SearchParams);
 
 static search_fn_t pick_search_kernel(int metric, bool coop, uint32_t tpr)
 {
+#ifdef PGEMB_PROTO
 	if (metric == DIST_L2 && tpr == 8) return coop ? search_kernel<M_L2, true, 8> : search_kernel<M_L2, false, 8>;
+#else
+	if (tpr != 4) return nullptr;
+#endif
 	switch (metric)
 	{
 		case DIST_L2: return coop ? search_kernel<M_L2, true> : search_kernel<M_L2, false>;
@@ -601,6 +615,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.error_flag = idx->d_error;
 	apply_config(p, cfg, idx->row_f);
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
+#ifdef PGEMB_PROTO
 	p.visited_pairs = 0;
 	if (env_int("PGEMB_VISITED_PAIRS", 0) != 0)
 	{
@@ -619,6 +634,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		}
 		p.visited_pairs = idx->links_distinct ? 1u : 0u;
 	}
+#endif
 
 	if (vh && idx->l2_window_max > 0 && env_int("PGEMB_L2_PERSIST", 1))
 	{
@@ -897,7 +913,11 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	const int	   metric = (int) idx->meta.dist_func;
 	const uint32_t lanes = (metric == DIST_L2) ? 8 : 4;
 	// tiled distance step (scan_tile_kernel.cuh): same bits, rows read once per query tile.  Opt-in until measured.
+#ifdef PGEMB_PROTO
 	const bool tiled = env_int("PGEMB_SCAN_TILED", 0) != 0;
+#else
+	const bool tiled = false;
+#endif
 	if (tiled && metric == DIST_COSINE)
 	{
 		PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nq * 4 + 127) / 128), 128, 0, s, d_q, (uint32_t) dim, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
@@ -915,13 +935,16 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 #define SCAN_TILE(MM)                                                                                                              \
 	PGEMB_LAUNCH(scan_tile_kernel<MM>, dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), kScanThreads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, d_qn,  \
 												 (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
+#ifdef PGEMB_PROTO
 		if (tiled)
 		{
 			if (metric == DIST_L2) SCAN_TILE(M_L2);
 			else if (metric == DIST_COSINE) SCAN_TILE(M_COS);
 			else SCAN_TILE(M_MAN);
 		}
-		else if (metric == DIST_L2) SCAN_DIST(M_L2);
+		else
+#endif
+		if (metric == DIST_L2) SCAN_DIST(M_L2);
 		else if (metric == DIST_COSINE) SCAN_DIST(M_COS);
 		else SCAN_DIST(M_MAN);
 #undef SCAN_TILE

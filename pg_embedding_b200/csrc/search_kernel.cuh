@@ -40,7 +40,15 @@
 
 namespace pgemb {
 
+// Opt-in prototypes that have not run on a B200 yet are compiled only with -DPGEMB_PROTO, into a
+// separate library (libpgemb_b200_proto.so): the product library's traversal kernels stay instruction-for-instruction
+// the ones that were measured.
+#ifdef PGEMB_PROTO
 #define PGEMB_HAS_VISITED_PAIRS 1
+constexpr bool kProto = true;
+#else
+constexpr bool kProto = false;
+#endif
 struct SearchParams
 {
 	// index (HBM, SoA)
@@ -70,7 +78,9 @@ struct SearchParams
 	uint32_t	 *vhash;		 // [slots][vh_size]     open-addressing visited set, 0xffffffff = empty
 	uint32_t	  vis_words, vlog_cap;
 	uint32_t	  vh_size, vh_shift;  // vh_size = 2^k entries (0: bitmap only), hash = (id * 2654435761) >> vh_shift
+#ifdef PGEMB_PROTO
 	uint32_t	  off_vhs, vhs_entries;	 // latency mode: the hash set lives in the CTA's shared memory (2^k entries, 0 = use vhash)
+#endif
 	unsigned int *counter;		 // work-stealing query counter
 	const unsigned int *avail;	 // optional: number of queries whose data has landed (host API streams them in while the kernel runs)
 	int			 *error_flag;	 // sticky: 1 = bad link id / count, 2 = overflow buffer exceeded
@@ -80,7 +90,9 @@ struct SearchParams
 	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
 	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
 	uint32_t prefetch_links;
+#ifdef PGEMB_PROTO
 	uint32_t visited_pairs;	 // 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
+#endif
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
 	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
 };
@@ -89,8 +101,10 @@ struct SearchParams
 // copy the shared-memory layout chosen by make_search_config into the kernel parameters
 inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_f)
 {
+#ifdef PGEMB_PROTO
 	p.off_vhs = cfg.off_vhs;
 	p.vhs_entries = cfg.vhs_entries;
+#endif
 	p.rings = cfg.rings;
 	p.ring_bytes = cfg.ring_bytes;
 	p.off_pool = cfg.off_pool;
@@ -347,13 +361,23 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	const int	   main_n = main_len<METRIC>(dim);
 	// latency mode keeps the open-addressing visited set in shared memory when the CTA has room for it: a hop's
 	// test-and-set round then costs shared-memory atomics instead of L2 round trips
+#ifdef PGEMB_PROTO
 	const bool	   vh_shared = COOP && p.vhs_entries != 0u;
 	const uint32_t H = vh_shared ? p.vhs_entries : p.vh_size;
 	const uint32_t vh_shift = vh_shared ? (32u - (uint32_t) __popc(p.vhs_entries - 1u)) : p.vh_shift;
+#else
+	constexpr bool vh_shared = false;
+	const uint32_t H = p.vh_size;
+	const uint32_t vh_shift = p.vh_shift;
+#endif
 	uint32_t	  *vis = p.visited + (size_t) slot * p.vis_words;
 	uint32_t	  *vlog = p.vlog + (size_t) slot * p.vlog_cap;
 	uint64_t	  *ovf = p.ovf + (size_t) slot * ef;
+#ifdef PGEMB_PROTO
 	uint32_t	  *vh = vh_shared ? reinterpret_cast<uint32_t *>(smem + p.off_vhs) : p.vhash + (size_t) slot * H;
+#else
+	uint32_t	  *vh = p.vhash + (size_t) slot * H;
+#endif
 	const uint64_t pol_stream = l2_policy_evict_first();
 	const uint64_t pol_keep = l2_policy_evict_last();
 	constexpr uint32_t kEmpty = 0xffffffffu;
@@ -844,6 +868,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				__syncwarp();
 				vmode = 1;
 			}
+#ifdef PGEMB_PROTO
 			if (p.visited_pairs)
 			{
 				// Two 32-id chunks of the list per iteration with BOTH chunks' test-and-set atomics in flight before
@@ -910,6 +935,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				}
 			}
 			else
+#endif
 			for (uint32_t base = 0; base < cnt; base += 32)
 			{
 				// list position k = base + lane lives in word k + 1

@@ -53,7 +53,11 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
 	if (rc) return rc;
+#ifdef PGEMB_PROTO
 	if (coop && smem_visited && cfg.vhs_entries == 0) return 77;  // the test asked for the shared-memory set
+#else
+	if (visited_pairs || smem_visited || cfg.tpr != 4) return 78;  // prototypes exist only in the -DPGEMB_PROTO build
+#endif
 	const uint32_t slots = coop ? grid : grid * cfg.warps;
 	const uint32_t vis_words = (n_items + 31) / 32 + 1;
 	const uint32_t vlog_cap = n_items < 32768 ? n_items + 1 : 32768;
@@ -108,11 +112,13 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	apply_config(p, cfg, row_f);
 	unsigned g = nq < grid ? nq : grid;
 	if (g == 0) g = 1;
+#ifdef PGEMB_PROTO
 	if (cfg.tpr == 8)
 	{
 		if (coop) go<M_L2, true, 8>(p, g, cfg.warps, cfg.smem); else go<M_L2, false, 8>(p, g, cfg.warps, cfg.smem);
 	}
 	else
+#endif
 	switch (metric * 2 + (coop ? 1 : 0))
 	{
 		case 0: go<M_L2, false>(p, g, cfg.warps, cfg.smem); break;

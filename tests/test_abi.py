@@ -85,3 +85,29 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "libpgemb_port" not in src \
                     and "libpgemb_ref" not in src, f
+
+
+def test_product_library_holds_no_prototype_kernels(lib):
+    """Prototypes that have not been measured on a B200 are compiled only into the -DPGEMB_PROTO
+    variant; the product library's device code must not contain them, and both variants export the whole C ABI."""
+    import shutil
+    import subprocess
+    from pg_embedding_b200 import _lib, build
+    assert b"+proto" not in lib.pgemb_version()
+    proto = C.CDLL(build.OUT_PROTO)
+    proto.pgemb_version.restype = C.c_char_p
+    assert b"+proto" in proto.pgemb_version()
+    for name in _lib.ABI_SYMBOLS:
+        assert hasattr(proto, name), f"{name} not exported by the prototype variant"
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    def kernels(path):
+        out = subprocess.run([cuobjdump, "-symbols", path], capture_output=True, text=True).stdout
+        return set(re.findall(r"_ZN5pgemb\w+", out))
+    prod, prot = kernels(build.OUT), kernels(build.OUT_PROTO)
+    marks = ("scan_tile_kernel", "links_distinct_kernel", "ELi8EEEvNS_12SearchParams")
+    assert not [k for k in prod if any(m in k for m in marks)]
+    for m in marks:
+        assert any(m in k for k in prot), m
+    assert prod <= prot

@@ -16,10 +16,9 @@ pytestmark = pytest.mark.timeout(1800, method="thread")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def emu_lib(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("emu") / "libpgemb_emulated.so")
-    cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
+def _build_emulated(tmp_path_factory, proto):
+    out = str(tmp_path_factory.mktemp("emu") / ("libpgemb_emulated_proto.so" if proto else "libpgemb_emulated.so"))
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"] + (["-DPGEMB_PROTO"] if proto else []) + [
            "-I", os.path.join(ROOT, "tests", "emu", "fake_cuda"), "-I", os.path.join(ROOT, "include"), "-o", out,
            os.path.join(ROOT, "pg_embedding_b200", "csrc", "capi.cu"), os.path.join(ROOT, "tests", "emu", "emu_runtime.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -28,15 +27,43 @@ def emu_lib(tmp_path_factory):
     return _lib._bind(C.CDLL(out))
 
 
-@pytest.fixture()
-def pg(emu_lib, monkeypatch):
-    """pg_embedding_b200 with its library handle swapped for the emulated build (restored after each test)."""
+@pytest.fixture(scope="module")
+def emu_lib(tmp_path_factory):
+    """capi.cu as the product library compiles it."""
+    return _build_emulated(tmp_path_factory, False)
+
+
+@pytest.fixture(scope="module")
+def emu_lib_proto(tmp_path_factory):
+    """capi.cu with -DPGEMB_PROTO (what libpgemb_b200_proto.so holds): the opt-in prototypes are compiled in."""
+    return _build_emulated(tmp_path_factory, True)
+
+
+def _swap(lib, monkeypatch):
     import pg_embedding_b200 as pkg
     from pg_embedding_b200 import _lib
-    monkeypatch.setattr(_lib, "_lib", emu_lib)
+    monkeypatch.setattr(_lib, "_lib", lib)
     monkeypatch.setenv("PGEMB_EMU_SMS", "2")
     assert pkg.device_count() == 1
     return pkg
+
+
+@pytest.fixture()
+def pg(emu_lib, monkeypatch):
+    """pg_embedding_b200 with its library handle swapped for the emulated build (restored after each test)."""
+    return _swap(emu_lib, monkeypatch)
+
+
+@pytest.fixture()
+def pg_proto(emu_lib_proto, monkeypatch):
+    assert b"+proto" in emu_lib_proto.pgemb_version()
+    return _swap(emu_lib_proto, monkeypatch)
+
+
+@pytest.fixture(scope="module")
+def P():
+    import test_gpu_prototypes as p     # GPU tests of the prototype flags: bodies reused below
+    return p
 
 
 @pytest.fixture(scope="module")
@@ -164,11 +191,22 @@ def test_host_pointer_search_both_copy_orders(pg, G, oracle_mod, env, monkeypatc
     idx.close()
 
 
-# ---- prototype flags (branch r2-prototypes) through the whole emulated library ------------------------------------
+# ---- prototype flags (the -DPGEMB_PROTO build) through the whole emulated library -----------------------------------
+def test_product_build_ignores_prototype_flags(pg, G, oracle_mod, monkeypatch):
+    """The product library has no prototype code: the opt-in flags change nothing (same results, same version string)."""
+    from pg_embedding_b200 import _lib
+    assert b"+proto" not in _lib.load().pgemb_version()
+    for k, v in {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "1024", "PGEMB_L2_TPR8": "1", "PGEMB_L2_TPR8_MIN_BYTES": "0", "PGEMB_SCAN_TILED": "1"}.items():
+        monkeypatch.setenv(k, v)
+    G.test_search_identical_to_oracle(pg, oracle_mod, "l2", G.SEARCH_CFGS[3])
+    G.test_scan_topk_regress_seqscan(pg)
+
+
 @pytest.mark.parametrize("flags", [{"PGEMB_VISITED_PAIRS": "1"}, {"PGEMB_SMEM_VISITED": "1024"}, {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "2048"}],
                          ids=["pairs", "smem-visited", "both"])
-def test_prototype_traversal_flags(pg, G, oracle_mod, flags, monkeypatch):
-    G.test_visited_pairs_mode(pg, oracle_mod, G.SEARCH_CFGS[0], flags, monkeypatch)       # incl. the repeated-id fallback
+def test_prototype_traversal_flags(pg_proto, G, P, oracle_mod, flags, monkeypatch):
+    pg = pg_proto
+    P.test_visited_pairs_mode(pg, oracle_mod, G.SEARCH_CFGS[0], flags, monkeypatch)       # incl. the repeated-id fallback
     for k, v in flags.items():
         monkeypatch.setenv(k, v)
     G.test_search_identical_to_oracle(pg, oracle_mod, "cosine", G.SEARCH_CFGS[3])
@@ -176,7 +214,8 @@ def test_prototype_traversal_flags(pg, G, oracle_mod, flags, monkeypatch):
 
 
 @pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
-def test_prototype_tiled_scan(pg, G, oracle_mod, metric, monkeypatch):
+def test_prototype_tiled_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
+    pg = pg_proto
     monkeypatch.setenv("PGEMB_SCAN_TILED", "1")
     G.test_scan_topk_regress_seqscan(pg)
     rng = np.random.default_rng(3)
@@ -195,7 +234,8 @@ def test_prototype_tiled_scan(pg, G, oracle_mod, metric, monkeypatch):
         idx.close()
 
 
-def test_prototype_l2_eight_lanes(pg, G, oracle_mod, monkeypatch):
+def test_prototype_l2_eight_lanes(pg_proto, G, oracle_mod, monkeypatch):
+    pg = pg_proto
     monkeypatch.setenv("PGEMB_L2_TPR8", "1")
     monkeypatch.setenv("PGEMB_L2_TPR8_MIN_BYTES", "0")     # the small test rows too
     G.test_search_identical_to_oracle(pg, oracle_mod, "l2", G.SEARCH_CFGS[3])

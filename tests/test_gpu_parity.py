@@ -198,49 +198,6 @@ def test_search_identical_to_oracle(pg, oracle_mod, metric, cfg):
     idx.close()
 
 
-@pytest.mark.parametrize("flags", [{"PGEMB_VISITED_PAIRS": "1"}, {"PGEMB_SMEM_VISITED": "4096"}, {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "1024"}],
-                         ids=["pairs", "smem-visited", "both"])
-@pytest.mark.parametrize("cfg", [SEARCH_CFGS[0], SEARCH_CFGS[5], SEARCH_CFGS[6], SEARCH_CFGS[7]], ids=lambda c: f"d{c[0]}m{c[1]}")
-def test_visited_pairs_mode(pg, oracle_mod, cfg, flags, monkeypatch):
-    """PGEMB_VISITED_PAIRS=1: both 32-id halves of a link list are test-and-set concurrently.  Same results, same
-    traversal counters; a graph whose lists repeat an id must be detected and served by the ordered path."""
-    for k, v in flags.items():
-        monkeypatch.setenv(k, v)
-    dims, m, efc, n, kw, efs = cfg
-    rng = np.random.default_rng(4242 + dims)
-    x = _data(rng, n, dims, **kw)
-    q = _data(rng, 200, dims, **{k: v for k, v in kw.items() if k == "levels"})
-    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
-    orc.build(x)
-    links = orc.links()
-    for dup in (False, True):
-        if dup:
-            # repeat an id inside the lists of a few well-connected nodes (positions in different 32-id halves when possible)
-            for node in np.argsort(-links[:, 0].astype(np.int64))[:5]:
-                c = int(links[node, 0])
-                if c >= 2:
-                    links[node, c] = links[node, 1]
-            orc.set_links(links)
-        idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
-        idx.append(x, None, links)
-        for coop, nq in (("1", 64), ("0", 200)):
-            with kernel_mode(coop):
-                out = idx.search_batch(q[:nq], efs[-1], want_stats=True)
-            want = orc.search_many(q[:nq], efs[-1], want_counters=True)
-            assert out["labels"].tobytes() == want["labels"].tobytes(), (dup, coop)
-            assert out["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), (dup, coop)
-        idx.close()
-
-
-def test_l2_eight_lanes_per_row(pg, oracle_mod, monkeypatch):
-    """PGEMB_L2_TPR8=1 (prototype): long L2 rows scored by 8 lanes per row, rings of 4 rows."""
-    monkeypatch.setenv("PGEMB_L2_TPR8", "1")
-    monkeypatch.setenv("PGEMB_L2_TPR8_MIN_BYTES", "0")
-    for cfg in (SEARCH_CFGS[3], SEARCH_CFGS[4], SEARCH_CFGS[7]):
-        test_search_identical_to_oracle(pg, oracle_mod, "l2", cfg)
-    test_bind_links_identical_to_oracle(pg, oracle_mod, "l2", BIND_CFGS[4])
-
-
 def test_search_empty_and_tiny(pg, oracle_mod):
     idx = pg.HnswIndex(4, 3, 8, 8, "l2", capacity=8)
     out = idx.search_batch(np.zeros((3, 4), np.float32), 8)
@@ -556,10 +513,8 @@ def test_edge_parameters(pg, oracle_mod, cfg):
 # ---------------------------------------------------------------------------------------------------
 # f3: exact scan (what ORDER BY val <op> q LIMIT k returns without the index; knn.out:63-91)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tiled", ["0", "1"])
 @pytest.mark.parametrize("metric", METRICS)
-def test_scan_topk_matches_exact_order(pg, oracle_mod, metric, tiled, monkeypatch):
-    monkeypatch.setenv("PGEMB_SCAN_TILED", tiled)      # 1: scan_tile_kernel (shared-memory tiles), 0: one pair per thread group
+def test_scan_topk_matches_exact_order(pg, oracle_mod, metric):
     rng = np.random.default_rng(99)
     for dims, n, k, levels in ((3, 500, 7, 3), (33, 3000, 64, 0), (128, 20000, 10, 0), (203, 4000, 10, 0), (768, 1500, 10, 0)):
         x = _data(rng, n, dims, levels=levels)

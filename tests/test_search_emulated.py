@@ -34,17 +34,30 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = str(tmp_path_factory.mktemp("emu") / "libsearch_emu.so")
+def _build_emu(tmp_path_factory, proto):
+    out = str(tmp_path_factory.mktemp("emu") / ("libsearch_emu_proto.so" if proto else "libsearch_emu.so"))
     src = [os.path.join(ROOT, "tests", "emu", f) for f in ("search_emu.cpp", "emu_runtime.cpp")]
     cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-I", os.path.join(ROOT, "tests", "emu", "fake_cuda"), "-o", out] + src
+    if proto:
+        cmd.insert(1, "-DPGEMB_PROTO")
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
     lib = C.CDLL(out)
     lib.emu_search.restype = C.c_int
     lib.emu_search_ex.restype = C.c_int
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    """The kernels as the product library compiles them (no -DPGEMB_PROTO)."""
+    return _build_emu(tmp_path_factory, False)
+
+
+@pytest.fixture(scope="module")
+def emu_proto(tmp_path_factory):
+    """The kernels as libpgemb_b200_proto.so compiles them: opt-in prototypes included."""
+    return _build_emu(tmp_path_factory, True)
 
 
 def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0, tpr8=False):
@@ -80,7 +93,8 @@ CASES = [
 @pytest.mark.parametrize("pairs", [0, 1], ids=["ordered-visited", "paired-visited"])
 @pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-d{c[1]}m{c[2]}" for c in CASES])
-def test_search_kernel_emulated_matches_oracle(emu, oracle_mod, case, coop, pairs):
+def test_search_kernel_emulated_matches_oracle(emu, emu_proto, oracle_mod, case, coop, pairs):
+    emu = emu_proto if pairs else emu
     metric, dims, m, efc, n, levels, ef, nq = case
     rng = np.random.default_rng(31 + dims)
     if levels:
@@ -145,7 +159,8 @@ def test_bind_kernels_emulated_match_oracle(emu, oracle_mod, case, coop):
 
 
 @pytest.mark.parametrize("n,ef", [(300, 12), (1500, 220)], ids=["small", "migrates-to-bitmap"])
-def test_latency_mode_shared_memory_visited_set(emu, oracle_mod, n, ef):
+def test_latency_mode_shared_memory_visited_set(emu_proto, oracle_mod, n, ef):
+    emu = emu_proto
     """Prototype (PGEMB_SMEM_VISITED): in latency mode the open-addressing visited set lives in the CTA's shared memory.
     The 1500-node case visits more than half of the 1024-entry table, so it also crosses the migration to the bitmap."""
     rng = np.random.default_rng(n)
@@ -162,7 +177,7 @@ def test_latency_mode_shared_memory_visited_set(emu, oracle_mod, n, ef):
         assert int(want["counters"][:, 0].max()) > 512, "case too small to cross the half-full migration"
 
 
-def test_fuzz_traversal_emulated(emu, oracle_mod):
+def test_fuzz_traversal_emulated(emu, emu_proto, oracle_mod):
     """300 seeded random configurations (metric, dims, m, ef, graph size, ties/duplicates, deleted labels, kernel mode,
     slots/rings/CTAs, visited-table size): labels, counts and traversal counters must equal the oracle's every time."""
     for seed in range(300):
@@ -195,7 +210,8 @@ def test_fuzz_traversal_emulated(emu, oracle_mod):
                 orc.mark_deleted(i)
         want = orc.search_many(q, ef, want_counters=True)
         pairs, sv = int(rng.integers(0, 2)), int(rng.choice([0, 1024]))
-        got = run_emu(emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh, pairs=pairs, smem_visited=sv if coop else 0)
+        sv = sv if coop else 0
+        got = run_emu(emu_proto if (pairs or sv) else emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh, pairs=pairs, smem_visited=sv)
         what = (seed, pairs, sv, metric, dims, m, efc, n, levels, ef, nq, coop, warps, rings, grid, vh)
         assert got["n"].tolist() == want["n"].tolist(), what
         assert got["labels"].tobytes() == want["labels"].tobytes(), what
@@ -205,7 +221,8 @@ def test_fuzz_traversal_emulated(emu, oracle_mod):
 
 @pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
 @pytest.mark.parametrize("dims,m,n,levels", [(3, 3, 120, 3), (40, 20, 200, 0), (100, 6, 150, 0), (16, 4, 90, 2)])
-def test_l2_eight_lanes_per_row(emu, oracle_mod, dims, m, n, levels, coop):
+def test_l2_eight_lanes_per_row(emu_proto, oracle_mod, dims, m, n, levels, coop):
+    emu = emu_proto
     """Prototype (PGEMB_L2_TPR8): L2 rows scored by 8 lanes, one reference accumulator lane each, rings of 4 rows."""
     rng = np.random.default_rng(dims * 3 + n)
     x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)

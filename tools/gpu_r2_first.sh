@@ -4,13 +4,15 @@
 mkdir -p gpurun_out
 L=gpurun_out/r2_first.log; : > $L
 say() { echo "== $*" | tee -a $L; }
-say "pytest -m gpu (includes the prototype parametrisations)"
+say "pytest -m gpu (product library: the measured kernels)"
 timeout 900 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider 2>&1 | tail -6 | tee -a $L
+say "pytest -m gpu of the prototypes (libpgemb_b200_proto.so)"
+PGEMB_LIB_VARIANT=proto timeout 900 python -m pytest tests/test_gpu_prototypes.py -m gpu -q --timeout=600 -p no:cacheprovider 2>&1 | tail -6 | tee -a $L
 say "smoke"; timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -1 | tee -a $L
 say "bench default"
 timeout 900 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err; echo "exit $?" | tee -a $L
 say "bench PGEMB_VISITED_PAIRS=1 (no cpu leg)"
-PGEMB_VISITED_PAIRS=1 timeout 600 python bench.py --no-cpu > gpurun_out/r2_bench_vpairs.json 2> gpurun_out/r2_bench_vpairs.err; echo "exit $?" | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_VISITED_PAIRS=1 timeout 600 python bench.py --no-cpu > gpurun_out/r2_bench_vpairs.json 2> gpurun_out/r2_bench_vpairs.err; echo "exit $?" | tee -a $L
 python - <<'PY' | tee -a $L
 import json
 for f in ("r2_bench_default", "r2_bench_vpairs"):
@@ -22,12 +24,12 @@ for f in ("r2_bench_default", "r2_bench_vpairs"):
 PY
 say "latency (both kernel modes), default and VISITED_PAIRS"
 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "latency with the shared-memory visited set (PGEMB_SMEM_VISITED=4096)"
-PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "1536-d L2 (configs[3] row shape): 4 lanes/row vs 8 lanes/row"
 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
-PGEMB_L2_TPR8=1 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_L2_TPR8=1 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
 say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
-PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
