@@ -1,5 +1,5 @@
 #!/bin/bash
-# First GPU run of round 2 (branch r2-prototypes): validate everything that round 1 could not re-run, then A/B the
+# First GPU run of round 2: validate everything that round 1 could not re-run, then A/B the
 # opt-in prototypes.  One gpurun call, ~6 min of box time.  Output: gpurun_out/r2_first.log (+ bench JSONs).
 mkdir -p gpurun_out
 L=gpurun_out/r2_first.log; : > $L
