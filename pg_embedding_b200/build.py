@@ -22,6 +22,12 @@ HEADERS = ["common.cuh", "dist_exact.cuh", "search_kernel.cuh", "aux_kernels.cuh
            os.path.join("..", "..", "include", "pgemb_b200.h")]
 
 
+# the GPU-owning sidecar process and the CUDA-free client library backends link against (csrc/sidecar)
+SIDECAR_DIR = os.path.join(CSRC, "sidecar")
+OUT_SIDECAR = os.path.join(HERE, "pgemb_sidecar")
+OUT_CLIENT = os.path.join(HERE, "libpgemb_client.so")
+
+
 def nvcc_path() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.isfile(cand):
@@ -55,6 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or needs_build(out):
             cmd = _cmd(out, proto, verbose)
             jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    build_sidecar(force)
     for cmd, pr in jobs:
         so, se = pr.communicate()
         if pr.returncode != 0:
@@ -63,6 +70,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(so)
             print(se)
     return OUT
+
+
+def build_sidecar(force: bool = False) -> tuple:
+    """pgemb_sidecar (C++, dlopen()s the C-ABI library) and libpgemb_client.so (plain C): host code only, no nvcc."""
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(SIDECAR_DIR, f) for f in ("server.cpp", "client.c", "ipc.h")] + [os.path.join(inc, "pgemb_b200.h"), os.path.join(inc, "pgemb_client.h")]
+    cmds = [
+        (OUT_SIDECAR, ["g++", "-std=c++17", "-O2", "-Wall", "-o", OUT_SIDECAR, os.path.join(SIDECAR_DIR, "server.cpp"), "-ldl", "-lrt"]),
+        (OUT_CLIENT, ["gcc", "-std=gnu11", "-O2", "-Wall", "-fPIC", "-shared", "-o", OUT_CLIENT, os.path.join(SIDECAR_DIR, "client.c"), "-lrt", "-lm"]),
+    ]
+    for out, cmd in cmds:
+        if force or not os.path.isfile(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                raise RuntimeError("sidecar build failed:\n" + " ".join(cmd) + "\n" + res.stdout + "\n" + res.stderr)
+    return OUT_SIDECAR, OUT_CLIENT
 
 
 if __name__ == "__main__":

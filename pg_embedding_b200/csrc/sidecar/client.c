@@ -1,0 +1,444 @@
+/*
+ * client.c -- libpgemb_client.so: the backend-side half of the sidecar protocol (ipc.h, include/pgemb_client.h).
+ * Plain C, no CUDA, no arithmetic: every call is a request executed by pgemb_sidecar with libpgemb_b200.so.
+ *
+ * Reference-shaped exports: hnsw_search (embedding.h:46, hnswalg.cpp:256-277), hnsw_bind_point (embedding.h:47,
+ * hnswalg.cpp:279-291), hnsw_dist_func / hnsw_init_dist_func (embedding.h:55-56, distfunc.c:157-174), hnsw_is_deleted
+ * (embedding.h:44, embedding.c:948-953) -- same signatures, ownership (results are malloc()ed here, free()d by the
+ * caller, embedding.c:327) and failure behaviour (false, never an exception or a longjmp).
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <fcntl.h>
+#include <linux/futex.h>
+#include <math.h>
+#include <sched.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/syscall.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../../include/pgemb_client.h"
+#include "ipc.h"
+
+static PgembIpcHeader *g_hdr = NULL;
+static unsigned char  *g_base = NULL;
+static size_t		   g_bytes = 0;
+static char			   g_name[256]; /* the segment we connected to last: a restarted sidecar re-creates it under the same name */
+static __thread char   g_err[256];
+
+static void set_err(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+const char *pgemb_client_last_error(void) { return g_err; }
+const char *pgemb_client_segment_name(void) { return g_name; }
+
+static inline uint32_t ld(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void	   st(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+static long futex(uint32_t *addr, int op, uint32_t val, const struct timespec *ts) { return syscall(SYS_futex, addr, op, val, ts, NULL, 0); }
+
+static double now_s(void)
+{
+	struct timespec t;
+	clock_gettime(CLOCK_MONOTONIC, &t);
+	return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
+}
+
+static PgembIpcSlot *slot_at(uint32_t i) { return (PgembIpcSlot *) (g_base + g_hdr->slots_off + (size_t) i * g_hdr->slot_stride); }
+static float		*slot_vec(PgembIpcSlot *s) { return (float *) ((unsigned char *) s + pgemb_ipc_payload_vec_off()); }
+static label_t		*slot_labels(PgembIpcSlot *s) { return (label_t *) ((unsigned char *) s + pgemb_ipc_payload_labels_off(g_hdr->max_dim)); }
+
+static int server_alive(void)
+{
+	if (!g_hdr || !ld(&g_hdr->ready)) return 0;
+	const pid_t pid = (pid_t) g_hdr->server_pid;
+	return pid > 0 && (kill(pid, 0) == 0 || errno != ESRCH);
+}
+
+int pgemb_client_connect(const char *shm_name, int timeout_ms)
+{
+	if (g_hdr && server_alive()) return PGEMB_OK;
+	if (g_hdr) pgemb_client_disconnect();  /* the sidecar we were mapped to is gone: look for a new one */
+	if ((!shm_name || !*shm_name) && g_name[0]) shm_name = g_name;
+	if (!shm_name || !*shm_name) shm_name = getenv("PGEMB_SIDECAR_SHM");
+	if (!shm_name || !*shm_name)
+	{
+		set_err("pgemb_client_connect: no segment name (argument or PGEMB_SIDECAR_SHM)");
+		return PGEMB_ERR_ARG;
+	}
+	const double deadline = now_s() + 1e-3 * (double) (timeout_ms > 0 ? timeout_ms : 0);
+	for (;;)
+	{
+		const int fd = shm_open(shm_name, O_RDWR, 0600);
+		if (fd >= 0)
+		{
+			struct stat sb;
+			if (fstat(fd, &sb) == 0 && (size_t) sb.st_size >= sizeof(PgembIpcHeader))
+			{
+				void *mem = mmap(NULL, (size_t) sb.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+				if (mem != MAP_FAILED)
+				{
+					PgembIpcHeader *h = (PgembIpcHeader *) mem;
+					if (__atomic_load_n(&h->magic, __ATOMIC_ACQUIRE) == PGEMB_IPC_MAGIC && h->version == PGEMB_IPC_VERSION && ld(&h->ready) &&
+						(size_t) sb.st_size >= h->bulk_off + h->bulk_bytes)
+					{
+						g_hdr = h;
+						g_base = (unsigned char *) mem;
+						g_bytes = (size_t) sb.st_size;
+						if (server_alive())
+						{
+							if (shm_name != g_name) snprintf(g_name, sizeof(g_name), "%s", shm_name);
+							close(fd);
+							return PGEMB_OK;
+						}
+						g_hdr = NULL;
+						g_base = NULL;
+					}
+					munmap(mem, (size_t) sb.st_size);
+				}
+			}
+			close(fd);
+		}
+		if (now_s() >= deadline) break;
+		usleep(2000);
+	}
+	set_err("pgemb_client_connect: no sidecar is serving %s", shm_name);
+	return PGEMB_ERR_STATE;
+}
+
+void pgemb_client_disconnect(void)
+{
+	if (g_base) munmap(g_base, g_bytes);
+	g_base = NULL;
+	g_hdr = NULL;
+	g_bytes = 0;
+}
+
+static int ensure_connected(void)
+{
+	if (g_hdr && server_alive()) return PGEMB_OK;
+	return pgemb_client_connect(NULL, 0);
+}
+
+/* ---- one request ------------------------------------------------------------------------------------------------ */
+static PgembIpcSlot *claim_slot(void)
+{
+	const uint32_t n = g_hdr->n_slots;
+	uint32_t	   start = ((uint32_t) getpid() * 2654435761u) % n;
+	const double   deadline = now_s() + 10.0;
+	for (;;)
+	{
+		for (uint32_t k = 0; k < n; k++)
+		{
+			PgembIpcSlot *s = slot_at((start + k) % n);
+			uint32_t	  expect = PGEMB_SLOT_FREE;
+			if (ld(&s->state) == PGEMB_SLOT_FREE &&
+				__atomic_compare_exchange_n(&s->state, &expect, PGEMB_SLOT_CLAIMED, 0, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED))
+			{
+				s->owner_pid = (int32_t) getpid();
+				s->status = 0;
+				s->n_out = 0;
+				s->a0 = s->a1 = s->a2 = s->a3 = 0;
+				s->ef = 0;
+				s->err[0] = 0;
+				return s;
+			}
+		}
+		if (!server_alive() || now_s() > deadline)
+		{
+			set_err("no free request slot (sidecar %s)", server_alive() ? "busy" : "gone");
+			return NULL;
+		}
+		sched_yield();
+	}
+}
+
+/* publish a filled slot, wait for the result; returns the request's status (the slot stays DONE: caller releases it) */
+static int submit_wait(PgembIpcSlot *s)
+{
+	st(&s->state, PGEMB_SLOT_READY);
+	__atomic_fetch_add(&g_hdr->submit_seq, 1u, __ATOMIC_SEQ_CST);
+	__atomic_thread_fence(__ATOMIC_SEQ_CST);
+	if (ld(&g_hdr->server_sleeping)) futex(&g_hdr->submit_seq, FUTEX_WAKE, 1, NULL);
+	/* a served request takes tens of microseconds to milliseconds: spin briefly, then sleep on the slot's futex */
+	const double spin_until = now_s() + 50e-6;
+	for (;;)
+	{
+		uint32_t v = ld(&s->state);
+		if (v == PGEMB_SLOT_DONE) break;
+		if (now_s() < spin_until)
+		{
+			__builtin_ia32_pause();
+			continue;
+		}
+		struct timespec ts = {0, 200 * 1000 * 1000};
+		futex(&s->state, FUTEX_WAIT, v, &ts);
+		if (ld(&s->state) != PGEMB_SLOT_DONE && !server_alive())
+		{
+			set_err("the sidecar went away while a request was pending");
+			/* the slot is lost to this segment; a new sidecar creates a new one */
+			return PGEMB_ERR_STATE;
+		}
+	}
+	if (s->status != PGEMB_OK) set_err("%s", s->err);
+	return s->status;
+}
+
+static void release_slot(PgembIpcSlot *s) { st(&s->state, PGEMB_SLOT_FREE); }
+
+/* the bulk area is one request's at a time */
+static int bulk_acquire(void)
+{
+	const uint32_t me = (uint32_t) getpid();
+	const double   deadline = now_s() + 60.0;
+	for (;;)
+	{
+		uint32_t expect = 0;
+		if (__atomic_compare_exchange_n(&g_hdr->bulk_lock, &expect, me, 0, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED)) return PGEMB_OK;
+		if (!server_alive() || now_s() > deadline)
+		{
+			set_err("bulk area unavailable");
+			return PGEMB_ERR_STATE;
+		}
+		usleep(50);
+	}
+}
+static void bulk_release(void) { st(&g_hdr->bulk_lock, 0); }
+
+/* a request without payload on the current mapping (never re-maps: callers may hold pointers into the segment) */
+static int do_request(PgembClientIndex *h, uint32_t op, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t *r0, uint64_t *r1,
+					  uint64_t *r2)
+{
+	int			  rc;
+	PgembIpcSlot *s = claim_slot();
+	if (!s) return PGEMB_ERR_STATE;
+	s->op = op;
+	s->index_key = h ? h->rel_key : 0;
+	s->a0 = a0;
+	s->a1 = a1;
+	s->a2 = a2;
+	s->a3 = a3;
+	rc = submit_wait(s);
+	if (r0) *r0 = s->a0;
+	if (r1) *r1 = s->a1;
+	if (r2) *r2 = s->a2;
+	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	return rc;
+}
+
+static int simple_request(PgembClientIndex *h, uint32_t op, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t *r0, uint64_t *r1,
+						  uint64_t *r2)
+{
+	const int rc = ensure_connected();
+	if (rc) return rc;
+	return do_request(h, op, a0, a1, a2, a3, r0, r1, r2);
+}
+
+/* ---- mirror maintenance ------------------------------------------------------------------------------------------ */
+int pgemb_client_attach(PgembClientIndex *h, size_t capacity, size_t *size_out, size_t *capacity_out)
+{
+	if (!h)
+	{
+		set_err("null index");
+		return PGEMB_ERR_ARG;
+	}
+	int rc = ensure_connected();
+	if (rc) return rc;
+	PgembIpcSlot *s = claim_slot();
+	if (!s) return PGEMB_ERR_STATE;
+	s->op = PGEMB_OP_ATTACH;
+	s->index_key = h->rel_key;
+	s->a0 = capacity;
+	memcpy(slot_vec(s), &h->meta, sizeof(HnswMetadata));
+	rc = submit_wait(s);
+	if (rc == PGEMB_OK)
+	{
+		if (size_out) *size_out = (size_t) s->a1;
+		if (capacity_out) *capacity_out = (size_t) s->a2;
+	}
+	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	return rc;
+}
+
+/* move `n` items of `item_bytes` through the bulk area in chunks; to_server: copy in before each request, else copy out after */
+static int bulk_transfer(PgembClientIndex *h, uint32_t op, size_t first, size_t n, size_t item_bytes, uint64_t stride_arg, void *data, int to_server)
+{
+	if (!h || (!data && n))
+	{
+		set_err("null argument");
+		return PGEMB_ERR_ARG;
+	}
+	if (n == 0) return PGEMB_OK;
+	int rc = ensure_connected();
+	if (rc) return rc;
+	if (item_bytes == 0 || item_bytes > g_hdr->bulk_bytes)
+	{
+		set_err("item larger than the sidecar's bulk area");
+		return PGEMB_ERR_ARG;
+	}
+	const size_t per = g_hdr->bulk_bytes / item_bytes;
+	rc = bulk_acquire();
+	if (rc) return rc;
+	unsigned char *bulk = g_base + g_hdr->bulk_off;
+	for (size_t done = 0; done < n && rc == PGEMB_OK; done += per)
+	{
+		const size_t k = (n - done < per) ? (n - done) : per;
+		if (to_server) memcpy(bulk, (const unsigned char *) data + done * item_bytes, k * item_bytes);
+		if (op == PGEMB_OP_APPEND_RECORDS)
+			rc = do_request(h, op, k, stride_arg, 0, 0, NULL, NULL, NULL);
+		else
+			rc = do_request(h, op, first + done, k, stride_arg, 0, NULL, NULL, NULL);
+		if (rc == PGEMB_OK && !to_server) memcpy((unsigned char *) data + done * item_bytes, bulk, k * item_bytes);
+	}
+	bulk_release();
+	return rc;
+}
+
+int pgemb_client_append_records(PgembClientIndex *h, size_t n, const void *records, size_t record_stride)
+{
+	return bulk_transfer(h, PGEMB_OP_APPEND_RECORDS, 0, n, record_stride, record_stride, (void *) records, 1);
+}
+
+int pgemb_client_export_records(PgembClientIndex *h, size_t first, size_t n, void *records, size_t record_stride)
+{
+	return bulk_transfer(h, PGEMB_OP_EXPORT_RECORDS, first, n, record_stride, record_stride, records, 0);
+}
+
+int pgemb_client_get_links(PgembClientIndex *h, size_t first, size_t n, idx_t *links_out)
+{
+	if (!h)
+	{
+		set_err("null index");
+		return PGEMB_ERR_ARG;
+	}
+	return bulk_transfer(h, PGEMB_OP_GET_LINKS, first, n, (h->meta.maxM + 1) * sizeof(idx_t), 0, links_out, 0);
+}
+
+int pgemb_client_set_labels(PgembClientIndex *h, size_t first, size_t n, const label_t *labels)
+{
+	return bulk_transfer(h, PGEMB_OP_SET_LABELS, first, n, sizeof(label_t), 0, (void *) labels, 1);
+}
+
+int pgemb_client_size(PgembClientIndex *h, size_t *size_out, size_t *capacity_out)
+{
+	uint64_t  a = 0, b = 0;
+	const int rc = simple_request(h, PGEMB_OP_SIZE, 0, 0, 0, 0, &a, &b, NULL);
+	if (rc == PGEMB_OK)
+	{
+		if (size_out) *size_out = (size_t) a;
+		if (capacity_out) *capacity_out = (size_t) b;
+	}
+	return rc;
+}
+
+int pgemb_client_truncate(PgembClientIndex *h) { return simple_request(h, PGEMB_OP_TRUNCATE, 0, 0, 0, 0, NULL, NULL, NULL); }
+int pgemb_client_drop(PgembClientIndex *h) { return simple_request(h, PGEMB_OP_DROP, 0, 0, 0, 0, NULL, NULL, NULL); }
+
+int pgemb_client_build(PgembClientIndex *h, size_t first, size_t n, size_t batch_max, int exact, double *seconds_out)
+{
+	uint64_t  sec_bits = 0;
+	const int rc = simple_request(h, PGEMB_OP_BUILD, first, n, batch_max, exact ? 1 : 0, NULL, NULL, &sec_bits);
+	if (rc == PGEMB_OK && seconds_out) memcpy(seconds_out, &sec_bits, sizeof(double));
+	return rc;
+}
+
+int pgemb_client_stats(uint64_t *n_batches, uint64_t *n_searches, uint64_t *max_batch)
+{
+	const int rc = ensure_connected();
+	if (rc) return rc;
+	if (n_batches) *n_batches = __atomic_load_n(&g_hdr->n_batches, __ATOMIC_RELAXED);
+	if (n_searches) *n_searches = __atomic_load_n(&g_hdr->n_searches, __ATOMIC_RELAXED);
+	if (max_batch) *max_batch = __atomic_load_n(&g_hdr->max_batch, __ATOMIC_RELAXED);
+	return PGEMB_OK;
+}
+
+int pgemb_client_shutdown_server(void) { return simple_request(NULL, PGEMB_OP_SHUTDOWN, 0, 0, 0, 0, NULL, NULL, NULL); }
+
+/* ---- the reference's algorithm-side symbols (embedding.h:44-56) -------------------------------------------------------- */
+bool hnsw_search(HnswMetadata *meta, const coord_t *point, size_t *n_results, label_t **results)
+{
+	if (!meta || !point || !n_results || !results) return false;
+	PgembClientIndex *h = (PgembClientIndex *) meta; /* embedding.c:706: the metadata is the first member of the handle */
+	if (ensure_connected() != PGEMB_OK) return false;
+	const size_t ef = meta->efSearch; /* re-read on every call: the caller doubles it (embedding.c:334) */
+	if (ef < 1 || ef > g_hdr->max_ef || meta->dim < 1 || meta->dim > g_hdr->max_dim)
+	{
+		set_err("hnsw_search: efSearch or dims outside the sidecar's limits");
+		return false;
+	}
+	label_t *buf = (label_t *) malloc(ef * sizeof(label_t));
+	if (!buf) return false;
+	PgembIpcSlot *s = claim_slot();
+	if (!s)
+	{
+		free(buf);
+		return false;
+	}
+	s->op = PGEMB_OP_SEARCH;
+	s->index_key = h->rel_key;
+	s->ef = (uint32_t) ef;
+	memcpy(slot_vec(s), point, meta->dim * sizeof(coord_t));
+	const int rc = submit_wait(s);
+	bool	  ok = false;
+	if (rc == PGEMB_OK && s->n_out >= 0 && (size_t) s->n_out <= ef)
+	{
+		memcpy(buf, slot_labels(s), (size_t) s->n_out * sizeof(label_t));
+		*n_results = (size_t) s->n_out;
+		*results = buf;
+		ok = true;
+	}
+	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	if (!ok) free(buf);
+	return ok;
+}
+
+bool hnsw_bind_point(HnswMetadata *meta, const coord_t *point, idx_t cur)
+{
+	(void) point; /* the node's record was shipped to the mirror before this call (embedding.c:619-621 stores it first) */
+	if (!meta) return false;
+	PgembClientIndex *h = (PgembClientIndex *) meta;
+	const int		  rc = simple_request(h, PGEMB_OP_BIND, cur, meta->efConstruction, 0, 0, NULL, NULL, NULL);
+	if (rc != PGEMB_OK)
+	{
+		fprintf(stderr, "Catch %s\n", pgemb_client_last_error()); /* hnswalg.cpp:288 */
+		return false;
+	}
+	return true;
+}
+
+dist_t hnsw_dist_func(dist_func_t dist, coord_t const *ax, coord_t const *bx, size_t dim)
+{
+	if (!ax || !bx || ensure_connected() != PGEMB_OK || dim < 1 || dim > g_hdr->max_dim) return NAN;
+	PgembIpcSlot *s = claim_slot();
+	if (!s) return NAN;
+	s->op = PGEMB_OP_DIST;
+	s->index_key = 0;
+	s->a0 = dim;
+	s->a1 = (uint64_t) dist;
+	memcpy(slot_vec(s), ax, dim * sizeof(coord_t));
+	memcpy(slot_vec(s) + g_hdr->max_dim, bx, dim * sizeof(coord_t));
+	const int rc = submit_wait(s);
+	float	  out = NAN;
+	if (rc == PGEMB_OK)
+	{
+		const uint32_t bits = (uint32_t) s->a2;
+		memcpy(&out, &bits, 4);
+	}
+	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	return out;
+}
+
+void hnsw_init_dist_func(void) { (void) pgemb_client_connect(NULL, 0); } /* called once from _PG_init (embedding.c:150) */
+
+bool hnsw_is_deleted(label_t label) { return ((label >> 48) & 1u) != 0; } /* embedding.c:44, :948-953 */

@@ -17,14 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _build_emulated(tmp_path_factory, proto):
-    out = str(tmp_path_factory.mktemp("emu") / ("libpgemb_emulated_proto.so" if proto else "libpgemb_emulated.so"))
-    cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"] + (["-DPGEMB_PROTO"] if proto else []) + [
-           "-I", os.path.join(ROOT, "tests", "emu", "fake_cuda"), "-I", os.path.join(ROOT, "include"), "-o", out,
-           os.path.join(ROOT, "pg_embedding_b200", "csrc", "capi.cu"), os.path.join(ROOT, "tests", "emu", "emu_runtime.cpp")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    assert res.returncode == 0, res.stderr[-4000:]
+    from emu_build import build_emulated
     from pg_embedding_b200 import _lib
-    return _lib._bind(C.CDLL(out))
+    return _lib._bind(C.CDLL(build_emulated(tmp_path_factory.mktemp("emu"), proto)))
 
 
 @pytest.fixture(scope="module")
