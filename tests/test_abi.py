@@ -111,3 +111,26 @@ def test_product_library_holds_no_prototype_kernels(lib):
     for m in marks:
         assert any(m in k for k in prot), m
     assert prod <= prot
+
+
+def test_client_library_exports_the_reference_symbols_and_no_cuda():
+    """libpgemb_client.so (what a forked backend links instead of hnswalg.o distfunc.o when a sidecar owns the GPU) exports
+    the algorithm-side symbols of embedding.h:44-56 plus everything include/pgemb_client.h declares, and has no CUDA in it."""
+    import subprocess
+    from pg_embedding_b200 import build
+    _, client_path = build.build_sidecar()
+    lib = C.CDLL(client_path)
+    header = open(os.path.join(ROOT, "include", "pgemb_client.h")).read()
+    declared = set(re.findall(r"\b(pgemb_client_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 12
+    for name in declared | {"hnsw_search", "hnsw_bind_point", "hnsw_dist_func", "hnsw_init_dist_func", "hnsw_is_deleted"}:
+        assert hasattr(lib, name), f"{name} not exported by libpgemb_client.so"
+    needed = subprocess.run(["ldd", client_path], capture_output=True, text=True).stdout
+    assert "cuda" not in needed.lower() and "pgemb_b200" not in needed
+    # without a sidecar every call fails -- there is nothing to fall back to
+    import numpy as np
+    lib.hnsw_dist_func.restype = C.c_float
+    a = np.ones(4, np.float32)
+    os.environ.pop("PGEMB_SIDECAR_SHM", None)
+    d = lib.hnsw_dist_func(0, a.ctypes.data_as(C.POINTER(C.c_float)), a.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(4))
+    assert np.isnan(d)
