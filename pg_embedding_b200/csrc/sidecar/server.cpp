@@ -506,9 +506,13 @@ int main(int argc, char **argv)
 	const size_t bytes = bulk_off + (bulk_mb << 20);
 	shm_unlink(shm_name.c_str());  // a stale segment of a dead sidecar
 	const int fd = shm_open(shm_name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
-	if (fd < 0 || ftruncate(fd, (off_t) bytes) != 0)
+	// posix_fallocate: a /dev/shm that is too small fails here, not with SIGBUS when a client touches the bulk area
+	int fe = 0;
+	if (fd < 0 || ftruncate(fd, (off_t) bytes) != 0 || (fe = posix_fallocate(fd, 0, (off_t) bytes)) != 0)
 	{
-		perror("pgemb_sidecar: shm_open/ftruncate");
+		if (fe) errno = fe;
+		perror("pgemb_sidecar: shm_open/ftruncate/posix_fallocate");
+		if (fd >= 0) shm_unlink(shm_name.c_str());
 		return 5;
 	}
 	void *mem = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);

@@ -203,6 +203,7 @@ class SidecarProcess:
                 raise SidecarError(f"pgemb_sidecar exited with {self.proc.returncode}: {self.proc.stderr.read()[-2000:]}")
             if client().pgemb_client_connect(self.shm_name.encode(), 50) == 0:
                 return
+        self.stop()
         raise SidecarError("pgemb_sidecar did not start serving")
 
     def stop(self, timeout_s: float = 30.0) -> int:

@@ -265,7 +265,7 @@ def test_sidecar_on_gpu_matches_oracle(oracle_mod, tmp_path):
     from pg_embedding_b200 import build, sidecar
     build.build()
     name = f"/pgemb_gpu_{os.getpid()}"
-    srv = sidecar.SidecarProcess(name, slots=128, bulk_mb=64)
+    srv = sidecar.SidecarProcess(name, slots=128, bulk_mb=8)
     srv.wait_ready(120)
     try:
         rng = np.random.default_rng(8)

@@ -86,7 +86,7 @@ def main():
     X = X.cpu().numpy() if hasattr(X, "cpu") else X
     Q = Q.cpu().numpy() if hasattr(Q, "cpu") else Q
     shm = f"/pgemb_bench_{os.getpid()}"
-    srv = sidecar.SidecarProcess(shm, lib=a.lib, slots=512, bulk_mb=256, linger_us=a.linger_us)
+    srv = sidecar.SidecarProcess(shm, lib=a.lib, slots=512, bulk_mb=64, linger_us=a.linger_us)
     srv.wait_ready(120)
     tmp = f"/tmp/pgemb_bench_{os.getpid()}"
     os.makedirs(tmp, exist_ok=True)
@@ -94,7 +94,7 @@ def main():
         idx = sidecar.RemoteIndex(1, a.dims, a.m, a.efc, a.efs, a.metric, capacity=a.rows)
         rs = idx.record_bytes
         t0 = time.time()
-        step = 65536
+        step = 16384  # 16384 x 3340 B = 55 MB per request: within the 64 MB bulk area
         for lo in range(0, a.rows, step):
             hi = min(a.rows, lo + step)
             rec = np.zeros((hi - lo, rs), np.uint8)
