@@ -6,6 +6,8 @@ namespace emu {
 thread_local Warp *tl_warp = nullptr;
 dim3			   g_block_dim, g_grid_dim;
 pthread_mutex_t	   g_mbar_mu = PTHREAD_MUTEX_INITIALIZER;
+int				   g_tma_late = 0;
+int				   g_tma_unwaited = 0;
 
 static void lane_trampoline()
 {
@@ -88,6 +90,10 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 {
 	g_grid_dim = grid;
 	g_block_dim = dim3(block_threads);
+	{
+		const char *m = getenv("PGEMB_EMU_TMA");
+		g_tma_late = (m && strcmp(m, "late") == 0) ? 1 : 0;
+	}
 	const unsigned nwarps = (block_threads + 31) / 32;
 	for (unsigned by = 0; by < grid.y; by++)
 		for (unsigned bx = 0; bx < grid.x; bx++)
@@ -115,9 +121,17 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 			}
 			for (auto &t : th) t.join();
 			for (auto *w : warps) delete w;
+			if (!cta.pending.empty())
+			{
+				// a bulk copy nobody waited for would land in the shared memory of a CTA that is gone
+				g_tma_unwaited += (int) cta.pending.size();
+				fprintf(stderr, "emu: %zu bulk copies were still in flight when CTA %u exited\n", cta.pending.size(), bx);
+			}
 			for (auto &b : cta.bars) pthread_barrier_destroy(&b);
 			free(cta.dyn_smem);
 		}
 }
 
 }  // namespace emu
+
+extern "C" int emu_tma_unwaited() { return emu::g_tma_unwaited; }

@@ -8,8 +8,10 @@
 //     and all lanes resume.  Warps of a CTA really run concurrently, so shared-memory locks and atomics between warps
 //     are exercised; CTAs of a grid run one after another.
 //   * shared memory: `__shared__` arrays become function-local statics, dynamic shared memory is a per-CTA buffer.
-//   * mbarrier + 1-D bulk TMA: the copy is performed synchronously by the issuing lane and accounted on the barrier
-//     (expect-tx / complete-tx / phase parity) -- one of the legal hardware schedules.
+//   * mbarrier + 1-D bulk TMA: the copy is accounted on the barrier (expect-tx / complete-tx / phase parity) and performed
+//     either by the issuing lane at once or -- PGEMB_EMU_TMA=late -- only when somebody polls that barrier: the two
+//     extreme legal hardware schedules.  Under "late" a consumer that reads a ring without waiting for its barrier sees
+//     the 0xAA fill instead of data, and a wait on the wrong barrier / parity never completes.
 //   * arithmetic: the _rn intrinsics are plain IEEE operations (compile with -ffp-contract=off, no fast-math).
 // It checks LOGIC (indexing, protocols, summation order), not memory-model races inside a warp and not speed.
 // Test infrastructure only; never part of the product build.
@@ -53,8 +55,10 @@ constexpr size_t kLaneStack = 192 * 1024;
 enum State { RUNNABLE, AT_COLL, DONE };
 enum Kind { K_WARP, K_CTA_BAR, K_CTA_OR };
 
+struct PendingCopy { void *dst; const void *src; uint32_t bytes; uint64_t *bar; };
 struct Cta
 {
+	std::vector<PendingCopy> pending;  // PGEMB_EMU_TMA=late: bulk copies issued but not yet performed (guarded by g_mbar_mu)
 	pthread_barrier_t bars[16];
 	unsigned		  nwarps = 0;
 	unsigned		  or_acc[2] = {0, 0};  // __syncthreads_or accumulators, double-buffered by phase
@@ -86,6 +90,8 @@ struct Warp
 extern thread_local Warp *tl_warp;
 extern dim3				   g_block_dim, g_grid_dim;
 extern pthread_mutex_t	   g_mbar_mu;
+extern int				   g_tma_late;	// set from PGEMB_EMU_TMA at every launch
+extern int				   g_tma_unwaited;	// copies still pending when their CTA exited (late schedule), since load
 
 inline Warp &W() { return *tl_warp; }
 inline Lane &L() { return tl_warp->lane[tl_warp->cur]; }
@@ -258,6 +264,24 @@ static inline bool mbar_try_wait(uint64_t *bar, uint32_t parity)
 	pthread_mutex_lock(&emu::g_mbar_mu);
 	emu::BarView v;
 	memcpy(&v, bar, 8);
+	{
+		// late schedule: the copies that signal this barrier land now
+		std::vector<emu::PendingCopy> &pq = emu::W().cta->pending;
+		for (size_t i = 0; i < pq.size();)
+		{
+			if (pq[i].bar != bar)
+			{
+				i++;
+				continue;
+			}
+			memcpy(pq[i].dst, pq[i].src, pq[i].bytes);
+			v.tx -= (int32_t) pq[i].bytes;
+			pq[i] = pq.back();
+			pq.pop_back();
+		}
+		emu::bar_complete_if_done(v);
+		memcpy(bar, &v, 8);
+	}
 	pthread_mutex_unlock(&emu::g_mbar_mu);
 	if ((v.w0 & 1u) != (parity & 1u)) return true;
 	emu::yield();
@@ -276,8 +300,14 @@ static inline void	   tma_load_1d(void *dst, const void *src, uint32_t bytes, ui
 		fprintf(stderr, "emu: cp.async.bulk needs 16-byte aligned addresses and size (dst %p src %p bytes %u)\n", dst, src, bytes);
 		abort();
 	}
-	memcpy(dst, src, bytes);
 	pthread_mutex_lock(&emu::g_mbar_mu);
+	if (emu::g_tma_late)
+	{
+		emu::W().cta->pending.push_back(emu::PendingCopy{dst, src, bytes, bar});
+		pthread_mutex_unlock(&emu::g_mbar_mu);
+		return;
+	}
+	memcpy(dst, src, bytes);
 	emu::BarView v;
 	memcpy(&v, bar, 8);
 	v.tx -= (int32_t) bytes;

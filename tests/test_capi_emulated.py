@@ -39,6 +39,9 @@ def _swap(lib, monkeypatch):
     from pg_embedding_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", lib)
     monkeypatch.setenv("PGEMB_EMU_SMS", "2")
+    # bulk copies land only when their mbarrier is polled (the schedule that exposes a missing / wrong wait);
+    # tests/test_search_emulated.py runs the kernels under both schedules
+    monkeypatch.setenv("PGEMB_EMU_TMA", "late")
     assert pkg.device_count() == 1
     return pkg
 

@@ -34,6 +34,14 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
 
+@pytest.fixture(autouse=True, params=["issue", "late"], ids=["tma-at-issue", "tma-late"])
+def tma_schedule(request, monkeypatch):
+    """Every test runs under the two extreme legal completion times of a bulk copy: performed when issued, or only when
+    its mbarrier is polled (a consumer that does not wait -- or waits on the wrong barrier / parity -- fails under "late")."""
+    monkeypatch.setenv("PGEMB_EMU_TMA", request.param)
+    return request.param
+
+
 def _build_emu(tmp_path_factory, proto):
     out = str(tmp_path_factory.mktemp("emu") / ("libsearch_emu_proto.so" if proto else "libsearch_emu.so"))
     src = [os.path.join(ROOT, "tests", "emu", f) for f in ("search_emu.cpp", "emu_runtime.cpp")]
@@ -77,6 +85,7 @@ def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid
                         _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited | (0x80000000 if tpr8 else 0)), C.byref(err))
     assert rc == 0, rc
     assert err.value == 0, hex(err.value)
+    assert lib.emu_tma_unwaited() == 0, "a bulk copy was still in flight when its CTA exited"
     return dict(labels=lab, dists=dd, ids=ids, n=nn, stats=st)
 
 
