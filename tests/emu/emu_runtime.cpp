@@ -57,7 +57,23 @@ void run_warp(Warp &w)
 		int live = 0;
 		for (int i = 0; i < 32; i++) live += (w.lane[i].st != DONE);
 		if (live == 0) break;
-		// every live lane waits at a collective: exchange and release
+		// every live lane waits at a collective: exchange and release.  The kernels of this repo only use full-mask
+		// collectives in warp-uniform control flow, so all waiting lanes must have arrived at the SAME call: lanes of
+		// one warp meeting at different collectives is divergence the hardware would not reconcile the way this
+		// scheduler does.
+		{
+			int site = -1;
+			for (int i = 0; i < 32; i++)
+			{
+				if (w.lane[i].st != AT_COLL) continue;
+				if (site < 0) site = w.lane[i].site;
+				if (w.lane[i].site != site)
+				{
+					fprintf(stderr, "emu: lanes of one warp wait at different collectives (source lines %d and %d): divergent use of a full-mask collective\n", site, w.lane[i].site);
+					abort();
+				}
+			}
+		}
 		if (w.kind == K_CTA_BAR) pthread_barrier_wait(&w.cta->bars[w.bar_id & 15]);
 		unsigned cta_or = 0;
 		if (w.kind == K_CTA_OR)

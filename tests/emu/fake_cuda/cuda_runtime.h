@@ -72,6 +72,7 @@ struct Lane
 	char	  *stack = nullptr;
 	State	   st = RUNNABLE;
 	uint64_t   xchg = 0;
+	int		   site = 0;  // source line of the collective this lane waits at
 	dim3	   tid;
 };
 
@@ -97,11 +98,12 @@ inline Warp &W() { return *tl_warp; }
 inline Lane &L() { return tl_warp->lane[tl_warp->cur]; }
 inline int	 lane_index() { return tl_warp->cur; }
 
-inline void collective(int kind, uint64_t v, int bar_id = 0)
+inline void collective(int kind, uint64_t v, int bar_id = 0, int site = 0)
 {
 	Warp &w = W();
 	Lane &l = w.lane[w.cur];
 	l.xchg = v;
+	l.site = site;
 	l.st = AT_COLL;
 	w.kind = kind;
 	w.bar_id = bar_id;
@@ -129,38 +131,38 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 #define gridDim (emu::g_grid_dim)
 
 // ---- barriers and warp collectives ------------------------------------------------------------------
-static inline void __syncthreads() { emu::collective(emu::K_CTA_BAR, 0, 0); }
-static inline int  __syncthreads_or(int pred)
+static inline void __syncthreads(int site = __builtin_LINE()) { emu::collective(emu::K_CTA_BAR, 0, 0, site); }
+static inline int  __syncthreads_or(int pred, int site = __builtin_LINE())
 {
-	emu::collective(emu::K_CTA_OR, pred ? 1u : 0u, 0);
+	emu::collective(emu::K_CTA_OR, pred ? 1u : 0u, 0, site);
 	return (int) emu::W().snap[emu::W().cur];  // the scheduler stores the CTA-wide result in every lane's slot
 }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::collective(emu::K_WARP, 0); }
-static inline unsigned __ballot_sync(unsigned, int pred)
+static inline void __syncwarp(unsigned = 0xffffffffu, int site = __builtin_LINE()) { emu::collective(emu::K_WARP, 0, 0, site); }
+static inline unsigned __ballot_sync(unsigned, int pred, int site = __builtin_LINE())
 {
-	emu::collective(emu::K_WARP, pred ? 1u : 0u);
+	emu::collective(emu::K_WARP, pred ? 1u : 0u, 0, site);
 	const emu::Warp &w = emu::W();
 	unsigned		 r = 0;
 	for (int i = 0; i < 32; i++)
 		if (w.present[i] && w.snap[i]) r |= 1u << i;
 	return r;
 }
-template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32)
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int width = 32, int site = __builtin_LINE())
 {
 	uint64_t b = 0;
 	memcpy(&b, &v, sizeof(T));
-	emu::collective(emu::K_WARP, b);
+	emu::collective(emu::K_WARP, b, 0, site);
 	const emu::Warp &w = emu::W();
 	const int		 base = w.cur / width * width;
 	T				 out;
 	memcpy(&out, &w.snap[base + ((src % width) + width) % width], sizeof(T));
 	return out;
 }
-template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32)
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lanemask, int width = 32, int site = __builtin_LINE())
 {
 	uint64_t b = 0;
 	memcpy(&b, &v, sizeof(T));
-	emu::collective(emu::K_WARP, b);
+	emu::collective(emu::K_WARP, b, 0, site);
 	const emu::Warp &w = emu::W();
 	int				 s = w.cur ^ lanemask;
 	if (s / width != w.cur / width) s = w.cur;
@@ -168,17 +170,17 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lanemas
 	memcpy(&out, &w.snap[s], sizeof(T));
 	return out;
 }
-static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
-static inline unsigned __match_any_sync(unsigned, unsigned v)
+static inline int __any_sync(unsigned m, int pred, int site = __builtin_LINE()) { return __ballot_sync(m, pred, site) != 0u; }
+static inline unsigned __match_any_sync(unsigned, unsigned v, int site = __builtin_LINE())
 {
-	emu::collective(emu::K_WARP, v);
+	emu::collective(emu::K_WARP, v, 0, site);
 	const emu::Warp &w = emu::W();
 	unsigned		 r = 0;
 	for (int i = 0; i < 32; i++)
 		if (w.present[i] && (unsigned) w.snap[i] == v) r |= 1u << i;
 	return r;
 }
-static inline void coop_bar(int id, uint32_t) { emu::collective(emu::K_CTA_BAR, 0, id); }
+static inline void coop_bar(int id, uint32_t, int site = __builtin_LINE()) { emu::collective(emu::K_CTA_BAR, 0, id, site); }
 
 // ---- bit tricks, conversions, arithmetic ------------------------------------------------------------
 static inline int	   __popc(unsigned v) { return __builtin_popcount(v); }
