@@ -7,6 +7,7 @@ thread_local Warp *tl_warp = nullptr;
 dim3			   g_block_dim, g_grid_dim;
 pthread_mutex_t	   g_mbar_mu = PTHREAD_MUTEX_INITIALIZER;
 int				   g_tma_late = 0;
+int				   g_jitter = 0;
 int				   g_tma_unwaited = 0;
 
 static void lane_trampoline()
@@ -109,6 +110,8 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 	{
 		const char *m = getenv("PGEMB_EMU_TMA");
 		g_tma_late = (m && strcmp(m, "late") == 0) ? 1 : 0;
+		const char *j = getenv("PGEMB_EMU_JITTER");
+		g_jitter = (j && *j && atoi(j) != 0) ? 1 : 0;
 	}
 	const unsigned nwarps = (block_threads + 31) / 32;
 	for (unsigned by = 0; by < grid.y; by++)

@@ -27,6 +27,7 @@
 #include <functional>
 #include <pthread.h>
 #include <sched.h>
+#include <time.h>
 #include <thread>
 #include <ucontext.h>
 #include <vector>
@@ -91,6 +92,7 @@ struct Warp
 extern thread_local Warp *tl_warp;
 extern dim3				   g_block_dim, g_grid_dim;
 extern pthread_mutex_t	   g_mbar_mu;
+extern int				   g_jitter;	// PGEMB_EMU_JITTER != 0: warps pause at random around atomics (perturbs the interleaving of slots)
 extern int				   g_tma_late;	// set from PGEMB_EMU_TMA at every launch
 extern int				   g_tma_unwaited;	// copies still pending when their CTA exited (late schedule), since load
 
@@ -115,6 +117,23 @@ inline void yield()
 	Warp &w = W();
 	Lane &l = w.lane[w.cur];
 	swapcontext(&l.ctx, &w.sched);
+}
+// interleaving stress: called around every atomic; a warp's thread gives up the core (or sleeps a little) at random so that
+// lock hand-overs, work stealing and table updates of different warps meet in many orders
+inline void jitter()
+{
+	if (!g_jitter) return;
+	static thread_local uint32_t r = 0;
+	if (r == 0) r = (uint32_t) (uintptr_t) &r * 2654435761u | 1u;
+	r ^= r << 13;
+	r ^= r >> 17;
+	r ^= r << 5;
+	if ((r & 7u) == 0u) sched_yield();
+	if ((r & 127u) == 1u)
+	{
+		struct timespec ts = {0, (long) (20000 + (r >> 20))};
+		nanosleep(&ts, nullptr);
+	}
 }
 inline unsigned char *dynamic_smem() { return W().cta->dyn_smem; }
 
@@ -209,9 +228,9 @@ static inline void __nanosleep(unsigned)
 	sched_yield();
 	emu::yield();
 }
-static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
-static inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
-static inline unsigned atomicXor(unsigned *p, unsigned v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { emu::jitter(); return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicOr(unsigned *p, unsigned v) { emu::jitter(); return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned atomicXor(unsigned *p, unsigned v) { emu::jitter(); return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicMin(unsigned *p, unsigned v)
 {
 	unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
@@ -221,7 +240,9 @@ static inline unsigned atomicMin(unsigned *p, unsigned v)
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
 {
 	unsigned e = cmp;
+	emu::jitter();
 	__atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+	emu::jitter();
 	return e;
 }
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t) p; }

@@ -186,7 +186,9 @@ def test_latency_mode_shared_memory_visited_set(emu_proto, oracle_mod, n, ef):
         assert int(want["counters"][:, 0].max()) > 512, "case too small to cross the half-full migration"
 
 
-def test_fuzz_traversal_emulated(emu, emu_proto, oracle_mod):
+@pytest.mark.parametrize("jitter", ["0", "1"], ids=["", "jitter"])
+def test_fuzz_traversal_emulated(emu, emu_proto, oracle_mod, jitter, monkeypatch):
+    monkeypatch.setenv("PGEMB_EMU_JITTER", jitter)   # 1: warps pause at random around atomics (ring-pool hand-overs, work stealing meet in many orders)
     """300 seeded random configurations (metric, dims, m, ef, graph size, ties/duplicates, deleted labels, kernel mode,
     slots/rings/CTAs, visited-table size): labels, counts and traversal counters must equal the oracle's every time."""
     for seed in range(300):
