@@ -409,16 +409,17 @@ struct Server
 		double idle_since = now_s();
 		while (!g_stop)
 		{
-			if (serve_once() > 0)
-			{
-				idle_since = now_s();
-				continue;
-			}
+			const size_t served = serve_once();
 			const double t = now_s();
 			if (t - last_reclaim > 1.0)
 			{
-				reclaim();
+				reclaim();	// also under constant load: a dead client must not keep the bulk area or a slot for ever
 				last_reclaim = t;
+			}
+			if (served > 0)
+			{
+				idle_since = t;
+				continue;
 			}
 			if (t - idle_since < 200e-6) continue;	// stay hot for a moment: the next query of a scan follows at once
 			// sleep until a client bumps submit_seq (it wakes us only when it sees server_sleeping)

@@ -247,6 +247,33 @@ def test_client_does_not_hang_when_the_sidecar_dies(emulated_lib, oracle_mod):
     assert srv2.stop() == 0
 
 
+def test_resources_of_a_dead_backend_are_reclaimed(served, oracle_mod):
+    """A backend that dies while it owns the bulk area and a claimed request slot must not block the others for ever."""
+    import struct
+    name = idx_shm(served)
+    code = (
+        "import mmap, os, struct, sys\n"
+        "f = open('/dev/shm' + sys.argv[1], 'r+b'); m = mmap.mmap(f.fileno(), 0)\n"
+        "slots_off = struct.unpack_from('<Q', m, 24)[0]\n"
+        "struct.pack_into('<I', m, 64, os.getpid())            # PgembIpcHeader.bulk_lock\n"
+        "struct.pack_into('<IIii', m, slots_off, 1, 0, 0, os.getpid())   # slot 0: CLAIMED, owner = me\n"
+        "m.flush()\n")
+    subprocess.run([sys.executable, "-c", code, name], check=True)
+    hdr = open("/dev/shm" + name, "rb").read(72)
+    assert struct.unpack_from("<I", hdr, 64)[0] != 0                      # the dead process still owns the bulk area
+    rng = np.random.default_rng(4)
+    x, orc = _graph(oracle_mod, rng, 40, 8, 3, 8, "l2")
+    idx = served.RemoteIndex(9, 8, 3, 8, 16, "l2", capacity=40)
+    t0 = time.time()
+    idx.append_records(orc.records())                                     # needs the bulk area: waits for the sidecar's reclaim pass
+    assert time.time() - t0 < 20.0
+    assert idx.search(x[0]).tolist() == orc.search(x[0], 16).tolist()
+    time.sleep(1.2)
+    raw = open("/dev/shm" + name, "rb").read()
+    slots_off = struct.unpack_from("<Q", raw, 24)[0]
+    assert struct.unpack_from("<I", raw, slots_off)[0] == 0 and struct.unpack_from("<I", raw, 64)[0] == 0   # slot FREE again, bulk area free
+
+
 def test_sidecar_refuses_to_start_without_a_device(tmp_path):
     """No CPU fallback anywhere: with the product library and no CUDA device the sidecar exits instead of serving."""
     import subprocess
