@@ -20,6 +20,11 @@
 #include "common.cuh"
 #ifdef PGEMB_PROTO
 #include "scan_tile_kernel.cuh"
+#include "scan_tc_kernel.cuh"
+#include <cublas_v2.h>	// types only: libcublas is dlopen()ed when PGEMB_SCAN_TC is used (no link-time dependency)
+#ifndef PGEMB_HOST_EMULATION
+#include <dlfcn.h>
+#endif
 #endif
 #include "search_kernel.cuh"
 
@@ -130,6 +135,9 @@ struct pgemb_index
 	size_t stage_bytes = 0;
 	// bind workspace
 	BindWorkspace bind_ws;
+#ifdef PGEMB_PROTO
+	cublasHandle_t cublas = nullptr;  // PGEMB_SCAN_TC: created on first use
+#endif
 };
 
 static pgemb_status set_device(const pgemb_index *idx)
@@ -137,6 +145,58 @@ static pgemb_status set_device(const pgemb_index *idx)
 	CU_TRY(cudaSetDevice(idx->device));
 	return PGEMB_OK;
 }
+
+#ifdef PGEMB_PROTO
+// ---- PGEMB_SCAN_TC: libcublas, loaded on first use (scan_tc_kernel.cuh) -------------------------------------------------
+static std::atomic<uint64_t> g_tc_scans{0}, g_tc_fallbacks{0}, g_tc_rescored{0}, g_tc_pairs{0};
+extern "C" void pgemb_proto_counters(uint64_t out[4])
+{
+	out[0] = g_tc_scans.load();
+	out[1] = g_tc_fallbacks.load();
+	out[2] = g_tc_rescored.load();
+	out[3] = g_tc_pairs.load();
+}
+struct CublasApi
+{
+	cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
+	cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
+	cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
+	cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *, const void *, cudaDataType, int,
+							  const void *, cudaDataType, int, const void *, void *, cudaDataType, int, cublasComputeType_t, cublasGemmAlgo_t) = nullptr;
+	bool ok = false;
+};
+static CublasApi &cublas_api()
+{
+	static CublasApi api;
+	static bool		 tried = false;
+	if (tried) return api;
+	tried = true;
+#ifdef PGEMB_HOST_EMULATION
+	api.create = cublasCreate_v2;
+	api.destroy = cublasDestroy_v2;
+	api.set_stream = cublasSetStream_v2;
+	api.gemm_ex = cublasGemmEx;
+	api.ok = true;
+#else
+	const char *cands[] = {getenv("PGEMB_CUBLAS_PATH"), "libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
+	void	   *h = nullptr;
+	for (const char *c : cands)
+		if (c && *c && (h = dlopen(c, RTLD_NOW | RTLD_LOCAL))) break;
+	if (!h) return api;
+	api.create = (decltype(api.create)) dlsym(h, "cublasCreate_v2");
+	api.destroy = (decltype(api.destroy)) dlsym(h, "cublasDestroy_v2");
+	api.set_stream = (decltype(api.set_stream)) dlsym(h, "cublasSetStream_v2");
+	api.gemm_ex = (decltype(api.gemm_ex)) dlsym(h, "cublasGemmEx");
+	api.ok = api.create && api.destroy && api.set_stream && api.gemm_ex;
+#endif
+	return api;
+}
+static void scan_tc_release(pgemb_index *idx)
+{
+	if (idx->cublas && cublas_api().ok) cublas_api().destroy(idx->cublas);
+	idx->cublas = nullptr;
+}
+#endif
 
 extern "C" pgemb_status pgemb_index_create(const HnswMetadata *meta, size_t capacity, int device, pgemb_index **out)
 {
@@ -208,6 +268,9 @@ extern "C" void pgemb_index_destroy(pgemb_index *idx)
 	cudaFree(idx->d_error);
 	cudaFree(idx->d_stage);
 	bind_ws_free(idx->bind_ws);
+#ifdef PGEMB_PROTO
+	scan_tc_release(idx);
+#endif
 	if (idx->stream) cudaStreamDestroy(idx->stream);
 	if (idx->s_in) cudaStreamDestroy(idx->s_in);
 	if (idx->h_avail) cudaFreeHost(idx->h_avail);
@@ -881,9 +944,31 @@ extern "C" pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coo
 	return PGEMB_OK;
 }
 
+static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
+								   int32_t *n_out, bool allow_tc, bool *tc_violation);
+
 extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
 										int32_t *n_out)
 {
+	bool		 viol = false;
+	pgemb_status st = scan_topk_impl(idx, nq, queries, k, labels_out, dists_out, n_out, true, &viol);
+#ifdef PGEMB_PROTO
+	if (st == PGEMB_OK && viol)
+	{
+		// the tensor-core filter saw an approximation outside its assumed error bound: its result is not trusted
+		g_tc_fallbacks++;
+		fprintf(stderr, "pgemb_scan_topk: PGEMB_SCAN_TC error bound exceeded, repeating the scan on the exact path\n");
+		st = scan_topk_impl(idx, nq, queries, k, labels_out, dists_out, n_out, false, &viol);
+	}
+#endif
+	return st;
+}
+
+static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
+								   int32_t *n_out, bool allow_tc, bool *tc_violation)
+{
+	(void) allow_tc;
+	*tc_violation = false;
 	if (!idx || ((!queries || !labels_out || !n_out) && nq)) return fail(PGEMB_ERR_ARG, "null argument");
 	if (nq == 0) return PGEMB_OK;
 	if (k < 1 || k > 4096) return fail(PGEMB_ERR_ARG, "k out of range (1..4096)");
@@ -896,7 +981,7 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	size_t		 chunk = (size_t) 1 << 14;
 	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
 	const size_t qb = nq * dim * 4, db = nq * chunk * 4, kd = nq * k * 4, kl = nq * k * 8, nb = nq * 4;
-	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + 2 * up(nb));
+	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + 2 * up(nb) + up(chunk * 4) + 256);
 	if (st) return st;
 	char	 *base = (char *) idx->d_stage;
 	float	 *d_q = (float *) base;			base += up(qb);
@@ -906,7 +991,11 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	uint64_t *d_tl = (uint64_t *) base;		base += up(kl);
 	uint64_t *d_sl = (uint64_t *) base;		base += up(kl);
 	uint32_t *d_tn = (uint32_t *) base;			base += up(nb);
-	float	 *d_qn = (float *) base;
+	float	 *d_qn = (float *) base;			base += up(nb);
+	float	 *d_vn = (float *) base;			base += up(chunk * 4);	// PGEMB_SCAN_TC, L2: squared norms of the chunk's rows
+	uint32_t *d_tcflags = (uint32_t *) base;	// [0] rows re-scored, [1] error-bound violation
+	(void) d_vn;
+	(void) d_tcflags;
 	cudaStream_t s = idx->stream;
 	CU_TRY(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, s));
 	CU_TRY(cudaMemsetAsync(d_tn, 0, nb, s));
@@ -918,7 +1007,33 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 #else
 	const bool tiled = false;
 #endif
+#ifdef PGEMB_PROTO
+	// tensor-core filter (scan_tc_kernel.cuh): one TF32 GEMM per chunk discards rows, survivors are re-scored exactly
+	const bool tc = allow_tc && env_int("PGEMB_SCAN_TC", 0) != 0 && metric != DIST_MANHATTAN;
+	float	   tc_rel = 0.f;
+	if (tc)
+	{
+		CublasApi &cb = cublas_api();
+		if (!cb.ok) return fail(PGEMB_ERR_CUDA, "PGEMB_SCAN_TC=1 but libcublas could not be loaded (PGEMB_CUBLAS_PATH)");
+		if (!idx->cublas && cb.create(&idx->cublas) != CUBLAS_STATUS_SUCCESS)
+		{
+			idx->cublas = nullptr;
+			return fail(PGEMB_ERR_CUDA, "cublasCreate failed");
+		}
+		if (cb.set_stream(idx->cublas, s) != CUBLAS_STATUS_SUCCESS) return fail(PGEMB_ERR_CUDA, "cublasSetStream failed");
+		// TF32: both operands cut to 10 mantissa bits (2 * 2^-10 relative per product), fp32 accumulation over dim terms
+		// (dim * 2^-23), 50 % slack; PGEMB_SCAN_TC_REL_PPM overrides (parts per million)
+		tc_rel = 1.5f * (2.0f / 1024.0f + (float) dim / 8388608.0f);
+		const int ppm = env_int("PGEMB_SCAN_TC_REL_PPM", 0);
+		if (ppm > 0) tc_rel = (float) ppm * 1e-6f;
+		CU_TRY(cudaMemsetAsync(d_tcflags, 0, 8, s));
+		g_tc_scans++;
+		g_tc_pairs += (uint64_t) nq * N;
+	}
+	if (tc || (tiled && metric == DIST_COSINE))
+#else
 	if (tiled && metric == DIST_COSINE)
+#endif
 	{
 		PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nq * 4 + 127) / 128), 128, 0, s, d_q, (uint32_t) dim, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
 		g_launches++;
@@ -936,6 +1051,31 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	PGEMB_LAUNCH(scan_tile_kernel<MM>, dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), kScanThreads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, d_qn,  \
 												 (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
 #ifdef PGEMB_PROTO
+		if (tc)
+		{
+			const float one = 1.0f, zero = 0.0f;
+			// row-major S[nq][nr] = column-major (nr x nq): S^T = V_chunk (nr x dim) . Q^T (dim x nq)
+			if (cublas_api().gemm_ex(idx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int) nr, (int) nq, (int) dim, &one, idx->d_vectors + r0 * idx->row_f, CUDA_R_32F,
+									 (int) idx->row_f, d_q, CUDA_R_32F, (int) dim, &zero, d_dist, CUDA_R_32F, (int) nr, CUBLAS_COMPUTE_32F_FAST_TF32,
+									 CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
+				return fail(PGEMB_ERR_CUDA, "cublasGemmEx failed");
+			const float *vn = idx->d_norms + r0;
+			if (metric == DIST_L2)
+			{
+				PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nr * 4 + 127) / 128), 128, 0, s, idx->d_vectors + r0 * idx->row_f, idx->row_f, (uint32_t) dim, 0u, (uint32_t) nr, d_vn);
+				g_launches++;
+				vn = d_vn;
+			}
+#define SCAN_TC(MM)                                                                                                                \
+	PGEMB_LAUNCH(scan_select_tc_kernel<MM>, (uint32_t) ((nq + 3) / 4), 128, 0, s, d_dist, idx->d_vectors, idx->row_f, (uint32_t) dim, vn, d_q, (uint32_t) dim, d_qn, \
+				 idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k, tc_rel, d_td, d_tl, d_tn, d_sd, d_sl, d_tcflags, (int *) (d_tcflags + 1))
+			if (metric == DIST_L2) SCAN_TC(M_L2);
+			else SCAN_TC(M_COS);
+#undef SCAN_TC
+			g_launches += 2;  // the GEMM (library kernel) + the filter/select kernel
+			CU_TRY(cudaGetLastError());
+			continue;
+		}
 		if (tiled)
 		{
 			if (metric == DIST_L2) SCAN_TILE(M_L2);
@@ -968,7 +1108,18 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 	CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
+#ifdef PGEMB_PROTO
+	uint32_t tcf[2] = {0, 0};
+	if (tc) CU_TRY(cudaMemcpyAsync(tcf, d_tcflags, 8, cudaMemcpyDeviceToHost, s));
+#endif
 	CU_TRY(cudaStreamSynchronize(s));
+#ifdef PGEMB_PROTO
+	if (tc)
+	{
+		g_tc_rescored += tcf[0];
+		if (tcf[1]) *tc_violation = true;
+	}
+#endif
 	for (size_t q = 0; q < nq; q++)
 	{
 		n_out[q] = (int32_t) hn[q];

@@ -232,6 +232,64 @@ def test_prototype_tiled_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
         idx.close()
 
 
+def _proto_counters(pg):
+    from pg_embedding_b200 import _lib
+    out = (C.c_uint64 * 4)()
+    _lib.load().pgemb_proto_counters(out)
+    return dict(scans=out[0], fallbacks=out[1], rescored=out[2], pairs=out[3])
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_prototype_tensor_core_filter_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
+    """PGEMB_SCAN_TC=1: a reduced-precision GEMM only DISCARDS rows, survivors are re-scored exactly -> the exact scan's
+    labels, order and bits.  The stand-in GEMM perturbs every dot product by +-90 % of the error bound the filter assumes
+    (adversarial but legal); with an error of 3x the bound the tripwire must fire and the exact path must take over."""
+    pg = pg_proto
+    rng = np.random.default_rng(17)
+    cases = []
+    for dims, n, k in ((33, 900, 20), (100, 400, 5), (16, 300, 64)):
+        c = rng.standard_normal((12, dims)).astype(np.float32)
+        x = (c[rng.integers(0, 12, n)] + 0.15 * rng.standard_normal((n, dims))).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        x[n // 2] = x[n // 3]                                  # an exact tie: ordered by label
+        q = (c[rng.integers(0, 12, 9)] + 0.15 * rng.standard_normal((9, dims))).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        labels = rng.permutation(n).astype(np.uint64) + np.uint64(9)
+        labels[::7] |= np.uint64(1 << 48)                      # deleted rows are skipped
+        cases.append((dims, n, k, x, q, labels))
+    bound_ppm = lambda dims: 1.5 * (2.0 / 1024.0 + dims / 8388608.0) * 1e6
+    for dims, n, k, x, q, labels in cases:
+        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
+        idx.append(x, labels)
+        monkeypatch.setenv("PGEMB_SCAN_TC", "0")
+        want = idx.scan_topk(q, k)
+        for i in range(q.shape[0]):                              # the exact path itself against the oracle's distances
+            d = oracle_mod.dist_many("port", metric, q[i], x)
+            order = sorted((float(d[j]), int(labels[j])) for j in range(n) if not (int(labels[j]) >> 48) & 1)[:k]
+            assert want["labels"][i, :len(order)].tolist() == [o[1] for o in order]
+        c0 = _proto_counters(pg)
+        monkeypatch.setenv("PGEMB_SCAN_TC", "1")
+        for err_frac in (0.0, 0.9):
+            monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", str(err_frac * bound_ppm(dims) / 1.5))   # fraction of the un-slacked bound
+            got = idx.scan_topk(q, k)
+            assert got["labels"].tobytes() == want["labels"].tobytes(), (metric, dims, err_frac)
+            assert got["dists"].tobytes() == want["dists"].tobytes() and got["n"].tolist() == want["n"].tolist()
+        c1 = _proto_counters(pg)
+        assert c1["scans"] - c0["scans"] == 2 and c1["fallbacks"] == c0["fallbacks"]
+        frac = (c1["rescored"] - c0["rescored"]) / (c1["pairs"] - c0["pairs"])
+        print(f"tc filter {metric} dims={dims} n={n} k={k}: {frac:.3f} of the pairs re-scored exactly")
+        if k * 20 <= n:
+            assert frac < 0.5, "the filter discarded almost nothing"
+        # a GEMM that is worse than assumed: detected, exact path takes over, results still right
+        monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", str(4.0 * bound_ppm(dims)))
+        got = idx.scan_topk(q, k)
+        assert got["labels"].tobytes() == want["labels"].tobytes()
+        assert _proto_counters(pg)["fallbacks"] == c1["fallbacks"] + 1
+        monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", "0")
+        idx.close()
+    # manhattan has no bilinear form: the flag is ignored
+    if metric == "l2":
+        G.test_scan_topk_regress_seqscan(pg)
+
+
 def test_prototype_l2_eight_lanes(pg_proto, G, oracle_mod, monkeypatch):
     pg = pg_proto
     monkeypatch.setenv("PGEMB_L2_TPR8", "1")

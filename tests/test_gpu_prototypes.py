@@ -77,3 +77,43 @@ def test_scan_topk_tiled(pg, oracle_mod, metric, monkeypatch):
     monkeypatch.setenv("PGEMB_SCAN_TILED", "1")
     G.test_scan_topk_matches_exact_order(pg, oracle_mod, metric)
     G.test_scan_topk_regress_seqscan(pg)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_scan_topk_tensor_core_filter(pg, oracle_mod, metric, monkeypatch):
+    """PGEMB_SCAN_TC=1: one TF32 GEMM per chunk (cuBLAS, tensor cores) discards rows, survivors are re-scored with the
+    reference-exact arithmetic -> the exact scan's labels, order and bits; the error-bound tripwire must stay silent."""
+    import ctypes as C
+    from pg_embedding_b200 import _lib
+
+    def counters():
+        out = (C.c_uint64 * 4)()
+        _lib.load().pgemb_proto_counters(out)
+        return dict(scans=out[0], fallbacks=out[1], rescored=out[2], pairs=out[3])
+
+    rng = np.random.default_rng(23)
+    for dims, n, k, nq in ((33, 3000, 64, 40), (128, 30000, 10, 70), (768, 40000, 10, 130)):
+        x = _data(rng, n, dims)
+        q = _data(rng, nq, dims)
+        if metric == "cosine":
+            x, q = x + 0.5, q + 0.5
+        x[n // 2] = x[n // 3]
+        labels = rng.permutation(n).astype(np.uint64) + np.uint64(3)
+        labels[::11] |= np.uint64(1 << 48)
+        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
+        idx.append(x, labels)
+        monkeypatch.setenv("PGEMB_SCAN_TC", "0")
+        want = idx.scan_topk(q, k)
+        c0 = counters()
+        monkeypatch.setenv("PGEMB_SCAN_TC", "1")
+        got = idx.scan_topk(q, k)
+        c1 = counters()
+        assert got["labels"].tobytes() == want["labels"].tobytes(), (metric, dims)
+        assert got["dists"].tobytes() == want["dists"].tobytes() and got["n"].tolist() == want["n"].tolist()
+        assert c1["scans"] == c0["scans"] + 1 and c1["fallbacks"] == c0["fallbacks"], "the TF32 error bound was exceeded"
+        frac = (c1["rescored"] - c0["rescored"]) / (c1["pairs"] - c0["pairs"])
+        print(f"tc filter {metric} dims={dims} n={n} k={k}: {frac:.4f} of the pairs re-scored exactly")
+        if n >= 30000:
+            assert frac < 0.2
+        idx.close()
+

@@ -33,5 +33,8 @@ PGEMB_LIB_VARIANT=proto PGEMB_L2_TPR8=1 timeout 600 python tools/bench_shapes.py
 say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
+say "exact scan through the tensor-core filter (PGEMB_SCAN_TC=1), 64 and 1024 queries x 1M rows"
+PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TC=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TC=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 1024 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 say "sidecar: one-query-per-call hnsw_search from 1..128 backend processes (tools/bench_sidecar.py)"
 timeout 900 python tools/bench_sidecar.py --backends 1,16,64,128 --seconds 4 2> gpurun_out/r2_sidecar.err | tee -a $L
