@@ -1511,6 +1511,12 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 		// Speculative searches are nearly free (one launch, one warp each, latency-bound), so the batch only
 		// shrinks while the graph is tiny (every search expands most of it and everything conflicts).
 		B = (acc == B) ? B * 2 : (acc * 8 > batch_max ? batch_max : acc * 8 + 1);
+#ifdef PGEMB_PROTO
+		// opt-in prototype: a batch that would only slightly exceed one query per SM is cut to one query per SM, so that the
+		// speculative searches run in latency mode (a CTA per search: shorter round) -- the accepted prefix is far shorter than
+		// the batch anyway.  Same result by construction (any batch size gives the sequential graph).
+		if (env_int("PGEMB_EXACT_CLAMP_SMS", 0) != 0 && B > (size_t) idx->sm_count && B <= 3 * (size_t) idx->sm_count) B = (size_t) idx->sm_count;
+#endif
 	}
 	CU_TRY(cudaEventRecord(e1, s));
 	st = check_device_error(idx, s);

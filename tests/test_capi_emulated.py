@@ -232,6 +232,21 @@ def test_prototype_tiled_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
         idx.close()
 
 
+def test_prototype_exact_build_batch_clamp(pg_proto, oracle_mod, monkeypatch):
+    """PGEMB_EXACT_CLAMP_SMS=1 only changes batch sizes of the exact parallel build: still the sequential graph."""
+    monkeypatch.setenv("PGEMB_EXACT_CLAMP_SMS", "1")
+    rng = np.random.default_rng(6)
+    n, dims, m, efc = 260, 6, 3, 10
+    x = rng.integers(0, 3, (n, dims)).astype(np.float32)          # ties and duplicates
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 16, "l2", capacity=n)
+    orc.build(x)
+    idx = pg_proto.HnswIndex(dims, m, efc, 16, "l2", capacity=n)
+    idx.append(x)
+    idx.build_exact(0, n, 64)
+    assert idx.links().tobytes() == orc.links().tobytes()
+    idx.close()
+
+
 def _proto_counters(pg):
     from pg_embedding_b200 import _lib
     out = (C.c_uint64 * 4)()

@@ -38,3 +38,6 @@ PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TC=1 timeout 600 python tools/bench_shapes.py
 PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TC=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 1024 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 say "sidecar: one-query-per-call hnsw_search from 1..128 backend processes (tools/bench_sidecar.py)"
 timeout 900 python tools/bench_sidecar.py --backends 1,16,64,128 --seconds 4 2> gpurun_out/r2_sidecar.err | tee -a $L
+say "exact parallel build, steady state at N~1M (20K exact inserts after a bulk-built prefix): default vs batch clamp"
+PGEMB_LIB_VARIANT=proto timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_EXACT_CLAMP_SMS=1 timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
