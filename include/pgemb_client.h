@@ -40,6 +40,12 @@ const char *pgemb_client_last_error(void);
 /* Name of the segment this process is (or was last) connected to; "" if never connected. */
 const char *pgemb_client_segment_name(void);
 
+/* Cancellation: `fn` (e.g. a function returning Postgres' InterruptPending) is polled about every 50 ms while a request is
+ * pending; when it returns non-zero the call gives up with PGEMB_CLIENT_INTERRUPTED (the reference-shaped calls return
+ * false) and the glue runs CHECK_FOR_INTERRUPTS().  The request itself is completed and dropped by the sidecar. */
+#define PGEMB_CLIENT_INTERRUPTED 100
+void pgemb_client_set_interrupt_check(int (*fn)(void));
+
 /* Create-or-look-up the device mirror of relation h->rel_key with the options in h->meta (capacity is used on creation).
  * Fails if an existing mirror has other dims / maxM / distance function (the reference's check at embedding.c:594-602).
  * size_out / capacity_out (optional): nodes stored / capacity of the mirror. */

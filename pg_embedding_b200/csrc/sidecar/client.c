@@ -27,11 +27,14 @@
 #include "../../../include/pgemb_client.h"
 #include "ipc.h"
 
+#define PGEMB_INTERRUPTED_COMPLETED 101 /* internal: interrupted, but the request had completed (slot already freed by us) */
+
 static PgembIpcHeader *g_hdr = NULL;
 static unsigned char  *g_base = NULL;
 static size_t		   g_bytes = 0;
 static char			   g_name[256]; /* the segment we connected to last: a restarted sidecar re-creates it under the same name */
 static __thread char   g_err[256];
+static int (*g_interrupt)(void) = NULL; /* e.g. a function returning InterruptPending: polled while a request is pending */
 
 static void set_err(const char *fmt, ...)
 {
@@ -43,6 +46,7 @@ static void set_err(const char *fmt, ...)
 
 const char *pgemb_client_last_error(void) { return g_err; }
 const char *pgemb_client_segment_name(void) { return g_name; }
+void		pgemb_client_set_interrupt_check(int (*fn)(void)) { g_interrupt = fn; }
 
 static inline uint32_t ld(const uint32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void	   st(uint32_t *p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
@@ -152,6 +156,7 @@ static PgembIpcSlot *claim_slot(void)
 				s->a0 = s->a1 = s->a2 = s->a3 = 0;
 				s->ef = 0;
 				s->err[0] = 0;
+				st(&s->abandoned, 0);
 				return s;
 			}
 		}
@@ -182,8 +187,21 @@ static int submit_wait(PgembIpcSlot *s)
 			__builtin_ia32_pause();
 			continue;
 		}
-		struct timespec ts = {0, 200 * 1000 * 1000};
+		struct timespec ts = {0, 50 * 1000 * 1000};
 		futex(&s->state, FUTEX_WAIT, v, &ts);
+		if (g_interrupt && ld(&s->state) != PGEMB_SLOT_DONE && g_interrupt())
+		{
+			/* the caller wants out (query cancel): leave the request to the sidecar, never touch the slot again except to free
+			 * it if the result arrived in the meantime */
+			st(&s->abandoned, 1);
+			__atomic_thread_fence(__ATOMIC_SEQ_CST);
+			uint32_t  expect = PGEMB_SLOT_DONE;
+			const int freed_here = __atomic_compare_exchange_n(&s->state, &expect, (uint32_t) PGEMB_SLOT_FREE, 0, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED);
+			set_err("interrupted while waiting for the sidecar");
+			/* freed_here: the request had just completed and we dropped its result; otherwise the sidecar completes it,
+			 * frees the slot and (for a bulk request) the bulk area */
+			return freed_here ? PGEMB_INTERRUPTED_COMPLETED : PGEMB_CLIENT_INTERRUPTED;
+		}
 		if (ld(&s->state) != PGEMB_SLOT_DONE && !server_alive())
 		{
 			set_err("the sidecar went away while a request was pending");
@@ -195,7 +213,12 @@ static int submit_wait(PgembIpcSlot *s)
 	return s->status;
 }
 
-static void release_slot(PgembIpcSlot *s) { st(&s->state, PGEMB_SLOT_FREE); }
+static int	interrupted(int rc) { return rc == PGEMB_CLIENT_INTERRUPTED || rc == PGEMB_INTERRUPTED_COMPLETED; }
+/* give a slot back after submit_wait() -- unless the request was abandoned: then the slot is not ours any more */
+static void release_slot(PgembIpcSlot *s, int rc)
+{
+	if (!interrupted(rc) && ld(&s->state) == PGEMB_SLOT_DONE) st(&s->state, PGEMB_SLOT_FREE);
+}
 
 /* the bulk area is one request's at a time */
 static int bulk_acquire(void)
@@ -233,16 +256,17 @@ static int do_request(PgembClientIndex *h, uint32_t op, uint64_t a0, uint64_t a1
 	if (r0) *r0 = s->a0;
 	if (r1) *r1 = s->a1;
 	if (r2) *r2 = s->a2;
-	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	release_slot(s, rc);
 	return rc;
 }
 
 static int simple_request(PgembClientIndex *h, uint32_t op, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t *r0, uint64_t *r1,
 						  uint64_t *r2)
 {
-	const int rc = ensure_connected();
+	int rc = ensure_connected();
 	if (rc) return rc;
-	return do_request(h, op, a0, a1, a2, a3, r0, r1, r2);
+	rc = do_request(h, op, a0, a1, a2, a3, r0, r1, r2);
+	return interrupted(rc) ? PGEMB_CLIENT_INTERRUPTED : rc;
 }
 
 /* ---- mirror maintenance ------------------------------------------------------------------------------------------ */
@@ -267,8 +291,8 @@ int pgemb_client_attach(PgembClientIndex *h, size_t capacity, size_t *size_out, 
 		if (size_out) *size_out = (size_t) s->a1;
 		if (capacity_out) *capacity_out = (size_t) s->a2;
 	}
-	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
-	return rc;
+	release_slot(s, rc);
+	return interrupted(rc) ? PGEMB_CLIENT_INTERRUPTED : rc;
 }
 
 /* move `n` items of `item_bytes` through the bulk area in chunks; to_server: copy in before each request, else copy out after */
@@ -301,8 +325,9 @@ static int bulk_transfer(PgembClientIndex *h, uint32_t op, size_t first, size_t 
 			rc = do_request(h, op, first + done, k, stride_arg, 0, NULL, NULL, NULL);
 		if (rc == PGEMB_OK && !to_server) memcpy((unsigned char *) data + done * item_bytes, bulk, k * item_bytes);
 	}
-	bulk_release();
-	return rc;
+	/* an abandoned request still uses the bulk area: the sidecar lets go of it when that request is done */
+	if (rc != PGEMB_CLIENT_INTERRUPTED) bulk_release();
+	return interrupted(rc) ? PGEMB_CLIENT_INTERRUPTED : rc;
 }
 
 int pgemb_client_append_records(PgembClientIndex *h, size_t n, const void *records, size_t record_stride)
@@ -398,7 +423,7 @@ bool hnsw_search(HnswMetadata *meta, const coord_t *point, size_t *n_results, la
 		*results = buf;
 		ok = true;
 	}
-	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	release_slot(s, rc);
 	if (!ok) free(buf);
 	return ok;
 }
@@ -435,7 +460,7 @@ dist_t hnsw_dist_func(dist_func_t dist, coord_t const *ax, coord_t const *bx, si
 		const uint32_t bits = (uint32_t) s->a2;
 		memcpy(&out, &bits, 4);
 	}
-	if (ld(&s->state) == PGEMB_SLOT_DONE) release_slot(s);
+	release_slot(s, rc);
 	return out;
 }
 

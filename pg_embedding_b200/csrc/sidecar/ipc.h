@@ -13,7 +13,8 @@
  *     IpcHeader | IpcSlot[n_slots] (each followed by its payload) | bulk area
  * A request is a slot: a client claims a FREE slot (CAS), fills it, publishes READY and bumps header.submit_seq (a
  * futex the server sleeps on when idle); the server sets BUSY, runs it, writes the result into the same slot, publishes
- * DONE and wakes the futex on slot.state; the client copies the result out and returns the slot to FREE.  Bulk data
+ * DONE and wakes the futex on slot.state; the client copies the result out and returns the slot to FREE.  A client that has to stop waiting (query cancel) marks
+ * the slot `abandoned`; the slot is then freed by whichever side sees DONE last, and its result is dropped.  Bulk data
  * (page records, link lists) travels through the bulk area, which a client holds exclusively (header.bulk_lock) for the
  * duration of one request.
  *
@@ -85,7 +86,8 @@ typedef struct
 	uint64_t a0, a1, a2, a3;
 	uint32_t ef;
 	int32_t	 n_out;
-	char	 err[168];
+	uint32_t abandoned; /* set by a client that stopped waiting (query cancel): whoever sees DONE afterwards frees the slot */
+	char	 err[164];
 	/* payload follows: float vec[2 * max_dim]; uint64_t labels[max_ef]  (8-byte aligned) */
 } PgembIpcSlot;
 

@@ -137,6 +137,21 @@ struct Server
 			s->err[0] = 0;
 		__atomic_fetch_add(&hdr->n_requests, 1, __ATOMIC_RELAXED);
 		st(&s->state, PGEMB_SLOT_DONE);
+		__atomic_thread_fence(__ATOMIC_SEQ_CST);
+		if (ld(&s->abandoned))
+		{
+			// the client stopped waiting (cancelled query): nobody will read the result
+			const uint32_t op = s->op, owner = (uint32_t) s->owner_pid;
+			uint32_t	   expect = PGEMB_SLOT_DONE;
+			if (__atomic_compare_exchange_n(&s->state, &expect, (uint32_t) PGEMB_SLOT_FREE, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED))
+			{
+				// we freed the slot (not the client): a bulk request's hold on the bulk area ends with it
+				const bool bulk_op = op == PGEMB_OP_APPEND_RECORDS || op == PGEMB_OP_GET_LINKS || op == PGEMB_OP_EXPORT_RECORDS || op == PGEMB_OP_SET_LABELS;
+				uint32_t   o = owner;
+				if (bulk_op) __atomic_compare_exchange_n(&hdr->bulk_lock, &o, 0u, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED);
+			}
+			return;
+		}
 		futex(&s->state, FUTEX_WAKE, 1, nullptr);
 	}
 	void finish_api(PgembIpcSlot *s, pgemb_status status) { finish(s, status, status == PGEMB_OK ? nullptr : api.last_error()); }

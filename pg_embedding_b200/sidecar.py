@@ -56,6 +56,7 @@ def client() -> C.CDLL:
     lib.pgemb_client_drop.argtypes = [hp]
     lib.pgemb_client_build.argtypes = [hp, sz, sz, sz, C.c_int, C.POINTER(C.c_double)]
     lib.pgemb_client_stats.argtypes = [C.POINTER(C.c_uint64)] * 3
+    lib.pgemb_client_set_interrupt_check.argtypes = [C.c_void_p]
     lib.hnsw_search.argtypes = [C.POINTER(HnswMetadata), C.POINTER(C.c_float), C.POINTER(sz), C.POINTER(C.POINTER(C.c_uint64))]
     lib.hnsw_search.restype = C.c_bool
     lib.hnsw_bind_point.argtypes = [C.POINTER(HnswMetadata), C.POINTER(C.c_float), C.c_uint32]

@@ -274,6 +274,46 @@ def test_resources_of_a_dead_backend_are_reclaimed(served, oracle_mod):
     assert struct.unpack_from("<I", raw, slots_off)[0] == 0 and struct.unpack_from("<I", raw, 64)[0] == 0   # slot FREE again, bulk area free
 
 
+def test_cancelled_call_returns_and_the_sidecar_cleans_up(served, oracle_mod):
+    """Query cancel: the glue's interrupt check makes a pending call give up (embedding.c then runs CHECK_FOR_INTERRUPTS);
+    the sidecar finishes the abandoned request, frees its slot and -- for a bulk request -- the bulk area."""
+    import ctypes as C
+    rng = np.random.default_rng(12)
+    n, dims, m, efc = 700, 8, 3, 10
+    x, orc = _graph(oracle_mod, rng, 50, dims, m, efc, "l2")
+    idx = served.RemoteIndex(31, dims, m, efc, 16, "l2", capacity=n)
+    rs = idx.record_bytes
+    big = rng.standard_normal((n, dims)).astype(np.float32)
+    rec = np.zeros((n, rs), np.uint8)
+    rec[:, (2 * m + 1) * 4:(2 * m + 1) * 4 + dims * 4] = big.view(np.uint8)
+    rec[:, rs - 8:] = np.arange(n, dtype=np.uint64).view(np.uint8).reshape(n, 8)
+    idx.append_records(rec)
+    pending = C.c_int(0)
+    CB = C.CFUNCTYPE(C.c_int)
+    cb = CB(lambda: pending.value)
+    served.client().pgemb_client_set_interrupt_check(C.cast(cb, C.c_void_p))
+    try:
+        pending.value = 1
+        t0 = time.time()
+        with pytest.raises(served.SidecarError, match="interrupted"):
+            idx.build(0, n, batch_max=32, exact=True)            # seconds of work on the emulated library
+        assert time.time() - t0 < 2.0
+        pending.value = 0
+        # the next call queues behind the abandoned build and then works; the index is fully bound by then
+        assert len(idx) == n
+        lk = idx.links()
+        assert (lk[1:, 0] > 0).all()
+        q = big[5]
+        assert idx.search(q, 8).size == 8
+    finally:
+        served.client().pgemb_client_set_interrupt_check(None)
+    raw = open("/dev/shm" + idx_shm(served), "rb").read()
+    import struct
+    slots_off, stride, nslots = struct.unpack_from("<Q", raw, 24)[0], struct.unpack_from("<I", raw, 20)[0], struct.unpack_from("<I", raw, 8)[0]
+    assert all(struct.unpack_from("<I", raw, slots_off + i * stride)[0] == 0 for i in range(nslots)), "a slot was leaked"
+    assert struct.unpack_from("<I", raw, 64)[0] == 0
+
+
 def test_sidecar_refuses_to_start_without_a_device(tmp_path):
     """No CPU fallback anywhere: with the product library and no CUDA device the sidecar exits instead of serving."""
     import subprocess
