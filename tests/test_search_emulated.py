@@ -131,6 +131,23 @@ def test_search_kernel_emulated_matches_oracle(emu, emu_proto, oracle_mod, case,
         assert got["dists"][qi, :k].tobytes() == dref.tobytes()
 
 
+@pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
+def test_search_kernel_emulated_very_large_ef(emu, oracle_mod, coop):
+    """efSearch in the thousands (the scan doubles it for large LIMITs, embedding.c:334): queues far larger than the graph."""
+    rng = np.random.default_rng(77)
+    n, dims, m = 500, 12, 6
+    x = rng.standard_normal((n, dims)).astype(np.float32)
+    q = rng.standard_normal((3, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, 24, 64, "l2", capacity=n)
+    orc.build(x)
+    for ef in (300, 6000):
+        want = orc.search_many(q, ef, want_counters=True)
+        got = run_emu(emu, "l2", coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=2, rings=2, grid=2, vh=64)
+        assert got["n"].tolist() == want["n"].tolist()
+        assert got["labels"].tobytes() == want["labels"].tobytes()
+        assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+
+
 BIND_CASES = [
     # metric, dims, m, efC, n, levels
     ("l2", 3, 3, 8, 70, 3),          # ties + duplicates: equal-distance scan order of the heuristic, full lists re-pruned
