@@ -247,6 +247,32 @@ def test_prototype_exact_build_batch_clamp(pg_proto, oracle_mod, monkeypatch):
     idx.close()
 
 
+def test_prototype_fast_small_batches(pg_proto, G, oracle_mod, monkeypatch):
+    """PGEMB_FAST_SMALL=1: <= 64 queries go copy -> launch -> copy back on one stream (no streaming protocol), repeated
+    launches skip the attribute / occupancy / L2-window driver calls.  Same results as the default host path."""
+    monkeypatch.setenv("PGEMB_FAST_SMALL", "1")
+    pg = pg_proto
+    for case in G.GOLD:
+        G.test_kat_regress(pg, case)
+    G.test_search_empty_and_tiny(pg, oracle_mod)
+    rng = np.random.default_rng(21)
+    n, dims, m, efc = 500, 20, 5, 24
+    x = rng.standard_normal((n, dims)).astype(np.float32) + 1.0
+    q = rng.standard_normal((70, dims)).astype(np.float32) + 1.0
+    for metric in ("cosine", "l2"):
+        orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x)
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+        idx.append(x, orc.labels(), orc.links())
+        for nq, ef in ((1, 10), (1, 10), (64, 16), (70, 16), (3, 40), (1, 10)):     # 70 > 64: the streamed path in between
+            out = idx.search_batch(q[:nq], ef, want_stats=True)
+            want = orc.search_many(q[:nq], ef, want_counters=True)
+            assert out["labels"].tobytes() == want["labels"].tobytes() and out["n"].tolist() == want["n"].tolist(), (metric, nq, ef)
+            assert out["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+        assert idx.search(q[0], 12).tolist() == orc.search(q[0], 12).tolist()         # hnsw_search
+        idx.close()
+
+
 def _proto_counters(pg):
     from pg_embedding_b200 import _lib
     out = (C.c_uint64 * 4)()
