@@ -64,7 +64,8 @@ def main():
     ap.add_argument("--backends", default="1,16,64,128")
     ap.add_argument("--seconds", type=float, default=5.0)
     ap.add_argument("--linger-us", type=int, default=0)
-    ap.add_argument("--lib", default=None, help="C-ABI library the sidecar loads (default: the product library); with it, data comes from numpy")
+    ap.add_argument("--lib", default=None, help="C-ABI library the sidecar loads (default: the product library)")
+    ap.add_argument("--numpy-data", action="store_true", help="iid numpy data instead of bench.py's generator (no torch / CUDA in this process: emulated runs)")
     # internal: backend mode
     ap.add_argument("--backend-id", type=int, default=-1)
     ap.add_argument("--shm"), ap.add_argument("--queries"), ap.add_argument("--out"), ap.add_argument("--go")
@@ -75,7 +76,7 @@ def main():
     from pg_embedding_b200 import build, sidecar
     build.build()
     X = None
-    if a.dims == 768 and not a.lib:
+    if a.dims == 768 and not a.numpy_data:
         import bench  # the BASELINE data generator (clustered mixture, seeds 1234/5678)
         import torch
         X, Q = bench.make_data(torch, a.rows, 8192)

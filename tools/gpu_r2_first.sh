@@ -44,3 +44,5 @@ timeout 900 python tools/bench_sidecar.py --backends 1,16,64,128 --seconds 4 2> 
 say "exact parallel build, steady state at N~1M (20K exact inserts after a bulk-built prefix): default vs batch clamp"
 PGEMB_LIB_VARIANT=proto timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_EXACT_CLAMP_SMS=1 timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
+say "sidecar over the prototype library: single-stream small batches + shared-memory visited set"
+PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 timeout 900 python tools/bench_sidecar.py --lib pg_embedding_b200/libpgemb_b200_proto.so --backends 1,16 --seconds 4 2>> gpurun_out/r2_sidecar.err | tee -a $L
