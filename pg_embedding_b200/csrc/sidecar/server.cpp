@@ -111,7 +111,11 @@ struct Server
 	size_t			bytes = 0;
 	int				device = 0;
 	size_t			max_batch = 4096;
-	long			linger_us = 0;
+	long			linger_us = 50;	 // upper bound of the adaptive wait for the callers that are about to resubmit (0 = never wait)
+	size_t			target = 1;		 // how many concurrent searchers the recent rounds showed (see serve_once)
+	double			last_service_s = 0.0;	// duration of the previous round's launches
+	size_t			carry = 0;				// searches that queued up while the current round's launches ran
+	bool			carry_counted = false;
 	std::unordered_map<uint64_t, Mirror> mirrors;
 	// per-batch scratch
 	std::vector<float>	  qbuf;
@@ -348,6 +352,17 @@ struct Server
 			nbuf.assign(nq, 0);
 			for (size_t i = 0; i < nq; i++) memcpy(&qbuf[i * dim], slot_vec(group[lo + i]), dim * sizeof(float));
 			const pgemb_status r = api.search_batch(m.host.dev, nq, qbuf.data(), ef, lbuf.data(), nullptr, nullptr, nbuf.data(), nullptr);
+			if (!carry_counted)
+			{
+				// who queued up while the launch ran (BEFORE any result of this round is published: a caller that gets its
+				// result resubmits at once and would be counted twice)
+				carry_counted = true;
+				for (uint32_t i = 0; i < hdr->n_slots; i++)
+				{
+					const PgembIpcSlot *c = slot(i);
+					if (ld(&c->state) == PGEMB_SLOT_READY && c->op == PGEMB_OP_SEARCH) carry++;
+				}
+			}
 			hdr->n_batches += 1;
 			hdr->n_searches += nq;
 			if (nq > hdr->max_batch) hdr->max_batch = nq;
@@ -370,7 +385,7 @@ struct Server
 	{
 		std::vector<PgembIpcSlot *> control;
 		std::map<std::pair<uint64_t, uint32_t>, std::vector<PgembIpcSlot *>> searches;
-		size_t found = 0;
+		size_t found = 0, nsearch = 0;
 		auto   collect = [&]() {
 			  for (uint32_t i = 0; i < hdr->n_slots; i++)
 			  {
@@ -379,27 +394,50 @@ struct Server
 				  st(&s->state, PGEMB_SLOT_BUSY);
 				  found++;
 				  if (s->op == PGEMB_OP_SEARCH)
+				  {
 					  searches[{s->index_key, s->ef}].push_back(s);
+					  nsearch++;
+				  }
 				  else
 					  control.push_back(s);
 			  }
 		};
 		collect();
 		if (found == 0) return 0;
-		if (linger_us > 0 && !searches.empty())
+		// Keeping the callers together.  A caller resubmits a few microseconds after it got its result, so a server that
+		// launches whatever is queued the moment it becomes free splits P steady callers into two groups that are served
+		// alternately -- each waits two launches per result.  `target` is the number of concurrent searchers the last
+		// round showed (its batch + those that were already queued when it finished, see below); when fewer are here
+		// now, the rest are about to arrive: wait for them, at most linger_us.  One caller never waits (target = 1).
+		if (linger_us > 0 && nsearch > 0 && nsearch < target)
 		{
-			// optional: give concurrent callers a moment to join the batch (off by default: while a batch runs on the GPU the
-			// next one fills up by itself)
-			const double until = now_s() + 1e-6 * (double) linger_us;
-			while (now_s() < until && found < hdr->n_slots)
-			{
-				const size_t before = found;
-				collect();
-				if (found == before) usleep(20);
-			}
+			// a caller needs its wake-up latency (it sleeps on a futex while a launch runs) plus a few microseconds to be
+			// back: wait linger_us, or a quarter of the previous round if that is longer (never more than 2 ms)
+			double wait = 1e-6 * (double) linger_us;
+			if (0.25 * last_service_s > wait) wait = 0.25 * last_service_s;
+			if (wait > 2e-3) wait = 2e-3;
+			const double until = now_s() + wait;
+			while (nsearch < target && now_s() < until) collect();
 		}
 		for (PgembIpcSlot *s : control) run_control(s);
+		const double t_run = now_s();
+		carry = 0;
+		carry_counted = false;
 		for (auto &kv : searches) run_searches(kv.second);
+		if (nsearch > 0)
+		{
+			last_service_s = now_s() - t_run;
+			if (const char *dbg = getenv("PGEMB_SIDECAR_DEBUG"))
+			{
+				FILE *f = fopen(dbg, "a");
+				if (f) { fprintf(f, "round: nsearch %zu target %zu service %.0f us\n", nsearch, target, last_service_s * 1e6); fclose(f); }
+			}
+			// carry: callers of the "other group" (counted in run_searches, before this round's results went out)
+			const size_t seen = nsearch + carry, decayed = target - (target + 9) / 10;	// forget departed callers by 10 % a round
+			target = seen > decayed ? seen : decayed;
+			if (target < 1) target = 1;
+			if (target > hdr->n_slots) target = hdr->n_slots;
+		}
 		return found;
 	}
 
@@ -456,7 +494,7 @@ void usage()
 {
 	fprintf(stderr,
 			"usage: pgemb_sidecar --shm /NAME [--lib PATH] [--device K] [--slots N] [--max-dim D] [--max-ef E] [--bulk-mb M]\n"
-			"                     [--max-batch B] [--linger-us U]\n");
+			"                     [--max-batch B] [--linger-us U (max adaptive wait for resubmitting callers, default 50, 0 = off)]\n");
 }
 
 }  // namespace

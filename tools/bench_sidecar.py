@@ -63,7 +63,7 @@ def main():
     ap.add_argument("--metric", default="cosine")
     ap.add_argument("--backends", default="1,16,64,128")
     ap.add_argument("--seconds", type=float, default=5.0)
-    ap.add_argument("--linger-us", type=int, default=0)
+    ap.add_argument("--linger-us", type=int, default=None, help="sidecar's --linger-us (default: the sidecar's own default)")
     ap.add_argument("--lib", default=None, help="C-ABI library the sidecar loads (default: the product library)")
     ap.add_argument("--numpy-data", action="store_true", help="iid numpy data instead of bench.py's generator (no torch / CUDA in this process: emulated runs)")
     # internal: backend mode
