@@ -177,7 +177,14 @@ static int submit_wait(PgembIpcSlot *s)
 	__atomic_thread_fence(__ATOMIC_SEQ_CST);
 	if (ld(&g_hdr->server_sleeping)) futex(&g_hdr->submit_seq, FUTEX_WAKE, 1, NULL);
 	/* a served request takes tens of microseconds to milliseconds: spin briefly, then sleep on the slot's futex */
-	const double spin_until = now_s() + 50e-6;
+	static double spin_s = -1.0; /* PGEMB_CLIENT_SPIN_US: how long a caller polls before it sleeps (default 50; a latency-critical
+								  * deployment with few backends may spin for a whole search, ~600 us, and save the wake-up) */
+	if (spin_s < 0.0)
+	{
+		const char *e = getenv("PGEMB_CLIENT_SPIN_US");
+		spin_s = (e && *e) ? 1e-6 * atof(e) : 50e-6;
+	}
+	const double spin_until = now_s() + spin_s;
 	for (;;)
 	{
 		uint32_t v = ld(&s->state);
