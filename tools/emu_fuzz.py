@@ -1,0 +1,105 @@
+"""Long-running seeded fuzz of the emulated traversal kernel against the oracle (CPU only; tests/emu).
+
+    python tools/emu_fuzz.py [--minutes 20] [--seed0 100000]
+
+Wider ranges than the test-suite's fuzz (graph size, dims, maxM, ef, slots / rings / CTAs, visited-table sizes), both
+kernel modes, product and prototype builds (paired test-and-set, shared-memory visited set, 8 lanes per L2 row), both
+bulk-copy schedules, random pauses around atomics.  Stops at the first mismatch and prints the configuration.
+"""
+import argparse
+import os
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+class _TmpFactory:
+    def __init__(self):
+        self.d = tempfile.mkdtemp(prefix="emu_fuzz_")
+
+    def mktemp(self, name):
+        p = os.path.join(self.d, name + "_%d" % len(os.listdir(self.d)))
+        os.makedirs(p)
+        import pathlib
+        return pathlib.Path(p)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--minutes", type=float, default=20.0)
+    ap.add_argument("--seed0", type=int, default=100000)
+    a = ap.parse_args()
+    import test_search_emulated as T
+    from oracle import oracle
+    oracle.build("port")
+    tf = _TmpFactory()
+    emu, emu_proto = T._build_emu(tf, False), T._build_emu(tf, True)
+    t_end = time.time() + 60.0 * a.minutes
+    seed, done = a.seed0, 0
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed)
+        metric = ["l2", "cosine", "manhattan"][rng.integers(0, 3)]
+        dims = int(rng.integers(1, 70))
+        m = int(rng.choice([1, 2, 3, 4, 6, 9, 16, 20, 33]))
+        efc = int(rng.choice([1, 2, 5, 8, 16, 30, 60]))
+        n = int(rng.choice([1, 2, 3, 10, 40, 90, 180, 400]))
+        levels = int(rng.choice([0, 0, 0, 2, 3, 5]))
+        ef = int(rng.choice([1, 2, 3, 5, 9, 16, 40, 100, 300]))
+        nq = int(rng.choice([1, 3, 7, 13]))
+        coop = int(rng.integers(0, 2))
+        warps, rings, grid = int(rng.integers(1, 7)), int(rng.integers(1, 5)), int(rng.integers(1, 5))
+        vh = int(rng.choice([0, 16, 64, 256, 1024]))
+        proto = bool(rng.integers(0, 2))
+        pairs = int(rng.integers(0, 2)) if proto else 0
+        sv = int(rng.choice([0, 1024, 4096])) if (proto and coop) else 0
+        tpr8 = bool(proto and metric == "l2" and rng.integers(0, 2))
+        os.environ["PGEMB_EMU_TMA"] = "late" if rng.integers(0, 2) else "issue"
+        os.environ["PGEMB_EMU_JITTER"] = str(int(rng.integers(0, 2)))
+        if levels:
+            x = rng.integers(0, levels, (n, dims)).astype(np.float32)
+            q = rng.integers(0, levels, (nq, dims)).astype(np.float32)
+        else:
+            x = rng.standard_normal((n, dims)).astype(np.float32)
+            q = rng.standard_normal((nq, dims)).astype(np.float32)
+        if metric == "cosine":
+            x, q = x + 1.0, q + 1.0
+        if rng.random() < 0.3 and n > 3:
+            k = max(1, n // 4)
+            x[rng.integers(0, n, k)] = x[rng.integers(0, n, k)]
+        labels = (rng.permutation(n).astype(np.uint64) << np.uint64(8)) | np.uint64(1)
+        orc = oracle.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x, labels)
+        for i in range(0, n, 5):
+            if rng.random() < 0.5:
+                orc.mark_deleted(i)
+        want = orc.search_many(q, ef, want_counters=True)
+        what = dict(seed=seed, metric=metric, dims=dims, m=m, efc=efc, n=n, levels=levels, ef=ef, nq=nq, coop=coop, warps=warps, rings=rings, grid=grid,
+                    vh=vh, proto=proto, pairs=pairs, sv=sv, tpr8=tpr8, tma=os.environ["PGEMB_EMU_TMA"], jitter=os.environ["PGEMB_EMU_JITTER"])
+        try:
+            got = T.run_emu(emu_proto if proto else emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh,
+                            pairs=pairs, smem_visited=sv, tpr8=tpr8)
+            ok = (got["n"].tolist() == want["n"].tolist() and got["labels"].tobytes() == want["labels"].tobytes()
+                  and got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist())
+        except AssertionError as e:
+            print("FAIL (assert)", e, what, flush=True)
+            return 1
+        if not ok:
+            print("FAIL (mismatch)", what, flush=True)
+            return 1
+        orc.close()
+        seed += 1
+        done += 1
+        if done % 500 == 0:
+            print(f"{done} configurations ok ({(time.time() - (t_end - 60 * a.minutes)) / 60:.1f} min)", flush=True)
+    print(f"emu_fuzz: {done} configurations, no mismatch (seeds {a.seed0}..{seed - 1})")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
