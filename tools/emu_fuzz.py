@@ -30,16 +30,62 @@ class _TmpFactory:
         return pathlib.Path(p)
 
 
+def fuzz_bind(a, T, oracle, emu):
+    """hnsw_bind_point sequences (raw traversal + select + back-link kernels per insert) against the oracle's link lists."""
+    import ctypes as C
+    t_end = time.time() + 60.0 * a.minutes
+    seed, done = a.seed0, 0
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed)
+        metric = ["l2", "cosine", "manhattan"][rng.integers(0, 3)]
+        dims = int(rng.integers(1, 40))
+        m = int(rng.choice([1, 2, 3, 4, 6, 9]))
+        efc = int(rng.choice([1, 2, 5, 8, 16, 30]))
+        n = int(rng.choice([2, 5, 20, 60, 120]))
+        levels = int(rng.choice([0, 0, 2, 3]))
+        coop = int(rng.integers(0, 2))
+        os.environ["PGEMB_EMU_TMA"] = "late" if rng.integers(0, 2) else "issue"
+        os.environ["PGEMB_EMU_JITTER"] = str(int(rng.integers(0, 2)))
+        x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
+        if metric == "cosine":
+            x = x + 1.0
+        orc = oracle.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x)
+        want = orc.links()
+        maxm = 2 * m
+        row_f, ls = (dims + 3) & ~3, (maxm + 1 + 3) & ~3
+        xv = np.zeros((n, row_f), np.float32); xv[:, :dims] = x
+        lk = np.zeros((n, ls), np.uint32)
+        norms = np.array([T.sqnorm_lane_order(x[i]) for i in range(n)], np.float32) if metric == "cosine" else np.zeros(n, np.float32)
+        err = C.c_int(0)
+        rc = emu.emu_bind_sequence(T.METRIC_ID[metric], coop, T._p(xv, C.c_float), T._p(lk, C.c_uint32), T._p(norms, C.c_float), C.c_uint32(n), C.c_uint32(dims),
+                                   C.c_uint32(row_f), C.c_uint32(ls), C.c_uint32(m), C.c_uint32(maxm), C.c_uint32(efc), C.c_uint32(0), C.c_uint32(n), C.byref(err))
+        what = dict(seed=seed, metric=metric, dims=dims, m=m, efc=efc, n=n, levels=levels, coop=coop, tma=os.environ["PGEMB_EMU_TMA"], jitter=os.environ["PGEMB_EMU_JITTER"])
+        if rc != 0 or err.value != 0 or (lk[:, :maxm + 1] != want).any():
+            print("FAIL (bind)", rc, err.value, what, flush=True)
+            return 1
+        orc.close()
+        seed += 1
+        done += 1
+        if done % 100 == 0:
+            print(f"{done} bind sequences ok", flush=True)
+    print(f"emu_fuzz --bind: {done} sequences, no mismatch (seeds {a.seed0}..{seed - 1})")
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--minutes", type=float, default=20.0)
     ap.add_argument("--seed0", type=int, default=100000)
+    ap.add_argument("--bind", action="store_true", help="fuzz the insert path (link lists) instead of the search")
     a = ap.parse_args()
     import test_search_emulated as T
     from oracle import oracle
     oracle.build("port")
     tf = _TmpFactory()
     emu, emu_proto = T._build_emu(tf, False), T._build_emu(tf, True)
+    if a.bind:
+        return fuzz_bind(a, T, oracle, emu)
     t_end = time.time() + 60.0 * a.minutes
     seed, done = a.seed0, 0
     while time.time() < t_end:
