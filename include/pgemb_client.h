@@ -33,12 +33,17 @@ typedef struct
 } PgembClientIndex;
 
 /* Map the sidecar's segment (`shm_name` as given to `pgemb_sidecar --shm`, NULL: $PGEMB_SIDECAR_SHM) and wait up to
- * timeout_ms for the sidecar to serve.  Idempotent; the mapping is inherited across fork(). */
+ * timeout_ms for the sidecar to serve.  Idempotent; the mapping is inherited across fork().
+ * Replicas: a comma-separated list ("/pgemb0,/pgemb1", one sidecar per GPU) connects to all of them: requests that change
+ * a mirror go to every replica in turn (the replicas stay bit-identical: binds are deterministic), reads of a mirror to
+ * the first, and the searches of this process to one replica (pid modulo the count; $PGEMB_CLIENT_REPLICA overrides). */
 int			pgemb_client_connect(const char *shm_name, int timeout_ms);
 void		pgemb_client_disconnect(void);
 const char *pgemb_client_last_error(void);
 /* Name of the segment this process is (or was last) connected to; "" if never connected. */
 const char *pgemb_client_segment_name(void);
+/* Number of sidecars this process is connected to. */
+int			pgemb_client_replicas(void);
 
 /* Cancellation: `fn` (e.g. a function returning Postgres' InterruptPending) is polled about every 50 ms while a request is
  * pending; when it returns non-zero the call gives up with PGEMB_CLIENT_INTERRUPTED (the reference-shaped calls return

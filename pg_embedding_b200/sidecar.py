@@ -46,6 +46,7 @@ def client() -> C.CDLL:
     lib.pgemb_client_connect.argtypes = [C.c_char_p, C.c_int]
     lib.pgemb_client_last_error.restype = C.c_char_p
     lib.pgemb_client_segment_name.restype = C.c_char_p
+    lib.pgemb_client_replicas.restype = C.c_int
     lib.pgemb_client_attach.argtypes = [hp, sz, C.POINTER(sz), C.POINTER(sz)]
     lib.pgemb_client_append_records.argtypes = [hp, sz, vp, sz]
     lib.pgemb_client_export_records.argtypes = [hp, sz, sz, vp, sz]

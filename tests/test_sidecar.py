@@ -314,6 +314,45 @@ def test_cancelled_call_returns_and_the_sidecar_cleans_up(served, oracle_mod):
     assert struct.unpack_from("<I", raw, 64)[0] == 0
 
 
+def test_two_replicas_stay_identical_and_share_the_searches(emulated_lib, oracle_mod, monkeypatch):
+    """One sidecar per GPU: every change goes to all replicas (same sequence of deterministic binds -> bit-identical
+    graphs), a backend's searches go to one of them."""
+    from pg_embedding_b200 import sidecar
+    names = [f"/pgemb_test_rep{i}_{os.getpid()}" for i in range(2)]
+    srvs = [_start(emulated_lib, nm, slots=8, max_dim=32, max_ef=32, bulk_mb=1) for nm in names]
+    try:
+        sidecar.client().pgemb_client_disconnect()
+        sidecar.connect(",".join(names))
+        assert sidecar.client().pgemb_client_replicas() == 2
+        rng = np.random.default_rng(8)
+        n, dims, m, efc = 40, 6, 3, 8
+        x = rng.integers(0, 3, (n, dims)).astype(np.float32)
+        orc = oracle_mod.FlatIndex("port", dims, m, efc, 16, "l2", capacity=n)
+        idx = sidecar.RemoteIndex(3, dims, m, efc, 16, "l2", capacity=n)
+        for i in range(n):
+            orc.add(x[i], 100 + i)
+            _add_point(idx, x[i], 100 + i)                      # record + hnsw_bind_point: both replicas
+        assert idx.links().tobytes() == orc.links().tobytes()
+        q = rng.integers(0, 3, (6, dims)).astype(np.float32)
+        for rep in ("0", "1"):                                   # the same answers from either replica
+            monkeypatch.setenv("PGEMB_CLIENT_REPLICA", rep)
+            for v in q:
+                assert idx.search(v, 8).tolist() == orc.search(v, 8).tolist()
+        monkeypatch.delenv("PGEMB_CLIENT_REPLICA")
+        assert sidecar.stats()["searches"] == 12
+        # each replica on its own holds the whole graph
+        for nm in names:
+            sidecar.client().pgemb_client_disconnect()
+            sidecar.connect(nm)
+            one = sidecar.RemoteIndex(3, dims, m, efc, 16, "l2", capacity=n)
+            assert len(one) == n and one.links().tobytes() == orc.links().tobytes()
+            assert sidecar.stats()["searches"] == 6
+    finally:
+        sidecar.client().pgemb_client_disconnect()
+        for s in srvs:
+            assert s.stop() == 0
+
+
 def test_sidecar_refuses_to_start_without_a_device(tmp_path):
     """No CPU fallback anywhere: with the product library and no CUDA device the sidecar exits instead of serving."""
     import subprocess
