@@ -73,15 +73,79 @@ def fuzz_bind(a, T, oracle, emu):
     return 0
 
 
+def fuzz_build(a, oracle):
+    """The library's build orchestration on the emulated build of capi.cu: pgemb_build_exact (speculative batches, validation,
+    restart) must give the sequential graph for every batch size; pgemb_build_bulk a valid graph the oracle searches identically."""
+    import ctypes as C
+    from emu_build import build_emulated
+    from pg_embedding_b200 import _lib
+    import pg_embedding_b200 as pg
+    os.environ["PGEMB_EMU_SMS"] = "2"
+    _lib._lib = _lib._bind(C.CDLL(build_emulated(tempfile.mkdtemp(prefix="emu_fuzz_lib_"))))
+    t_end = time.time() + 60.0 * a.minutes
+    seed, done = a.seed0, 0
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed)
+        metric = ["l2", "cosine", "manhattan"][rng.integers(0, 3)]
+        dims = int(rng.integers(1, 24))
+        m = int(rng.choice([1, 2, 3, 4, 6]))
+        efc = int(rng.choice([1, 3, 8, 16, 30]))
+        n = int(rng.choice([2, 9, 40, 90, 160]))
+        levels = int(rng.choice([0, 0, 2, 3]))
+        bmax = int(rng.choice([1, 2, 5, 16, 64, 256]))
+        os.environ["PGEMB_EMU_TMA"] = "late" if rng.integers(0, 2) else "issue"
+        os.environ["PGEMB_EMU_JITTER"] = str(int(rng.integers(0, 2)))
+        x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
+        if metric == "cosine":
+            x = x + 1.0
+        what = dict(seed=seed, metric=metric, dims=dims, m=m, efc=efc, n=n, levels=levels, bmax=bmax)
+        orc = oracle.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x)
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+        idx.append(x)
+        idx.build_exact(0, n, bmax)
+        if idx.links().tobytes() != orc.links().tobytes():
+            print("FAIL (build_exact)", what, flush=True)
+            return 1
+        idx.close()
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+        idx.build(x, batch_max=bmax)
+        links = idx.links()
+        cnt = links[:, 0]
+        ok = bool((cnt <= 2 * m).all())
+        for i in range(n):
+            l = links[i, 1:1 + cnt[i]]
+            ok = ok and bool((l < n).all()) and bool((l != i).all()) and len(set(l.tolist())) == len(l)
+        q = x[rng.integers(0, n, 4)] + np.float32(0.01)
+        orc2 = oracle.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc2.load_graph(x, links)
+        ok = ok and idx.search_batch(q, 16)["labels"].tobytes() == orc2.search_many(q, 16)["labels"].tobytes()
+        if bmax == 1:
+            ok = ok and links.tobytes() == orc.links().tobytes()
+        if not ok:
+            print("FAIL (build_bulk)", what, flush=True)
+            return 1
+        idx.close(); orc.close(); orc2.close()
+        seed += 1
+        done += 1
+        if done % 50 == 0:
+            print(f"{done} builds ok", flush=True)
+    print(f"emu_fuzz --build: {done} configurations, no mismatch (seeds {a.seed0}..{seed - 1})")
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--minutes", type=float, default=20.0)
     ap.add_argument("--seed0", type=int, default=100000)
     ap.add_argument("--bind", action="store_true", help="fuzz the insert path (link lists) instead of the search")
+    ap.add_argument("--build", action="store_true", help="fuzz pgemb_build_exact / pgemb_build_bulk through the emulated library")
     a = ap.parse_args()
-    import test_search_emulated as T
     from oracle import oracle
     oracle.build("port")
+    if a.build:
+        return fuzz_build(a, oracle)
+    import test_search_emulated as T
     tf = _TmpFactory()
     emu, emu_proto = T._build_emu(tf, False), T._build_emu(tf, True)
     if a.bind:
