@@ -95,8 +95,6 @@ def test_scan_topk_tensor_core_filter(pg, oracle_mod, metric, monkeypatch):
     for dims, n, k, nq in ((33, 3000, 64, 40), (128, 30000, 10, 70), (768, 40000, 10, 130)):
         x = _data(rng, n, dims)
         q = _data(rng, nq, dims)
-        if metric == "cosine":
-            x, q = x + 0.5, q + 0.5
         x[n // 2] = x[n // 3]
         labels = rng.permutation(n).astype(np.uint64) + np.uint64(3)
         labels[::11] |= np.uint64(1 << 48)
