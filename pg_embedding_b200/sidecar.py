@@ -168,6 +168,34 @@ class RemoteIndex:
         _libc.free(res)  # embedding.c:327
         return out
 
+    def scan(self, q: np.ndarray, limit: int | None = None):
+        """hnsw_gettuple's iteration (embedding.c:285-370) over the reference-shaped hnsw_search of the client library: when
+        the current results are used up and the search was full (n == efSearch), double efSearch in place (:334), search
+        again and continue with the labels not returned before; stop when a search finds nothing new."""
+        qv = np.ascontiguousarray(q, dtype=np.float32).ravel()
+        ef0 = int(self.h.meta.efSearch)
+        try:
+            results = self.search(qv).tolist()
+            returned = 0
+            no_more = len(results) < int(self.h.meta.efSearch)
+            while limit is None or returned < limit:
+                if returned >= len(results):
+                    if no_more:
+                        return
+                    self.h.meta.efSearch = int(self.h.meta.efSearch) * 2
+                    new = self.search(qv).tolist()
+                    if len(new) <= len(results):
+                        return
+                    no_more = len(new) < int(self.h.meta.efSearch)
+                    seen = set(results)
+                    results += [l for l in new if l not in seen]
+                    if returned >= len(results):
+                        return
+                yield results[returned]
+                returned += 1
+        finally:
+            self.h.meta.efSearch = ef0      # the reference's HnswIndex is per scan (embedding.c:254)
+
     def bind_point(self, idx: int, efconstruction: int | None = None) -> None:
         if efconstruction is not None:
             self.h.meta.efConstruction = efconstruction

@@ -163,6 +163,31 @@ def test_regress_kats_and_insert_path_through_the_sidecar(served, oracle_mod, ca
         orc.close()
 
 
+def test_scan_iteration_with_ef_doubling_through_the_sidecar(served, oracle_mod):
+    """`SELECT ... ORDER BY val <-> q LIMIT n` with n > efSearch: the scan doubles efSearch and de-duplicates (embedding.c:322-366)."""
+    rng = np.random.default_rng(14)
+    n, dims, m, efc = 300, 10, 5, 20
+    x, orc = _graph(oracle_mod, rng, n, dims, m, efc, "l2")
+    idx = served.RemoteIndex(61, dims, m, efc, 4, "l2", capacity=n)            # efSearch = 4
+    idx.append_records(orc.records())
+    q = rng.standard_normal(dims).astype(np.float32)
+    got = list(idx.scan(q, limit=50))
+    # the same iteration over the oracle's hnsw_search
+    want, ef = orc.search(q, 4).tolist(), 4
+    while len(want) < 50:
+        ef *= 2
+        new = orc.search(q, ef).tolist()
+        if len(new) <= len(want):
+            break
+        seen = set(want)
+        want += [l for l in new if l not in seen]
+        if len(new) < ef:
+            break
+    assert got == want[:50] and len(set(got)) == len(got)
+    assert int(idx.h.meta.efSearch) == 4                                         # restored: the handle is per scan
+    assert list(idx.scan(q, limit=3)) == want[:3]
+
+
 def test_failure_behaviour_at_the_boundary(served, oracle_mod):
     import ctypes as C
     rng = np.random.default_rng(1)
