@@ -25,7 +25,7 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat_reg
 def _start(lib, name, **kw):
     from pg_embedding_b200 import build, sidecar
     build.build_sidecar()
-    srv = sidecar.SidecarProcess(name, lib=lib, env={"PGEMB_EMU_SMS": "2"}, **kw)
+    srv = sidecar.SidecarProcess(name, lib=lib, env={"PGEMB_EMU_SMS": "2", "PGEMB_EMU_TMA": "late"}, **kw)
     srv.wait_ready()
     return srv
 
