@@ -695,6 +695,8 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	apply_config(p, cfg, idx->row_f);
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
 #ifdef PGEMB_PROTO
+	// opt-in prototype: rows up to PGEMB_GATHER_LDGSTS_MAX_BYTES (default: all) are gathered with 16-byte asynchronous copies
+	p.gather_ldgsts = (env_int("PGEMB_GATHER_LDGSTS", 0) != 0 && idx->row_f * 4u <= (uint32_t) env_int("PGEMB_GATHER_LDGSTS_MAX_BYTES", 1 << 30)) ? 1u : 0u;
 	p.visited_pairs = 0;
 	if (env_int("PGEMB_VISITED_PAIRS", 0) != 0)
 	{

@@ -116,6 +116,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 		: "memory");
 }
 
+// 16-byte asynchronous copies (SASS LDGSTS): one warp instruction moves 512 contiguous bytes, no uniform-datapath set-up
+// per row as the bulk copy needs.  Completion is per THREAD (commit / wait_group); the other lanes see the data after a
+// __syncwarp().  No L2 policy can be attached (see the note below).
+__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 #endif  // PGEMB_HOST_EMULATION
 
 // NOTE (kept from the LDGSTS experiments, profiles/README.md): `cp.async.cg.shared.global.L2::cache_hint` miscompiles with

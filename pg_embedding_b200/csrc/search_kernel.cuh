@@ -92,6 +92,7 @@ struct SearchParams
 	uint32_t prefetch_links;
 #ifdef PGEMB_PROTO
 	uint32_t visited_pairs;	 // 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
+	uint32_t gather_ldgsts;	 // 1: rows are gathered with 16-byte cp.async pieces (a warp instruction per 512 B) instead of one bulk copy per row
 #endif
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
 	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
@@ -297,6 +298,23 @@ __device__ __forceinline__ float score_row(const float *__restrict__ qts, const 
 __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif
 
+#ifdef PGEMB_PROTO
+// Prototype (PGEMB_GATHER_LDGSTS): gather `rows` rows of a hop into a ring with 16-byte asynchronous copies.  A bulk copy
+// costs ~75 issue cycles per ROW (its operands go through uniform registers, lane by lane); here a whole warp moves 512 B
+// per instruction, i.e. 1 (128-d) to 12 (1536-d) instructions per row.  The copies belong to the issuing threads: the
+// consumer side is cp_async_wait_all() + __syncwarp() instead of the ring's mbarrier.
+__device__ __forceinline__ void gather_rows_ldgsts(const SearchParams &p, unsigned char *ring, const uint32_t *ids, uint32_t rows, uint32_t lane)
+{
+	for (uint32_t r = 0; r < rows; r++)
+	{
+		const unsigned char *src = reinterpret_cast<const unsigned char *>(p.vectors + (size_t) ids[r] * p.row_f);
+		unsigned char		*dst = ring + (size_t) r * p.row_smem;
+		for (uint32_t o = lane * 16u; o < p.row_bytes; o += 512u) cp_async_16(dst + o, src + o);
+	}
+	cp_async_commit();
+}
+#endif
+
 template <int METRIC, int TPR>
 __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char *ring, uint64_t *rbar, uint32_t &rpar, uint32_t warp,
 											uint32_t nwarps, uint32_t n, const uint32_t *hop_id, uint64_t *hop_key, const float *qT,
@@ -311,20 +329,38 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 	for (uint32_t g = warp; g < G; g += nwarps)
 	{
 		const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
-		if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
-		__syncwarp();
-		if (lane < rows)
+#ifdef PGEMB_PROTO
+		const bool ldgsts = p.gather_ldgsts != 0u;
+		if (ldgsts)
+			gather_rows_ldgsts(p, ring, hop_id + g * kRows, rows, lane);
+		else
+#endif
 		{
-			const uint32_t id = hop_id[g * kRows + lane];
-			tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
+			if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
+			__syncwarp();
+			if (lane < rows)
+			{
+				const uint32_t id = hop_id[g * kRows + lane];
+				tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
+			}
 		}
 		const uint32_t k = g * kRows + row_in_stage;
 		const uint32_t kk = min(k, n - 1);
 		const uint32_t my_id = hop_id[kk];
 		float		   vn = 1.0f;
 		if (METRIC == M_COS) vn = p.norms[my_id];
-		mbar_wait(rbar, rpar);
-		rpar ^= 1u;
+#ifdef PGEMB_PROTO
+		if (ldgsts)
+		{
+			cp_async_wait_all();
+			__syncwarp();
+		}
+		else
+#endif
+		{
+			mbar_wait(rbar, rpar);
+			rpar ^= 1u;
+		}
 		const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
 		const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, (int) p.dim, qn, vn);
 		if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
@@ -569,8 +605,18 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				const uint32_t rpar0 = rpar;
 				unsigned char *ring = ring_base + (size_t) rb * p.ring_bytes;
 				uint64_t	  *rbar = &pool->bar[rb];
+#ifdef PGEMB_PROTO
+				const bool ldgsts = p.gather_ldgsts != 0u;
+#endif
 				auto		   issue = [&](uint32_t g) {
 					  const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
+#ifdef PGEMB_PROTO
+					  if (ldgsts)
+					  {
+						  gather_rows_ldgsts(p, ring, hop_id + g * kRows, rows, lane);
+						  return;
+					  }
+#endif
 					  if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
 					  __syncwarp();
 					  if (lane < rows)
@@ -588,8 +634,18 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					const uint32_t my_id = hop_id[kk];
 					float		   vn = 1.0f;
 					if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
-					mbar_wait(rbar, rpar);
-					rpar ^= 1u;
+#ifdef PGEMB_PROTO
+					if (ldgsts)
+					{
+						cp_async_wait_all();  // this thread's pieces have landed ...
+						__syncwarp();		  // ... and, after the warp barrier, everybody's
+					}
+					else
+#endif
+					{
+						mbar_wait(rbar, rpar);
+						rpar ^= 1u;
+					}
 					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
 					const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
 					if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);

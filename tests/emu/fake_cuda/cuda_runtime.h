@@ -55,8 +55,8 @@ namespace emu {
 constexpr size_t kLaneStack = 192 * 1024;
 enum State { RUNNABLE, AT_COLL, DONE };
 enum Kind { K_WARP, K_CTA_BAR, K_CTA_OR };
-
 struct PendingCopy { void *dst; const void *src; uint32_t bytes; uint64_t *bar; };
+
 struct Cta
 {
 	std::vector<PendingCopy> pending;  // PGEMB_EMU_TMA=late: bulk copies issued but not yet performed (guarded by g_mbar_mu)
@@ -75,6 +75,7 @@ struct Lane
 	uint64_t   xchg = 0;
 	int		   site = 0;  // source line of the collective this lane waits at
 	dim3	   tid;
+	std::vector<PendingCopy> cp_pending;  // this thread's cp.async pieces that have not landed yet (late schedule)
 };
 
 struct Warp
@@ -337,6 +338,27 @@ static inline void	   tma_load_1d(void *dst, const void *src, uint32_t bytes, ui
 	emu::bar_complete_if_done(v);
 	memcpy(bar, &v, 8);
 	pthread_mutex_unlock(&emu::g_mbar_mu);
+}
+// 16-byte cp.async pieces: owned by the issuing THREAD.  Under PGEMB_EMU_TMA=late a piece lands only when its own thread
+// waits for its groups -- another lane that reads it without the __syncwarp() after the wait sees the 0xAA fill.
+static inline void cp_async_16(void *dst, const void *src)
+{
+	if (((uintptr_t) dst & 15u) || ((uintptr_t) src & 15u))
+	{
+		fprintf(stderr, "emu: cp.async 16 needs 16-byte aligned addresses (dst %p src %p)\n", dst, src);
+		abort();
+	}
+	if (emu::g_tma_late)
+		emu::L().cp_pending.push_back(emu::PendingCopy{dst, src, 16u, nullptr});
+	else
+		memcpy(dst, src, 16);
+}
+static inline void cp_async_commit() {}
+static inline void cp_async_wait_all()
+{
+	std::vector<emu::PendingCopy> &pq = emu::L().cp_pending;
+	for (const emu::PendingCopy &c : pq) memcpy(c.dst, c.src, c.bytes);
+	pq.clear();
 }
 static inline uint32_t lanemask_lt() { return (1u << (emu::L().tid.x & 31u)) - 1u; }
 

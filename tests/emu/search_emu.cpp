@@ -47,8 +47,9 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	tu.want_warps = (int) want_warps;
 	tu.want_rings = (int) want_rings;
 	tu.want_coop_warps = (int) want_warps;
-	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;
-	smem_visited &= 0x7fffffffu;
+	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;		  // bit 31: 8 lanes per L2 row (prototype)
+	const uint32_t ldgsts = (smem_visited >> 30) & 1u;	  // bit 30: rows gathered with 16-byte cp.async pieces (prototype)
+	smem_visited &= 0x3fffffffu;
 	tu.smem_visited = (int) smem_visited;
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
@@ -56,7 +57,7 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 #ifdef PGEMB_PROTO
 	if (coop && smem_visited && cfg.vhs_entries == 0) return 77;  // the test asked for the shared-memory set
 #else
-	if (visited_pairs || smem_visited || cfg.tpr != 4) return 78;  // prototypes exist only in the -DPGEMB_PROTO build
+	if (visited_pairs || smem_visited || cfg.tpr != 4 || ldgsts) return 78;  // prototypes exist only in the -DPGEMB_PROTO build
 #endif
 	const uint32_t slots = coop ? grid : grid * cfg.warps;
 	const uint32_t vis_words = (n_items + 31) / 32 + 1;
@@ -106,6 +107,7 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	p.prefetch_links = 1;
 #ifdef PGEMB_HAS_VISITED_PAIRS
 	p.visited_pairs = visited_pairs;
+	p.gather_ldgsts = ldgsts;
 #else
 	(void) visited_pairs;
 #endif

@@ -273,6 +273,14 @@ def test_prototype_fast_small_batches(pg_proto, G, oracle_mod, monkeypatch):
         idx.close()
 
 
+def test_prototype_ldgsts_gather(pg_proto, G, oracle_mod, monkeypatch):
+    """PGEMB_GATHER_LDGSTS=1 through the library: searches (both kernel modes) and inserts unchanged."""
+    monkeypatch.setenv("PGEMB_GATHER_LDGSTS", "1")
+    G.test_search_identical_to_oracle(pg_proto, oracle_mod, "cosine", G.SEARCH_CFGS[3])
+    G.test_search_identical_to_oracle(pg_proto, oracle_mod, "l2", G.SEARCH_CFGS[0])
+    G.test_bind_links_identical_to_oracle(pg_proto, oracle_mod, "manhattan", G.BIND_CFGS[0])
+
+
 def _proto_counters(pg):
     from pg_embedding_b200 import _lib
     out = (C.c_uint64 * 4)()

@@ -115,3 +115,11 @@ def test_scan_topk_tensor_core_filter(pg, oracle_mod, metric, monkeypatch):
             assert frac < 0.2
         idx.close()
 
+
+def test_rows_gathered_with_cp_async_pieces(pg, oracle_mod, monkeypatch):
+    """PGEMB_GATHER_LDGSTS=1: LDGSTS row gather (a warp instruction per 512 B) instead of one bulk copy per row."""
+    monkeypatch.setenv("PGEMB_GATHER_LDGSTS", "1")
+    for metric, cfg in (("l2", SEARCH_CFGS[4]), ("cosine", SEARCH_CFGS[7]), ("manhattan", SEARCH_CFGS[3]), ("l2", SEARCH_CFGS[0])):
+        G.test_search_identical_to_oracle(pg, oracle_mod, metric, cfg)
+    G.test_bind_links_identical_to_oracle(pg, oracle_mod, "cosine", BIND_CFGS[1])
+

@@ -68,7 +68,7 @@ def emu_proto(tmp_path_factory):
     return _build_emu(tmp_path_factory, True)
 
 
-def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0, tpr8=False):
+def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0, tpr8=False, ldgsts=False):
     n, dim = x.shape
     row_f = (dim + 3) & ~3
     ls = (maxm + 1 + 3) & ~3
@@ -82,7 +82,7 @@ def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid
     rc = lib.emu_search_ex(METRIC_ID[metric], coop, _p(xv, C.c_float), _p(lk, C.c_uint32), _p(labels, C.c_uint64), _p(norms, C.c_float),
                         C.c_uint32(n), C.c_uint32(dim), C.c_uint32(row_f), C.c_uint32(ls), C.c_uint32(maxm), _p(np.ascontiguousarray(q), C.c_float),
                         C.c_uint32(nq), C.c_uint32(ef), 0, _p(lab, C.c_uint64), _p(dd, C.c_float), _p(ids, C.c_uint32), _p(nn, C.c_int32),
-                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited | (0x80000000 if tpr8 else 0)), C.byref(err))
+                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited | (0x80000000 if tpr8 else 0) | (0x40000000 if ldgsts else 0)), C.byref(err))
     assert rc == 0, rc
     assert err.value == 0, hex(err.value)
     assert lib.emu_tma_unwaited() == 0, "a bulk copy was still in flight when its CTA exited"
@@ -146,6 +146,33 @@ def test_search_kernel_emulated_very_large_ef(emu, oracle_mod, coop):
         assert got["n"].tolist() == want["n"].tolist()
         assert got["labels"].tobytes() == want["labels"].tobytes()
         assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+
+
+@pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
+@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-d{c[1]}m{c[2]}" for c in CASES])
+def test_rows_gathered_with_cp_async_pieces(emu_proto, oracle_mod, case, coop):
+    """Prototype (PGEMB_GATHER_LDGSTS): rows arrive as 16-byte asynchronous copies owned by the issuing lanes (wait_group +
+    __syncwarp instead of the ring's mbarrier).  Under the late schedule a lane that reads another lane's piece too early
+    sees the fill pattern."""
+    metric, dims, m, efc, n, levels, ef, nq = case
+    rng = np.random.default_rng(131 + dims)
+    if levels:
+        x = rng.integers(0, levels, (n, dims)).astype(np.float32); q = rng.integers(0, levels, (nq, dims)).astype(np.float32)
+    else:
+        x = rng.standard_normal((n, dims)).astype(np.float32); q = rng.standard_normal((nq, dims)).astype(np.float32)
+    if metric == "cosine":
+        x, q = x + 1.0, q + 1.0
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+    orc.build(x)
+    want = orc.search_many(q, ef, want_counters=True)
+    for tpr8 in ([False, True] if metric == "l2" else [False]):
+        got = run_emu(emu_proto, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=3, rings=2, grid=2, vh=64, ldgsts=True, tpr8=tpr8)
+        assert got["labels"].tobytes() == want["labels"].tobytes()
+        assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+        for qi in range(nq):
+            k = int(got["n"][qi])
+            dref = oracle_mod.dist_many("port", metric, q[qi], x[got["ids"][qi, :k]]) if k else np.zeros(0, np.float32)
+            assert got["dists"][qi, :k].tobytes() == dref.tobytes()
 
 
 BIND_CASES = [
@@ -238,9 +265,10 @@ def test_fuzz_traversal_emulated(emu, emu_proto, oracle_mod, jitter, monkeypatch
                 orc.mark_deleted(i)
         want = orc.search_many(q, ef, want_counters=True)
         pairs, sv = int(rng.integers(0, 2)), int(rng.choice([0, 1024]))
+        ldg = bool(rng.integers(0, 2))
         sv = sv if coop else 0
-        got = run_emu(emu_proto if (pairs or sv) else emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh, pairs=pairs, smem_visited=sv)
-        what = (seed, pairs, sv, metric, dims, m, efc, n, levels, ef, nq, coop, warps, rings, grid, vh)
+        got = run_emu(emu_proto if (pairs or sv or ldg) else emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh, pairs=pairs, smem_visited=sv, ldgsts=ldg)
+        what = (seed, pairs, sv, ldg, metric, dims, m, efc, n, levels, ef, nq, coop, warps, rings, grid, vh)
         assert got["n"].tolist() == want["n"].tolist(), what
         assert got["labels"].tobytes() == want["labels"].tobytes(), what
         assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), what

@@ -33,6 +33,11 @@ PGEMB_LIB_VARIANT=proto PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_l
 say "1536-d L2 (configs[3] row shape): 4 lanes/row vs 8 lanes/row"
 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_L2_TPR8=1 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
+say "configs[1] shape (dims 128, N 100K, L2, m 16: lives in L2, issue-bound): bulk-copy gather vs LDGSTS gather"
+timeout 600 python tools/bench_shapes.py --dims 128 --n 100000 --metric l2 --m 16 2>&1 | tail -1 | cut -c1-500 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_GATHER_LDGSTS=1 timeout 600 python tools/bench_shapes.py --dims 128 --n 100000 --metric l2 --m 16 2>&1 | tail -1 | cut -c1-500 | tee -a $L
+say "north-star shape with the LDGSTS gather (rows then allocate in L2 without the evict-first policy)"
+PGEMB_LIB_VARIANT=proto PGEMB_GATHER_LDGSTS=1 timeout 600 python bench.py --no-cpu > gpurun_out/r2_bench_ldgsts.json 2> gpurun_out/r2_bench_ldgsts.err; echo "exit $?" | tee -a $L; cut -c1-300 gpurun_out/r2_bench_ldgsts.json | tee -a $L
 say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
