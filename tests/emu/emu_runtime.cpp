@@ -139,7 +139,16 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 				th.emplace_back([w]() { run_warp(*w); });
 			}
 			for (auto &t : th) t.join();
-			for (auto *w : warps) delete w;
+			for (auto *w : warps)
+			{
+				for (int l = 0; l < 32; l++)
+					if (!w->lane[l].cp_pending.empty())
+					{
+						g_tma_unwaited += (int) w->lane[l].cp_pending.size();
+						fprintf(stderr, "emu: %zu cp.async pieces of a thread were never waited for (CTA %u)\n", w->lane[l].cp_pending.size(), bx);
+					}
+				delete w;
+			}
 			if (!cta.pending.empty())
 			{
 				// a bulk copy nobody waited for would land in the shared memory of a CTA that is gone
