@@ -134,17 +134,80 @@ def fuzz_build(a, oracle):
     return 0
 
 
+def fuzz_lib_proto(a, oracle):
+    """The prototype library (emulated -DPGEMB_PROTO build of capi.cu) under random combinations of its opt-in flags: batched
+    search through the host-pointer entry point, the reference-shaped hnsw_search, and insert sequences vs the oracle."""
+    import ctypes as C
+    from emu_build import build_emulated
+    from pg_embedding_b200 import _lib
+    import pg_embedding_b200 as pg
+    os.environ["PGEMB_EMU_SMS"] = "2"
+    _lib._lib = _lib._bind(C.CDLL(build_emulated(tempfile.mkdtemp(prefix="emu_fuzz_lib_"), proto=True)))
+    flags = {"PGEMB_VISITED_PAIRS": ["0", "1"], "PGEMB_SMEM_VISITED": ["0", "1024", "4096"], "PGEMB_L2_TPR8": ["0", "1"], "PGEMB_FAST_SMALL": ["0", "1"],
+             "PGEMB_GATHER_LDGSTS": ["0", "1"], "PGEMB_STREAM_QUERIES": ["0", "1"], "PGEMB_COOP": ["0", "1"]}
+    os.environ["PGEMB_L2_TPR8_MIN_BYTES"] = "0"
+    t_end = time.time() + 60.0 * a.minutes
+    seed, done = a.seed0, 0
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed)
+        chosen = {k: str(rng.choice(v)) for k, v in flags.items()}
+        os.environ.update(chosen)
+        os.environ["PGEMB_EMU_TMA"] = "late" if rng.integers(0, 2) else "issue"
+        os.environ["PGEMB_EMU_JITTER"] = str(int(rng.integers(0, 2)))
+        metric = ["l2", "cosine", "manhattan"][rng.integers(0, 3)]
+        dims = int(rng.integers(1, 40))
+        m = int(rng.choice([1, 2, 4, 6, 17, 33]))
+        efc = int(rng.choice([2, 8, 16, 30]))
+        n = int(rng.choice([3, 20, 90, 200]))
+        levels = int(rng.choice([0, 0, 2, 3]))
+        ef = int(rng.choice([1, 3, 9, 40, 100]))
+        nq = int(rng.choice([1, 2, 5, 70]))
+        x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
+        q = rng.integers(0, max(levels, 1) + 1, (nq, dims)).astype(np.float32) if levels else rng.standard_normal((nq, dims)).astype(np.float32)
+        if metric == "cosine":
+            x, q = x + 1.0, q + 1.0
+        what = dict(seed=seed, metric=metric, dims=dims, m=m, efc=efc, n=n, levels=levels, ef=ef, nq=nq, tma=os.environ["PGEMB_EMU_TMA"], **chosen)
+        orc = oracle.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x)
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=n)
+        if rng.integers(0, 2) and n <= 90:
+            idx.insert_many(x)                                     # sequential binds on the device
+            if idx.links().tobytes() != orc.links().tobytes():
+                print("FAIL (inserts)", what, flush=True)
+                return 1
+        else:
+            idx.append(x, orc.labels(), orc.links())
+        want = orc.search_many(q, ef, want_counters=True)
+        out = idx.search_batch(q, ef, want_stats=True)
+        ok = out["labels"].tobytes() == want["labels"].tobytes() and out["n"].tolist() == want["n"].tolist() and \
+            out["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+        ok = ok and idx.search(q[0], ef).tolist() == want["labels"][0, : want["n"][0]].tolist()
+        if not ok:
+            print("FAIL (search)", what, flush=True)
+            return 1
+        idx.close(); orc.close()
+        seed += 1
+        done += 1
+        if done % 200 == 0:
+            print(f"{done} library runs ok", flush=True)
+    print(f"emu_fuzz --lib-proto: {done} configurations, no mismatch (seeds {a.seed0}..{seed - 1})")
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--minutes", type=float, default=20.0)
     ap.add_argument("--seed0", type=int, default=100000)
     ap.add_argument("--bind", action="store_true", help="fuzz the insert path (link lists) instead of the search")
     ap.add_argument("--build", action="store_true", help="fuzz pgemb_build_exact / pgemb_build_bulk through the emulated library")
+    ap.add_argument("--lib-proto", action="store_true", help="fuzz the prototype library under random combinations of its opt-in flags")
     a = ap.parse_args()
     from oracle import oracle
     oracle.build("port")
     if a.build:
         return fuzz_build(a, oracle)
+    if a.lib_proto:
+        return fuzz_lib_proto(a, oracle)
     import test_search_emulated as T
     tf = _TmpFactory()
     emu, emu_proto = T._build_emu(tf, False), T._build_emu(tf, True)
