@@ -28,6 +28,8 @@ PGEMB_LIB_VARIANT=proto PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_lat
 say "latency with the single-stream small-batch host path (PGEMB_FAST_SMALL=1), alone and with the shared-memory visited set"
 PGEMB_LIB_VARIANT=proto PGEMB_FAST_SMALL=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_GATHER_LDGSTS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+PGEMB_LIB_VARIANT=proto PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 PGEMB_VISITED_PAIRS=1 PGEMB_GATHER_LDGSTS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "latency with the shared-memory visited set (PGEMB_SMEM_VISITED=4096)"
 PGEMB_LIB_VARIANT=proto PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "1536-d L2 (configs[3] row shape): 4 lanes/row vs 8 lanes/row"
