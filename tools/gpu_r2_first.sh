@@ -22,16 +22,10 @@ for f in ("r2_bench_default", "r2_bench_vpairs"):
     except Exception as e:
         print(f, "FAILED", e)
 PY
-say "latency (both kernel modes), default and VISITED_PAIRS"
+say "latency (both kernel modes), product library"
 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-PGEMB_LIB_VARIANT=proto PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-say "latency with the single-stream small-batch host path (PGEMB_FAST_SMALL=1), alone and with the shared-memory visited set"
-PGEMB_LIB_VARIANT=proto PGEMB_FAST_SMALL=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-PGEMB_LIB_VARIANT=proto PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 PGEMB_VISITED_PAIRS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-PGEMB_LIB_VARIANT=proto PGEMB_GATHER_LDGSTS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-PGEMB_LIB_VARIANT=proto PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 PGEMB_VISITED_PAIRS=1 PGEMB_GATHER_LDGSTS=1 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
-say "latency with the shared-memory visited set (PGEMB_SMEM_VISITED=4096)"
-PGEMB_LIB_VARIANT=proto PGEMB_SMEM_VISITED=4096 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
+say "latency prototypes, A/B in one process on the prototype library (graph built once)"
+PGEMB_LIB_VARIANT=proto timeout 900 python tools/bench_latency_ab.py 2> gpurun_out/r2_latency_ab.err | tee -a $L
 say "1536-d L2 (configs[3] row shape): 4 lanes/row vs 8 lanes/row"
 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_L2_TPR8=1 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
