@@ -123,3 +123,31 @@ def test_rows_gathered_with_cp_async_pieces(pg, oracle_mod, monkeypatch):
         G.test_search_identical_to_oracle(pg, oracle_mod, metric, cfg)
     G.test_bind_links_identical_to_oracle(pg, oracle_mod, "cosine", BIND_CFGS[1])
 
+
+def test_fast_small_batches_and_exact_build_clamp(pg, oracle_mod, monkeypatch):
+    """PGEMB_FAST_SMALL=1 (single-stream host path for <= 64 queries, cached launch configuration) and
+    PGEMB_EXACT_CLAMP_SMS=1 (exact parallel build keeps its batches at one search per SM): same results."""
+    monkeypatch.setenv("PGEMB_FAST_SMALL", "1")
+    for case in G.GOLD:
+        G.test_kat_regress(pg, case)
+    rng = np.random.default_rng(77)
+    n, dims, m, efc = 4000, 48, 8, 40
+    x = _data(rng, n, dims)
+    q = _data(rng, 100, dims)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "l2", capacity=n)
+    orc.build(x)
+    idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    idx.append(x, orc.labels(), orc.links())
+    for nq, ef in ((1, 10), (1, 10), (64, 16), (100, 16), (3, 40), (1, 64)):
+        out = idx.search_batch(q[:nq], ef, want_stats=True)
+        want = orc.search_many(q[:nq], ef, want_counters=True)
+        assert out["labels"].tobytes() == want["labels"].tobytes() and out["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), (nq, ef)
+    assert idx.search(q[0], 12).tolist() == orc.search(q[0], 12).tolist()
+    idx.close()
+    monkeypatch.setenv("PGEMB_EXACT_CLAMP_SMS", "1")
+    idx = pg.HnswIndex(dims, m, efc, 64, "l2", capacity=n)
+    idx.append(x)
+    idx.build_exact(0, n, 1024)
+    assert idx.links().tobytes() == orc.links().tobytes()
+    idx.close()
+
