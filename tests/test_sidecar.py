@@ -304,7 +304,7 @@ def test_cancelled_call_returns_and_the_sidecar_cleans_up(served, oracle_mod):
     the sidecar finishes the abandoned request, frees its slot and -- for a bulk request -- the bulk area."""
     import ctypes as C
     rng = np.random.default_rng(12)
-    n, dims, m, efc = 700, 8, 3, 10
+    n, dims, m, efc = 320, 8, 3, 10
     x, orc = _graph(oracle_mod, rng, 50, dims, m, efc, "l2")
     idx = served.RemoteIndex(31, dims, m, efc, 16, "l2", capacity=n)
     rs = idx.record_bytes
