@@ -188,6 +188,27 @@ def test_scan_iteration_with_ef_doubling_through_the_sidecar(served, oracle_mod)
     assert list(idx.scan(q, limit=3)) == want[:3]
 
 
+@pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
+def test_c_backend_linked_against_the_client_library(served, metric, tmp_path):
+    """examples/backend_demo.c: a C program with the reference's call sites (hnsw_bind_point, hnsw_search, free) linked
+    against libpgemb_client.so replays test/sql/knn.sql and prints test/expected/knn.out's order."""
+    from pg_embedding_b200 import sidecar
+    exe = str(tmp_path / "backend_demo")
+    res = subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "backend_demo.c"),
+                          "-L", os.path.dirname(sidecar.CLIENT_PATH), "-lpgemb_client", "-Wl,-rpath," + os.path.dirname(sidecar.CLIENT_PATH), "-o", exe],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    env = dict(os.environ, PGEMB_SIDECAR_SHM=idx_shm(served))
+    out = subprocess.run([exe, metric], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    knn = [c for c in GOLD if c["name"] == "knn"][0]
+    want = ["{%g,%g,%g}" % tuple(v) for v in knn["expected"][metric]]
+    assert out.stdout.split() == want
+    # a second backend finds the relation's mirror (nothing to insert) and gets the same answer
+    out2 = subprocess.run([exe, metric], capture_output=True, text=True, env=env, timeout=300)
+    assert out2.returncode == 0 and out2.stdout == out.stdout
+
+
 def test_failure_behaviour_at_the_boundary(served, oracle_mod):
     import ctypes as C
     rng = np.random.default_rng(1)
