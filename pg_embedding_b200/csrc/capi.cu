@@ -1032,6 +1032,14 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 	const size_t N = idx->n;
 	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
 	size_t		 chunk = (size_t) 1 << 14;
+#ifdef PGEMB_PROTO
+	// the tensor-core filter launches a GEMM + a select kernel per chunk: fewer, larger chunks (PGEMB_SCAN_CHUNK_LOG2 overrides)
+	if (allow_tc && env_int("PGEMB_SCAN_TC", 0) != 0) chunk = (size_t) 1 << 16;
+	{
+		const int lg = env_int("PGEMB_SCAN_CHUNK_LOG2", 0);
+		if (lg >= 8 && lg <= 20) chunk = (size_t) 1 << lg;
+	}
+#endif
 	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
 	const size_t qb = nq * dim * 4, db = nq * chunk * 4, kd = nq * k * 4, kl = nq * k * 8, nb = nq * 4;
 	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + 2 * up(nb) + up(chunk * 4) + 256);
