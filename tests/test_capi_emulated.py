@@ -323,6 +323,12 @@ def test_prototype_tensor_core_filter_scan(pg_proto, G, oracle_mod, metric, monk
             assert got["dists"].tobytes() == want["dists"].tobytes() and got["n"].tolist() == want["n"].tolist()
         c1 = _proto_counters(pg)
         assert c1["scans"] - c0["scans"] == 2 and c1["fallbacks"] == c0["fallbacks"]
+        # several chunks per scan: the running top-k (the filter's threshold) carries over from chunk to chunk
+        monkeypatch.setenv("PGEMB_SCAN_CHUNK_LOG2", "8")
+        got = idx.scan_topk(q, k)
+        assert got["labels"].tobytes() == want["labels"].tobytes() and got["dists"].tobytes() == want["dists"].tobytes()
+        monkeypatch.delenv("PGEMB_SCAN_CHUNK_LOG2")
+        c1 = _proto_counters(pg)
         frac = (c1["rescored"] - c0["rescored"]) / (c1["pairs"] - c0["pairs"])
         print(f"tc filter {metric} dims={dims} n={n} k={k}: {frac:.3f} of the pairs re-scored exactly")
         if k * 20 <= n:
