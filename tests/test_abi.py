@@ -134,3 +134,25 @@ def test_client_library_exports_the_reference_symbols_and_no_cuda():
     os.environ.pop("PGEMB_SIDECAR_SHM", None)
     d = lib.hnsw_dist_func(0, a.ctypes.data_as(C.POINTER(C.c_float)), a.ctypes.data_as(C.POINTER(C.c_float)), C.c_size_t(4))
     assert np.isnan(d)
+
+
+def _build_inprocess_demo(tmp_path):
+    import subprocess
+    from pg_embedding_b200 import build
+    build.build()
+    exe = str(tmp_path / "inprocess_demo")
+    d = os.path.dirname(build.OUT)
+    res = subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "inprocess_demo.c"),
+                          "-L", d, "-lpgemb_b200", "-Wl,-rpath," + d, "-o", exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_c_program_links_against_the_library_and_fails_loudly_without_a_device(lib, tmp_path):
+    """examples/inprocess_demo.c: the reference's call sites in C with libpgemb_b200.so where the reference links
+    hnswalg.o distfunc.o.  On a machine without a CUDA device it must refuse to run -- not compute on the CPU."""
+    import subprocess
+    if lib.pgemb_device_count() > 0:
+        pytest.skip("a CUDA device is present (the GPU variant of this test runs the demo)")
+    out = subprocess.run([_build_inprocess_demo(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 3 and "no CPU fallback" in out.stderr and out.stdout == ""

@@ -443,3 +443,16 @@ def test_sidecar_on_gpu_matches_oracle(oracle_mod, tmp_path):
     finally:
         sidecar.client().pgemb_client_disconnect()
         srv.stop()
+
+
+# (kept in this file because it sorts last: a first-time failure here must not stop the `-x` GPU run before the parity tests)
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
+def test_c_program_replays_the_knn_regress_test(metric, tmp_path):
+    """examples/inprocess_demo.c linked against libpgemb_b200.so (in-process variant of the drop-in boundary)."""
+    from test_abi import _build_inprocess_demo
+    out = subprocess.run([_build_inprocess_demo(tmp_path), metric], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    knn = [c for c in GOLD if c["name"] == "knn"][0]
+    assert out.stdout.split() == ["{%g,%g,%g}" % tuple(v) for v in knn["expected"][metric]]
+
