@@ -144,6 +144,9 @@ pgemb_status pgemb_index_get_labels(const pgemb_index *idx, size_t first, size_t
 pgemb_status pgemb_index_set_labels(pgemb_index *idx, size_t first, size_t n, const label_t *labels);
 /* Drop all nodes (TRUNCATE; test/sql/gh-3.sql). */
 pgemb_status pgemb_index_truncate(pgemb_index *idx);
+/* Grow the index to hold at least `capacity` nodes (a relation grows page by page, embedding.c:636-691); contents and node ids
+ * are preserved, a smaller or equal capacity is a no-op.  On failure the index is unchanged. */
+pgemb_status pgemb_index_reserve(pgemb_index *idx, size_t capacity);
 
 /* Batched k-NN search: nq independent hnsw_search calls (hnswalg.cpp:234-277 semantics per query).
  * ef plays the role of meta->efSearch (k == ef, hnswalg.cpp:260,:237).

@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "pgemb_index_device", "pgemb_index_append", "pgemb_index_append_device",
     "pgemb_index_append_records", "pgemb_index_export_records", "pgemb_index_get_links",
     "pgemb_index_set_links", "pgemb_index_get_labels", "pgemb_index_set_labels",
-    "pgemb_index_truncate", "pgemb_search_batch", "pgemb_search_batch_device",
+    "pgemb_index_truncate", "pgemb_index_reserve", "pgemb_search_batch", "pgemb_search_batch_device",
     "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather", "pgemb_scan_topk",
     "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_build_bulk", "pgemb_build_exact",
 ]
@@ -93,6 +93,7 @@ def _bind(lib: C.CDLL) -> C.CDLL:
     lib.pgemb_index_get_labels.argtypes = [vp, sz, sz, u64p]
     lib.pgemb_index_set_labels.argtypes = [vp, sz, sz, u64p]
     lib.pgemb_index_truncate.argtypes = [vp]
+    lib.pgemb_index_reserve.argtypes = [vp, sz]
     lib.pgemb_search_batch.argtypes = [vp, sz, f32p, sz, u64p, f32p, u32p, i32p, u32p]
     lib.pgemb_search_batch_device.argtypes = [vp, sz, vp, sz, vp, vp, vp, vp, vp, vp]
     lib.pgemb_last_kernel_ms.argtypes = [vp]

@@ -492,6 +492,48 @@ extern "C" pgemb_status pgemb_index_set_labels(pgemb_index *idx, size_t first, s
 	return PGEMB_OK;
 }
 
+extern "C" pgemb_status pgemb_index_reserve(pgemb_index *idx, size_t capacity)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	if (capacity <= idx->capacity) return PGEMB_OK;
+	if (capacity >= (1ull << 31)) return fail(PGEMB_ERR_ARG, "capacity must be in [1, 2^31)");
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	float	 *nv = nullptr, *nn = nullptr;
+	uint32_t *nl = nullptr;
+	uint64_t *nb = nullptr;
+	cudaError_t e = cudaMalloc((void **) &nv, capacity * idx->row_f * sizeof(float));
+	if (e == cudaSuccess) e = cudaMalloc((void **) &nl, capacity * idx->link_stride * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc((void **) &nb, capacity * sizeof(uint64_t));
+	if (e == cudaSuccess) e = cudaMalloc((void **) &nn, capacity * sizeof(float));
+	cudaStream_t s = idx->stream;
+	const size_t n = idx->n;
+	if (e == cudaSuccess && n) e = cudaMemcpyAsync(nv, idx->d_vectors, n * idx->row_f * sizeof(float), cudaMemcpyDeviceToDevice, s);
+	if (e == cudaSuccess && n) e = cudaMemcpyAsync(nl, idx->d_links, n * idx->link_stride * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s);
+	if (e == cudaSuccess && n) e = cudaMemcpyAsync(nb, idx->d_labels, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s);
+	if (e == cudaSuccess && n) e = cudaMemcpyAsync(nn, idx->d_norms, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+	if (e != cudaSuccess)
+	{
+		cudaFree(nv);
+		cudaFree(nl);
+		cudaFree(nb);
+		cudaFree(nn);
+		cudaGetLastError();
+		return fail(e == cudaErrorMemoryAllocation ? PGEMB_ERR_NOMEM : PGEMB_ERR_CUDA, std::string("pgemb_index_reserve: ") + cudaGetErrorString(e));
+	}
+	cudaFree(idx->d_vectors);
+	cudaFree(idx->d_links);
+	cudaFree(idx->d_labels);
+	cudaFree(idx->d_norms);
+	idx->d_vectors = nv;
+	idx->d_links = nl;
+	idx->d_labels = nb;
+	idx->d_norms = nn;
+	idx->capacity = capacity;  // the per-slot visited bitmaps and the build's stamps are sized by capacity: re-made on next use
+	return PGEMB_OK;
+}
+
 extern "C" pgemb_status pgemb_index_truncate(pgemb_index *idx)
 {
 	if (!idx) return fail(PGEMB_ERR_ARG, "null index");

@@ -50,6 +50,7 @@ struct Api
 	pgemb_status (*get_links)(const pgemb_index *, size_t, size_t, idx_t *);
 	pgemb_status (*set_labels)(pgemb_index *, size_t, size_t, const label_t *);
 	pgemb_status (*truncate)(pgemb_index *);
+	pgemb_status (*reserve)(pgemb_index *, size_t);
 	pgemb_status (*search_batch)(pgemb_index *, size_t, const coord_t *, size_t, label_t *, dist_t *, idx_t *, int32_t *, uint32_t *);
 	bool (*bind_point)(HnswMetadata *, const coord_t *, idx_t);	 // the reference-shaped hnsw_bind_point
 	pgemb_status (*build_bulk)(pgemb_index *, size_t, size_t, size_t, double *);
@@ -77,7 +78,7 @@ bool load_api(const char *path, Api &a)
 		   sym(h, "pgemb_index_create", a.index_create) && sym(h, "pgemb_index_destroy", a.index_destroy) && sym(h, "pgemb_index_size", a.index_size) &&
 		   sym(h, "pgemb_index_capacity", a.index_capacity) && sym(h, "pgemb_index_append_records", a.append_records) &&
 		   sym(h, "pgemb_index_export_records", a.export_records) && sym(h, "pgemb_index_get_links", a.get_links) &&
-		   sym(h, "pgemb_index_set_labels", a.set_labels) && sym(h, "pgemb_index_truncate", a.truncate) && sym(h, "pgemb_search_batch", a.search_batch) &&
+		   sym(h, "pgemb_index_set_labels", a.set_labels) && sym(h, "pgemb_index_truncate", a.truncate) && sym(h, "pgemb_index_reserve", a.reserve) && sym(h, "pgemb_search_batch", a.search_batch) &&
 		   sym(h, "hnsw_bind_point", a.bind_point) && sym(h, "pgemb_build_bulk", a.build_bulk) && sym(h, "pgemb_build_exact", a.build_exact) &&
 		   sym(h, "hnsw_dist_func", a.dist_func) && sym(h, "hnsw_init_dist_func", a.init_dist_func);
 }
@@ -220,6 +221,16 @@ struct Server
 					}
 					it = mirrors.emplace(s->index_key, m).first;
 				}
+				if ((size_t) s->a0 > api.index_capacity(it->second.host.dev))
+				{
+					// the relation has grown beyond the mirror: make room (ids and contents are kept)
+					const pgemb_status r = api.reserve(it->second.host.dev, (size_t) s->a0);
+					if (r != PGEMB_OK)
+					{
+						finish_api(s, r);
+						return;
+					}
+				}
 				s->a1 = api.index_size(it->second.host.dev);
 				s->a2 = api.index_capacity(it->second.host.dev);
 				finish(s, PGEMB_OK, nullptr);
@@ -230,6 +241,19 @@ struct Server
 				Mirror *m = find(s);
 				if (!m) return;
 				if (!bulk_owned_by(s, (size_t) s->a0 * (size_t) s->a1)) return;
+				{
+					// a relation grows page by page (embedding.c:636-691): the mirror grows with it, doubling
+					const size_t have = api.index_size(m->host.dev), cap = api.index_capacity(m->host.dev), need = have + (size_t) s->a0;
+					if (need > cap)
+					{
+						const pgemb_status r = api.reserve(m->host.dev, need > 2 * cap ? need : 2 * cap);
+						if (r != PGEMB_OK)
+						{
+							finish_api(s, r);
+							return;
+						}
+					}
+				}
 				finish_api(s, api.append_records(m->host.dev, (size_t) s->a0, bulk(), (size_t) s->a1));
 				return;
 			}

@@ -223,6 +223,10 @@ class HnswIndex:
     def truncate(self) -> None:
         check(self.lib.pgemb_index_truncate(self.dev))
 
+    def reserve(self, capacity: int) -> None:
+        """Grow the device index (a relation grows page by page); node ids and contents are preserved."""
+        check(self.lib.pgemb_index_reserve(self.dev, int(capacity)))
+
     # -- searching ---------------------------------------------------------------------------------
     def search(self, q, efsearch: int | None = None) -> np.ndarray:
         """One hnsw_search call through the reference-shaped entry point (embedding.c:317)."""

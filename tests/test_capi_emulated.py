@@ -150,6 +150,10 @@ def test_bulk_build_orchestration(pg, oracle_mod):
     b.close()
 
 
+def test_index_grows_in_place(pg, G, oracle_mod):
+    G.check_reserve_keeps_contents_and_ids(pg, oracle_mod)
+
+
 def test_scan_and_merge(pg, G, oracle_mod):
     G.test_scan_topk_regress_seqscan(pg)
     G.test_scan_doubles_efsearch(pg, oracle_mod)

@@ -549,3 +549,34 @@ def test_scan_topk_regress_seqscan(pg):
         by_label = {tid_label(*r["tid"]): r["val"] for r in rows}
         assert [by_label[int(l)] for l in out["labels"][0, : out["n"][0]]] == want, metric
         idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# growth: a relation grows page by page (embedding.c:636-691), the device index with it
+# ---------------------------------------------------------------------------------------------------
+def check_reserve_keeps_contents_and_ids(pg, oracle_mod):
+    """Body shared by tests/test_capi_emulated.py (emulated library) and the GPU test at the end of tests/test_sidecar.py."""
+    rng = np.random.default_rng(31)
+    n, dims, m, efc = 260, 12, 4, 16
+    for metric in ("cosine", "l2"):
+        x = rng.standard_normal((n, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
+        orc.build(x)
+        idx = pg.HnswIndex(dims, m, efc, 64, metric, capacity=40)
+        idx.insert_many(x[:40])                                  # full
+        with pytest.raises(Exception):
+            idx.insert_many(x[40:41])
+        idx.reserve(30)                                          # smaller: no-op
+        idx.reserve(150)
+        q = rng.standard_normal((9, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        idx.insert_many(x[40:150])                               # binds see the old nodes at their old ids
+        idx.reserve(n)
+        idx.insert_many(x[150:])
+        assert idx.links().tobytes() == orc.links().tobytes(), metric
+        assert idx.labels().tobytes() == orc.labels().tobytes()
+        for coop in ("1", "0"):                                  # visited bitmaps were re-made for the new capacity
+            with kernel_mode(coop):
+                out = idx.search_batch(q, 500)                   # ef > 4096-entry hash's half -> exercises the bitmap too on small tables
+            assert out["labels"].tobytes() == orc.search_many(q, 500)["labels"].tobytes(), (metric, coop)
+        idx.close()
+

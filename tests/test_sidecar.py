@@ -268,6 +268,24 @@ def test_bulk_transfers_larger_than_the_bulk_area_and_exact_build(served, oracle
     assert idx.links().tobytes() == orc.links().tobytes()
 
 
+def test_mirror_grows_with_the_relation(served, oracle_mod):
+    """The glue attaches with the relation's current size; rows keep arriving (embedding.c:636-691 extends the relation page by
+    page): the sidecar grows the mirror in place, ids and link lists stay what sequential inserts give."""
+    rng = np.random.default_rng(41)
+    n, dims, m, efc = 90, 6, 3, 8
+    x = rng.standard_normal((n, dims)).astype(np.float32)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 16, "l2", capacity=n)
+    idx = served.RemoteIndex(88, dims, m, efc, 16, "l2", capacity=4)              # room for 4 nodes only
+    assert idx.capacity == 4
+    for i in range(n):
+        orc.add(x[i], 500 + i)
+        _add_point(idx, x[i], 500 + i)
+    assert len(idx) == n and idx.links().tobytes() == orc.links().tobytes()
+    again = served.RemoteIndex(88, dims, m, efc, 16, "l2", capacity=4 * n)        # a later attach may ask for more room up front
+    assert again.capacity >= 4 * n and len(again) == n
+    assert idx.search(x[7], 16).tolist() == orc.search(x[7], 16).tolist()
+
+
 def test_client_does_not_hang_when_the_sidecar_dies(emulated_lib, oracle_mod):
     from pg_embedding_b200 import sidecar
     name = f"/pgemb_test_die_{os.getpid()}"
@@ -455,4 +473,12 @@ def test_c_program_replays_the_knn_regress_test(metric, tmp_path):
     assert out.returncode == 0, out.stderr
     knn = [c for c in GOLD if c["name"] == "knn"][0]
     assert out.stdout.split() == ["{%g,%g,%g}" % tuple(v) for v in knn["expected"][metric]]
+
+
+@pytest.mark.gpu
+def test_index_grows_in_place_on_gpu(oracle_mod):
+    """pgemb_index_reserve on the device (new entry point; body shared with the emulated test)."""
+    import pg_embedding_b200 as pg
+    import test_gpu_parity as G
+    G.check_reserve_keeps_contents_and_ids(pg, oracle_mod)
 
