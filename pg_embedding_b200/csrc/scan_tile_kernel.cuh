@@ -60,46 +60,49 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_kernel(const float *__
 #pragma unroll
 			for (int c = 0; c < NCH; c++) acc[a][b][c] = 0.0f;
 
-	// register staging of the next chunk (rows: float4, rows are 16-byte aligned; queries: scalars, any stride)
-	float4 rreg[RLD];
-	float  qreg[QLD];
-	auto   fetch = [&](int kc) {
+	// register staging of the next chunk (rows: float4, rows are 16-byte aligned; queries: scalars, any stride).
+	// Everything that does not depend on the chunk -- source pointers, shared-memory slots -- is computed once here: the
+	// per-chunk staging is then a handful of loads and stores next to the ~1000 arithmetic instructions of a chunk.
+	float4		 rreg[RLD];
+	float		 qreg[QLD];
+	const float *rsrc[RLD];
+	float4		*rdst[RLD];
+	int			 rcol[RLD];
 #pragma unroll
-		  for (int u = 0; u < RLD; u++)
-		  {
-			  const int f = (int) threadIdx.x + kScanThreads * u;
-			  const int r = f / (kScanTileK / 4), c4 = f % (kScanTileK / 4);
-			  uint32_t	rr = row_base + (uint32_t) r;
-			  if (rr >= nr) rr = nr - 1;  // clamp: padding rows are computed and dropped
-			  const int col = kc + c4 * 4;
-			  rreg[u] = (col < main_n) ? __ldg(reinterpret_cast<const float4 *>(vectors + (size_t) (r0 + rr) * row_f + col))
-									   : make_float4(0.f, 0.f, 0.f, 0.f);
-		  }
+	for (int u = 0; u < RLD; u++)
+	{
+		const int f = (int) threadIdx.x + kScanThreads * u;
+		const int r = f / (kScanTileK / 4), c4 = f % (kScanTileK / 4);
+		uint32_t  rr = row_base + (uint32_t) r;
+		if (rr >= nr) rr = nr - 1;	// clamp: padding rows are computed and dropped
+		rcol[u] = c4 * 4;
+		rsrc[u] = vectors + (size_t) (r0 + rr) * row_f + c4 * 4;
+		rdst[u] = reinterpret_cast<float4 *>(&rows_s[r * kScanRowPitch + c4 * 4]);
+	}
+	const float *qsrc[QLD];
+	int			 qcol[QLD];
 #pragma unroll
-		  for (int u = 0; u < QLD; u++)
-		  {
-			  const int e = (int) threadIdx.x + kScanThreads * u;
-			  const int q = e / kScanTileK, c = e % kScanTileK;
-			  uint32_t	qq = q_base + (uint32_t) q;
-			  if (qq >= nq) qq = nq - 1;
-			  const int col = kc + c;
-			  qreg[u] = (col < main_n) ? __ldg(queries + (size_t) qq * q_stride + col) : 0.0f;
-		  }
+	for (int u = 0; u < QLD; u++)
+	{
+		const int e = (int) threadIdx.x + kScanThreads * u;
+		const int q = e / kScanTileK, c = e % kScanTileK;
+		uint32_t  qq = q_base + (uint32_t) q;
+		if (qq >= nq) qq = nq - 1;
+		qcol[u] = c;
+		qsrc[u] = queries + (size_t) qq * q_stride + c;
+	}
+	auto fetch = [&](int kc) {
+#pragma unroll
+		for (int u = 0; u < RLD; u++)
+			rreg[u] = (kc + rcol[u] < main_n) ? __ldg(reinterpret_cast<const float4 *>(rsrc[u] + kc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+		for (int u = 0; u < QLD; u++) qreg[u] = (kc + qcol[u] < main_n) ? __ldg(qsrc[u] + kc) : 0.0f;
 	};
 	auto stash = [&]() {
 #pragma unroll
-		for (int u = 0; u < RLD; u++)
-		{
-			const int f = (int) threadIdx.x + kScanThreads * u;
-			const int r = f / (kScanTileK / 4), c4 = f % (kScanTileK / 4);
-			*reinterpret_cast<float4 *>(&rows_s[r * kScanRowPitch + c4 * 4]) = rreg[u];
-		}
+		for (int u = 0; u < RLD; u++) *rdst[u] = rreg[u];
 #pragma unroll
-		for (int u = 0; u < QLD; u++)
-		{
-			const int e = (int) threadIdx.x + kScanThreads * u;
-			qs_s[e] = qreg[u];	// e = q * kScanTileK + c
-		}
+		for (int u = 0; u < QLD; u++) qs_s[(int) threadIdx.x + kScanThreads * u] = qreg[u];  // e = q * kScanTileK + c
 	};
 
 	const float *rp0 = &rows_s[lane * kScanRowPitch];
