@@ -70,8 +70,9 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 	const uint32_t rows_per_ring = 32u / tpr;
 	// floats per lane run: 4 lanes x dim/4 (two L2 chains interleaved per lane), or 8 lanes x dim/8
 	const uint32_t run = (metric == 0) ? ((dim & ~15u) >> (tpr == 8 ? 3 : 2)) : ((dim & ~3u) >> 2);
-	// runs start 16 bytes apart modulo 128 (LDS.128, 4 lanes) or 8 bytes apart (LDS.64, 8 lanes): conflict-free
-	const uint32_t qt_stride = cfg_align_up(run ? run : 1, 32) + (tpr == 8 ? 2u : 4u);
+	// runs start 16 bytes apart modulo 128: the LDS.128 of the 4 (or 8) distinct runs a warp reads hit distinct banks, and
+	// every run is 16-byte aligned
+	const uint32_t qt_stride = cfg_align_up(run ? run : 1, 32) + 4u;
 
 	SearchConfig t;
 	t.tpr = tpr;

@@ -263,13 +263,51 @@ __device__ __forceinline__ float score_row8_l2(const float *__restrict__ qts, co
 	float		 S = 0.f;
 	const int	 nb = main_n >> 4;
 	const float *vp = rowp + sub;
-#pragma unroll 4
-	for (int b = 0; b < nb; b++)
+	// Four 16-float blocks per iteration, software-pipelined by hand like score_row4: the loads of the NEXT four blocks
+	// (2 x LDS.128 of the query run -- qT8 runs are padded to 16 bytes -- and 8 x LDS.32 of the row) are interleaved with the
+	// arithmetic of the current four; left to itself ptxas issues all loads of an unrolled batch, stalls on the first
+	// difference and then runs the dependent adds back to back.
+#define PGEMB_L2_STEP8(QX, QY, YA, YB)                                               \
+	{                                                                                \
+		const float d0_ = __fsub_rn(QX, YA), d1_ = __fsub_rn(QY, YB);                \
+		S = __fadd_rn(S, __fadd_rn(__fmul_rn(d0_, d0_), __fmul_rn(d1_, d1_)));       \
+	}
+	int		  b = 0;
+	const int nquad = nb >> 2;
+	if (nquad > 0)
+	{
+		const float4 *qp = reinterpret_cast<const float4 *>(qts);
+		float4		  qa = qp[0], qb = qp[1];
+		float		  a0 = vp[0], a1 = vp[8], a2 = vp[16], a3 = vp[24], a4 = vp[32], a5 = vp[40], a6 = vp[48], a7 = vp[56];
+#pragma unroll 1
+		for (int it = 1; it < nquad; it++)
+		{
+			const float *vn_ = vp + 64 * it;
+			const float4 nqa = qp[2 * it];
+			const float	 w0 = vn_[0], w1 = vn_[8];
+			PGEMB_L2_STEP8(qa.x, qa.y, a0, a1)
+			const float w2 = vn_[16], w3 = vn_[24];
+			PGEMB_L2_STEP8(qa.z, qa.w, a2, a3)
+			const float4 nqb = qp[2 * it + 1];
+			const float	 w4 = vn_[32], w5 = vn_[40];
+			PGEMB_L2_STEP8(qb.x, qb.y, a4, a5)
+			const float w6 = vn_[48], w7 = vn_[56];
+			PGEMB_L2_STEP8(qb.z, qb.w, a6, a7)
+			qa = nqa; qb = nqb;
+			a0 = w0; a1 = w1; a2 = w2; a3 = w3; a4 = w4; a5 = w5; a6 = w6; a7 = w7;
+		}
+		PGEMB_L2_STEP8(qa.x, qa.y, a0, a1)
+		PGEMB_L2_STEP8(qa.z, qa.w, a2, a3)
+		PGEMB_L2_STEP8(qb.x, qb.y, a4, a5)
+		PGEMB_L2_STEP8(qb.z, qb.w, a6, a7)
+		b = nquad << 2;
+	}
+	for (; b < nb; b++)
 	{
 		const float2 qq = *reinterpret_cast<const float2 *>(qts + 2 * b);
-		const float	 d0 = __fsub_rn(qq.x, vp[16 * b]), d1 = __fsub_rn(qq.y, vp[16 * b + 8]);
-		S = __fadd_rn(S, __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)));
+		PGEMB_L2_STEP8(qq.x, qq.y, vp[16 * b], vp[16 * b + 8])
 	}
+#undef PGEMB_L2_STEP8
 	float full[8];
 #pragma unroll
 	for (int l = 0; l < 8; l++) full[l] = __shfl_sync(kFull, S, l, 8);
