@@ -343,11 +343,19 @@ __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volati
 // consumer side is cp_async_wait_all() + __syncwarp() instead of the ring's mbarrier.
 __device__ __forceinline__ void gather_rows_ldgsts(const SearchParams &p, unsigned char *ring, const uint32_t *ids, uint32_t rows, uint32_t lane)
 {
+	const uint32_t lo = lane * 16u, rb = p.row_bytes;
+	const uint32_t ring32 = smem_u32(ring) + lo;  // one generic-to-shared conversion for the whole group
 	for (uint32_t r = 0; r < rows; r++)
 	{
-		const unsigned char *src = reinterpret_cast<const unsigned char *>(p.vectors + (size_t) ids[r] * p.row_f);
-		unsigned char		*dst = ring + (size_t) r * p.row_smem;
-		for (uint32_t o = lane * 16u; o < p.row_bytes; o += 512u) cp_async_16(dst + o, src + o);
+		const unsigned char *src = reinterpret_cast<const unsigned char *>(p.vectors + (size_t) ids[r] * p.row_f) + lo;
+		const uint32_t		 dst = ring32 + r * p.row_smem;
+		if (rb <= 512u)
+		{
+			if (lo < rb) cp_async_16_s32(dst, src);	 // short rows (<= 128 dimensions): one instruction per row
+			continue;
+		}
+		// 4 KB per step (a 3 KB row is one step): this lane's pieces at constant offsets, each under its own predicate
+		for (uint32_t o = 0; o + lo < rb; o += 4096u) cp_async_16_x8(dst + o, src + o, rb - o - lo);
 	}
 	cp_async_commit();
 }

@@ -264,7 +264,17 @@ inline void bar_complete_if_done(BarView &v)
 	}
 }
 }  // namespace emu
-static inline uint32_t smem_u32(const void *) { return 0; }
+// 32-bit shared-memory address of a pointer into the CTA's DYNAMIC shared memory (offset from its base; the only use)
+static inline uint32_t smem_u32(const void *p)
+{
+	const ptrdiff_t off = (const unsigned char *) p - emu::dynamic_smem();
+	if (off < 0 || off > (ptrdiff_t) (1 << 20))
+	{
+		fprintf(stderr, "emu: smem_u32 of a pointer outside dynamic shared memory\n");
+		abort();
+	}
+	return (uint32_t) off;
+}
 static inline void	   mbar_init(uint64_t *bar, uint32_t count)
 {
 	emu::BarView v{(count << 1) | (count << 16), 0};
@@ -353,6 +363,12 @@ static inline void cp_async_16(void *dst, const void *src)
 	else
 		memcpy(dst, src, 16);
 }
+static inline void cp_async_16_x8(uint32_t dst_smem_u32, const void *src, uint32_t rem)
+{
+	for (uint32_t j = 0; j < 8u; j++)
+		if (rem > 512u * j) cp_async_16(emu::dynamic_smem() + dst_smem_u32 + 512u * j, (const unsigned char *) src + 512u * j);
+}
+static inline void cp_async_16_s32(uint32_t dst_smem_u32, const void *src) { cp_async_16(emu::dynamic_smem() + dst_smem_u32, src); }
 static inline void cp_async_commit() {}
 static inline void cp_async_wait_all()
 {

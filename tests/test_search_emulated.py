@@ -175,6 +175,27 @@ def test_rows_gathered_with_cp_async_pieces(emu_proto, oracle_mod, case, coop):
             assert got["dists"][qi, :k].tobytes() == dref.tobytes()
 
 
+@pytest.mark.parametrize("coop", [0, 1], ids=["throughput", "latency"])
+@pytest.mark.parametrize("dims", [129, 200, 768, 1030, 1100])
+def test_cp_async_gather_of_long_rows(emu_proto, oracle_mod, dims, coop):
+    """Rows longer than 512 B take the 4-KB-step path of the LDGSTS gather (eight predicated pieces per lane and step):
+    exactly one step (768-d = 3 KB), a partial last piece (dims % 128 != 0), more than one step (> 1024 dims)."""
+    rng = np.random.default_rng(dims)
+    n, m = 70, 5
+    metric = "cosine" if dims % 2 == 0 else "l2"
+    x = rng.standard_normal((n, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+    q = rng.standard_normal((3, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+    orc = oracle_mod.FlatIndex("port", dims, m, 12, 64, metric, capacity=n)
+    orc.build(x)
+    want = orc.search_many(q, 9, want_counters=True)
+    got = run_emu(emu_proto, metric, coop, x, orc.links(), orc.labels(), q, 9, 2 * m, warps=2, rings=2, grid=2, vh=64, ldgsts=True)
+    assert got["labels"].tobytes() == want["labels"].tobytes()
+    assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
+    for qi in range(3):
+        k = int(got["n"][qi])
+        assert got["dists"][qi, :k].tobytes() == oracle_mod.dist_many("port", metric, q[qi], x[got["ids"][qi, :k]]).tobytes()
+
+
 BIND_CASES = [
     # metric, dims, m, efC, n, levels
     ("l2", 3, 3, 8, 70, 3),          # ties + duplicates: equal-distance scan order of the heuristic, full lists re-pruned
