@@ -338,8 +338,8 @@ __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volati
 
 #ifdef PGEMB_PROTO
 // Prototype (PGEMB_GATHER_LDGSTS): gather `rows` rows of a hop into a ring with 16-byte asynchronous copies.  A bulk copy
-// costs ~75 issue cycles per ROW (its operands go through uniform registers, lane by lane); here a whole warp moves 512 B
-// per instruction, i.e. 1 (128-d) to 12 (1536-d) instructions per row.  The copies belong to the issuing threads: the
+// takes ~75 cycles of the issuing warp per ROW (few instructions, but an ELECT / R2UR / UBLKCP loop that runs lane by lane
+// through the uniform datapath); here a whole warp moves 512 B per instruction and nothing is serialised.  The copies belong to the issuing threads: the
 // consumer side is cp_async_wait_all() + __syncwarp() instead of the ring's mbarrier.
 __device__ __forceinline__ void gather_rows_ldgsts(const SearchParams &p, unsigned char *ring, const uint32_t *ids, uint32_t rows, uint32_t lane)
 {
