@@ -109,7 +109,7 @@ def test_record_layout(pg, G, oracle_mod):
 def test_exact_parallel_build_orchestration(pg, oracle_mod):
     """pgemb_build_exact: speculative batches, stamp/validate kernels, prefix acceptance, restart -- must equal n sequential inserts."""
     rng = np.random.default_rng(5)
-    for metric, dims, m, efc, n, levels in (("l2", 4, 3, 10, 180, 3), ("cosine", 12, 4, 16, 200, 0)):
+    for metric, dims, m, efc, n, levels in (("l2", 4, 3, 10, 120, 3), ("cosine", 12, 4, 16, 130, 0)):
         x = rng.integers(0, levels, (n, dims)).astype(np.float32) if levels else rng.standard_normal((n, dims)).astype(np.float32)
         if metric == "cosine":
             x = x + 1.0
@@ -204,8 +204,8 @@ def test_product_build_ignores_prototype_flags(pg, G, oracle_mod, monkeypatch):
     G.test_scan_topk_regress_seqscan(pg)
 
 
-@pytest.mark.parametrize("flags", [{"PGEMB_VISITED_PAIRS": "1"}, {"PGEMB_SMEM_VISITED": "1024"}, {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "2048"}],
-                         ids=["pairs", "smem-visited", "both"])
+@pytest.mark.parametrize("flags", [{"PGEMB_VISITED_PAIRS": "1"}, {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "2048"}],
+                         ids=["pairs", "both"])     # the shared-memory set alone: tests/test_search_emulated.py
 def test_prototype_traversal_flags(pg_proto, G, P, oracle_mod, flags, monkeypatch):
     pg = pg_proto
     P.test_visited_pairs_mode(pg, oracle_mod, G.SEARCH_CFGS[0], flags, monkeypatch)       # incl. the repeated-id fallback
@@ -240,7 +240,7 @@ def test_prototype_exact_build_batch_clamp(pg_proto, oracle_mod, monkeypatch):
     """PGEMB_EXACT_CLAMP_SMS=1 only changes batch sizes of the exact parallel build: still the sequential graph."""
     monkeypatch.setenv("PGEMB_EXACT_CLAMP_SMS", "1")
     rng = np.random.default_rng(6)
-    n, dims, m, efc = 260, 6, 3, 10
+    n, dims, m, efc = 150, 6, 3, 10
     x = rng.integers(0, 3, (n, dims)).astype(np.float32)          # ties and duplicates
     orc = oracle_mod.FlatIndex("port", dims, m, efc, 16, "l2", capacity=n)
     orc.build(x)

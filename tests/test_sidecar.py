@@ -259,12 +259,12 @@ def test_bulk_transfers_larger_than_the_bulk_area_and_exact_build(served, oracle
     assert len(idx) == n
     back = idx.export_records(0, n)
     assert back.tobytes() == rec.tobytes()
-    # CREATE INDEX through the sidecar: exact parallel build of the first 300 nodes == 300 sequential reference inserts
+    # CREATE INDEX through the sidecar: exact parallel build of the first 160 nodes == 160 sequential reference inserts
     idx.truncate()
-    idx.append_records(rec[:300])
-    idx.build(0, 300, batch_max=64, exact=True)
-    orc = oracle_mod.FlatIndex("port", dims, m, efc, 16, "l2", capacity=300)
-    orc.build(x[:300], np.arange(300, dtype=np.uint64))
+    idx.append_records(rec[:160])
+    idx.build(0, 160, batch_max=64, exact=True)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 16, "l2", capacity=160)
+    orc.build(x[:160], np.arange(160, dtype=np.uint64))
     assert idx.links().tobytes() == orc.links().tobytes()
 
 
@@ -343,7 +343,7 @@ def test_cancelled_call_returns_and_the_sidecar_cleans_up(served, oracle_mod):
     the sidecar finishes the abandoned request, frees its slot and -- for a bulk request -- the bulk area."""
     import ctypes as C
     rng = np.random.default_rng(12)
-    n, dims, m, efc = 320, 8, 3, 10
+    n, dims, m, efc = 220, 8, 3, 10
     x, orc = _graph(oracle_mod, rng, 50, dims, m, efc, "l2")
     idx = served.RemoteIndex(31, dims, m, efc, 16, "l2", capacity=n)
     rs = idx.record_bytes
