@@ -214,7 +214,7 @@ class SidecarProcess:
     """Runs pgemb_sidecar as a child process (tests, benches).  `lib` = the C-ABI library it should dlopen()."""
 
     def __init__(self, shm_name: str, lib: str | None = None, slots: int = 64, max_dim: int = 2000, max_ef: int = 1024, bulk_mb: int = 16,
-                 linger_us: int | None = None, device: int = 0, env: dict | None = None):
+                 linger_us: int | None = None, device: int = 0, env: dict | None = None, max_batch: int | None = None):
         if not os.path.isfile(SERVER_PATH):
             raise ImportError(f"{SERVER_PATH} is missing: python -m pg_embedding_b200.build")
         self.shm_name = shm_name
@@ -222,6 +222,8 @@ class SidecarProcess:
                "--device", str(device)]
         if linger_us is not None:       # else the sidecar's default (adaptive wait of at most 50 us / a quarter of a round)
             cmd += ["--linger-us", str(linger_us)]
+        if max_batch is not None:
+            cmd += ["--max-batch", str(max_batch)]
         if lib:
             cmd += ["--lib", lib]
         e = dict(os.environ)

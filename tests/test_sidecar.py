@@ -286,6 +286,33 @@ def test_mirror_grows_with_the_relation(served, oracle_mod):
     assert idx.search(x[7], 16).tolist() == orc.search(x[7], 16).tolist()
 
 
+def test_groups_larger_than_max_batch_are_split(emulated_lib, oracle_mod, tmp_path):
+    """--max-batch 2 with five concurrent backends: a group of pending searches is served in several launches, every caller
+    still gets its own answer."""
+    from pg_embedding_b200 import sidecar
+    name = f"/pgemb_test_mb_{os.getpid()}"
+    srv = _start(emulated_lib, name, slots=16, max_dim=32, max_ef=32, bulk_mb=1, linger_us=20000, max_batch=2)
+    try:
+        sidecar.client().pgemb_client_disconnect()
+        sidecar.connect(name)
+        rng = np.random.default_rng(15)
+        n, dims, m, efc, ef = 200, 10, 4, 16, 8
+        x, orc = _graph(oracle_mod, rng, n, dims, m, efc, "l2")
+        idx = sidecar.RemoteIndex(21, dims, m, efc, 64, "l2", capacity=n)
+        idx.append_records(orc.records())
+        P, per = 5, 5
+        q = rng.standard_normal((P * per, dims)).astype(np.float32)
+        want = orc.search_many(q, ef)
+        got = _run_backends(name, 21, (dims, m, efc, 64, "l2"), q, ef, P, tmp_path)
+        for k in range(P * per):
+            assert got[k] == want["labels"][k, : want["n"][k]].tolist(), k
+        st = sidecar.stats()
+        assert st["searches"] == P * per and st["max_batch"] <= 2, st
+    finally:
+        sidecar.client().pgemb_client_disconnect()
+        assert srv.stop() == 0
+
+
 def test_client_does_not_hang_when_the_sidecar_dies(emulated_lib, oracle_mod):
     from pg_embedding_b200 import sidecar
     name = f"/pgemb_test_die_{os.getpid()}"
