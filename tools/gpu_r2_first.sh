@@ -47,3 +47,5 @@ PGEMB_LIB_VARIANT=proto timeout 600 python tools/bench_build.py --n 1000000 --bu
 PGEMB_LIB_VARIANT=proto PGEMB_EXACT_CLAMP_SMS=1 timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
 say "sidecar over the prototype library: single-stream small batches + shared-memory visited set"
 PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 timeout 900 python tools/bench_sidecar.py --lib pg_embedding_b200/libpgemb_b200_proto.so --backends 1,16 --seconds 4 2>> gpurun_out/r2_sidecar.err | tee -a $L
+say "sidecar, one backend that polls for the whole search instead of sleeping (PGEMB_CLIENT_SPIN_US=1000)"
+PGEMB_CLIENT_SPIN_US=1000 timeout 600 python tools/bench_sidecar.py --backends 1,4 --seconds 3 2>> gpurun_out/r2_sidecar.err | tee -a $L
