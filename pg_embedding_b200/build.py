@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpgemb_b200.so")
-# same sources with -DPGEMB_PROTO: the opt-in prototypes that have not been measured on a B200 yet (DESIGN.md section 11).
+# same sources with -DPGEMB_PROTO: the opt-in prototypes that have not been measured on a B200 yet (DESIGN.md section 11b).
 # Only loaded when PGEMB_LIB_VARIANT=proto (tests and tools/gpu_r2_first.sh); the product library above never contains them.
 OUT_PROTO = os.path.join(HERE, "libpgemb_b200_proto.so")
 SOURCES = ["capi.cu"]

@@ -40,7 +40,7 @@
 
 namespace pgemb {
 
-// Opt-in prototypes that have not run on a B200 yet (DESIGN.md section 11) are compiled only with -DPGEMB_PROTO, into a
+// Opt-in prototypes that have not run on a B200 yet (DESIGN.md section 11b) are compiled only with -DPGEMB_PROTO, into a
 // separate library (libpgemb_b200_proto.so): the product library's traversal kernels stay instruction-for-instruction
 // the ones that were measured.
 #ifdef PGEMB_PROTO

@@ -88,7 +88,7 @@ def test_product_does_not_import_oracle():
 
 
 def test_product_library_holds_no_prototype_kernels(lib):
-    """Prototypes that have not been measured on a B200 (DESIGN.md section 11) are compiled only into the -DPGEMB_PROTO
+    """Prototypes that have not been measured on a B200 (DESIGN.md section 11b) are compiled only into the -DPGEMB_PROTO
     variant; the product library's device code must not contain them, and both variants export the whole C ABI."""
     import shutil
     import subprocess

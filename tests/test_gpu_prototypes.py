@@ -1,4 +1,4 @@
-"""GPU parity tests of the OPT-IN PROTOTYPES (DESIGN.md section 11): code that has been checked on the host emulator
+"""GPU parity tests of the OPT-IN PROTOTYPES (DESIGN.md section 11b): code that has been checked on the host emulator
 against the oracle but has not run on a B200 yet.  It is compiled only into libpgemb_b200_proto.so (-DPGEMB_PROTO,
 pg_embedding_b200/build.py); the product library does not contain it.  Run with
 
