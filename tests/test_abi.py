@@ -156,3 +156,26 @@ def test_c_program_links_against_the_library_and_fails_loudly_without_a_device(l
         pytest.skip("a CUDA device is present (the GPU variant of this test runs the demo)")
     out = subprocess.run([_build_inprocess_demo(tmp_path)], capture_output=True, text=True, timeout=120)
     assert out.returncode == 3 and "no CPU fallback" in out.stderr and out.stdout == ""
+
+
+def test_product_kernels_are_the_measured_ones(lib):
+    """The kernels of libpgemb_b200.so must be, instruction for instruction, the ones the numbers in profiles/ and DESIGN.md
+    section 9 were measured with (tests/golden/product_sass.json; refresh it with tools/sass_hash.py --write together with the
+    numbers when a kernel changes on purpose).  Only meaningful with the toolchain that recorded the hashes."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    if not shutil.which("cuobjdump") or not shutil.which("nvcc"):
+        pytest.skip("CUDA toolchain not available")
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "product_sass.json")))
+    if subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2] != gold["nvcc"]:
+        pytest.skip("other nvcc than the one that recorded the hashes")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from sass_hash import sass_hashes
+    from pg_embedding_b200 import build
+    got = sass_hashes(build.OUT)
+    assert set(got) == set(gold["kernels"]), set(got) ^ set(gold["kernels"])
+    changed = sorted(k for k in got if got[k] != gold["kernels"][k])
+    assert not changed, f"kernels differ from the measured build: {changed}"
+
