@@ -25,6 +25,16 @@ identical labels for the sampled queries (`parity` in the JSON line).
 
 N>1 (`torchrun`): the index (3.3 GB) fits one GPU, so ranks hold replicas and split the queries
 (SURVEY.md section 8(e)): no data-path collective, "scaling": "weak" (per-GPU batch fixed).
+
+Besides the headline, the ONE JSON line carries legs for the other BASELINE configurations, each with its own in-run parity
+check against the compiled reference (untimed) -- so that the driver's records hold evidence for them too:
+  "configs1"   (N=1)  configs[1]: dims 128, N 100K, L2, m 16 -- a 51 MB working set that lives in L2 (bound stated as such);
+  "scan_topk"  (N=1)  the brute-force operator path: 1024 queries x the 1M x 768 table through the
+                      tcgen05 tensor-core filter + exact re-scoring, TF/s against the TF32 roof, parity against the exact kernels;
+  "sharded"    (N>1)  configs[3] shape: dims 1536, L2, m 32, id-range shards of PGEMB_BENCH_SHARD_ROWS (1.25M) rows per GPU
+                      (10M rows at 8 GPUs), every query searched on every shard, exchange + merge INSIDE the timed region --
+                      peers' lists read over NVLink by the wait+merge kernel (no collective) and, for comparison, ONE NCCL
+                      all-gather + merge; parity of a 1024-query sample against "compiled reference per shard + CPU merge".
 """
 from __future__ import annotations
 
@@ -63,6 +73,7 @@ def parse():
     ap.add_argument("--build-batch", type=int, default=int(os.environ.get("PGEMB_BENCH_BUILD_BATCH", 4096)))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (development)")
+    ap.add_argument("--no-legs", action="store_true", help="headline only: skip the configs1 / scan_topk / sharded legs (development)")
     return ap.parse_args()
 
 
@@ -90,6 +101,20 @@ def make_data(torch, n, nq):
     g.manual_seed(99)
     centres = torch.randn((max(4, int(round(n ** 0.5))), DIMS), generator=g, device="cuda")
     return gen_points(torch, n, 1234, centres), gen_points(torch, nq, 5678, centres)
+
+
+def gen_points_raw(torch, n, seed, centres, chunk=1 << 16):
+    """Same mixture, NOT normalised (the L2 legs)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    dims = centres.shape[1]
+    sigma = 0.3 * float((2.0 * dims) ** 0.5) / float(dims ** 0.5)
+    out = torch.empty((n, dims), dtype=torch.float32, device="cuda")
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        a = torch.randint(0, centres.shape[0], (e - s,), generator=g, device="cuda")
+        out[s:e] = centres[a] + sigma * torch.randn((e - s, dims), generator=g, device="cuda")
+    return out
 
 
 class ClockSampler:
@@ -215,12 +240,17 @@ def main():
     # ---- device-resident outputs ---------------------------------------------------------------------
     d_lab = torch.empty((B, ef), dtype=torch.int64, device="cuda")
     d_n = torch.empty((B,), dtype=torch.int32, device="cuda")
-    d_stats = torch.empty((B, 4), dtype=torch.int32, device="cuda")
+    # the traversal's own per-query counters, written by the TIMED launches themselves (16 bytes per query next to the ~3.8 MB
+    # it reads): the roofline below is "algorithmic bytes of the timed launches / their device time", nothing re-run
+    d_stats = torch.empty((K, B, 4), dtype=torch.int32, device="cuda")
+    d_nres = torch.empty((K, B), dtype=torch.int32, device="cuda")
+    d_stats_w = torch.empty((B, 4), dtype=torch.int32, device="cuda")
 
-    def step_device(s, want_stats=False):
+    def step_device(s, k_timed=None):
         q = Q[s * B:(s + 1) * B]
-        _lib.check(lib.pgemb_search_batch_device(idx.dev, B, q.data_ptr(), ef, d_lab.data_ptr(), None, None, d_n.data_ptr(),
-                                                  d_stats.data_ptr() if want_stats else None, stream))
+        st_ptr = d_stats[k_timed].data_ptr() if k_timed is not None else d_stats_w.data_ptr()
+        n_ptr = d_nres[k_timed].data_ptr() if k_timed is not None else d_n.data_ptr()
+        _lib.check(lib.pgemb_search_batch_device(idx.dev, B, q.data_ptr(), ef, d_lab.data_ptr(), None, None, n_ptr, st_ptr, stream))
 
     def barrier():
         if world > 1:
@@ -238,7 +268,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for s in range(W, W + K):
-        step_device(s)
+        step_device(s, s - W)
     ev1.record()
     torch.cuda.synchronize()
     if os.environ.get("PGEMB_PROFILE"):
@@ -253,19 +283,19 @@ def main():
     value = world * B * K / (ms_max * 1e-3)
     log(f"[rank {rank}] timed region: {ms_max:.1f} ms (max over ranks)")
 
-    # ---- roofline of the dominant kernel (the traversal = gather+score): one more step with counters ----
-    step_device(W, want_stats=True)
-    torch.cuda.synchronize()
-    kms = float(lib.pgemb_last_kernel_ms(idx.dev))
-    st = d_stats.cpu().numpy().astype(np.int64)
-    nres = d_n.cpu().numpy().astype(np.int64)
-    alg_bytes = int((st[:, 0] * DIMS * 4 + st[:, 2] * 4 + nres * 8).sum())
+    # ---- roofline of the dominant kernel (the traversal = gather+score; ONE launch per step, so the timed region IS K launches) ----
+    st = d_stats.cpu().numpy().astype(np.int64).reshape(K * B, 4)
+    nres = d_nres.cpu().numpy().astype(np.int64).reshape(K * B)
+    alg_bytes = int((st[:, 0] * DIMS * 4 + st[:, 2] * 4 + nres * 8).sum()) // K       # per launch, mean over the timed launches
+    kms = ms / K                                                                       # this rank's launches (CUDA events on the launching stream)
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = ncu_traffic_bytes(B) if n == 1_000_000 else None
     roofline = {"bound": "hbm", "kernel": "search_kernel<cosine> (K3: TMA row gather + exact distance + queue update)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "peak_source": peak_src, "traffic": ncu_traffic_bytes(B) if n == 1_000_000 else None,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kms, 3),
+                "peak_source": peak_src, "traffic": traffic,
+                "traffic_source": "static: profiles/r1_search_kernel_cosine768_metrics.csv (ncu --set full capture of this launch shape; not re-measured in this run)" if traffic else None,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kms, 3), "kernel_ms_source": "timed region / steps (one launch per step)",
                 "per_query": {"dist_evals": float(st[:, 0].mean()), "expansions": float(st[:, 1].mean()),
                               "bytes": float(alg_bytes / B)}}
 
@@ -299,6 +329,7 @@ def main():
 
     # ---- recall@10 vs exact brute force (rank 0; reported, not tuned) -----------------------------------
     out = None
+    recall = cpu_baseline = parity = None
     if rank == 0:
         ns = min(1000, B)
         qs = Q[W * B: W * B + ns]
@@ -307,14 +338,37 @@ def main():
         torch.cuda.synchronize()
         got = d_lab[:ns, :10].cpu().numpy()
         recall = float(np.mean([len(set(truth[i].tolist()) & set(got[i].tolist())) / 10.0 for i in range(ns)]))
-        cpu_baseline, parity = None, None
         if not args.no_cpu and world == 1:
             cpu_baseline, parity = cpu_leg(args, idx, Q[W * B:(W + 1) * B], d_lab.cpu().numpy(), d_n.cpu().numpy(), n)
+
+    # ---- the other BASELINE configurations (legs; each frees what it allocates) --------------------------
+    legs = {}
+    if not args.no_legs:
+        if world == 1:
+            try:
+                legs["scan_topk"] = leg_scan_topk(args, torch, lib, _lib, idx, X, Q, n)
+            except Exception as e:                                   # a leg must never take the headline down with it
+                legs["scan_topk"] = {"error": repr(e)[:300]}
+        del X, Q, d_stats, d_nres, hq
+        idx.close()
+        torch.cuda.empty_cache()
+        if world == 1:
+            try:
+                legs["configs1"] = leg_configs1(args, torch, pg, lib, _lib, local)
+            except Exception as e:
+                legs["configs1"] = {"error": repr(e)[:300]}
+        else:
+            try:
+                legs["sharded"] = leg_sharded(args, torch, dist, pg, lib, _lib, rank, world, local)
+            except Exception as e:
+                legs["sharded"] = {"error": repr(e)[:300]}
+                log(f"[rank {rank}] sharded leg failed: {e!r}")
+    if rank == 0:
         out = {
             "metric": "QPS @ recall@10, dims=768 N=1M efSearch=64", "value": round(value, 1), "unit": "queries/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms_max / K, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload, "queries_per_step_per_gpu": B, "k": ef, "parallelism": f"replicas x{world}, queries split",
+            "config": {"workload": workload, "queries_per_step": B, "queries_per_step_per_gpu": B, "k": ef, "parallelism": f"replicas x{world}, queries split",
                        "l2": "inputs larger than L2 (3.3 GB index vs 126 MB L2); distinct queries every step",
                        "graph": f"GPU bulk build (batch<={args.build_batch}), {build_s:.1f}s, shared by both arms",
                        "distribution": "mixture of sqrt(N) Gaussians, noise 0.3x inter-centre spacing, L2-normalised; seeds 1234/5678"},
@@ -322,6 +376,7 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu_baseline, "parity": parity,
         }
+        out.update(legs)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -329,6 +384,226 @@ def main():
         JSON_OUT.write(json.dumps(out) + "\n")
         JSON_OUT.flush()
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: the brute-force operator path (K6) on the headline table
+# ---------------------------------------------------------------------------------------------------------------------
+def scan_counters(lib):
+    out = (C.c_uint64 * 6)()
+    lib.pgemb_scan_counters(out)
+    return dict(tc=out[0], pairs=out[1], rescored=out[2], fallbacks=out[3], overflow=out[4], exact=out[5])
+
+
+def leg_scan_topk(args, torch, lib, _lib, idx, X, Q, n):
+    nq, k = int(os.environ.get("PGEMB_BENCH_SCAN_QUERIES", 1024)), 64
+    q = Q[:nq].cpu().numpy()
+    fp, u64p, i32p = C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+    lab = np.empty((nq, k), np.uint64); dd = np.empty((nq, k), np.float32); nn = np.zeros(nq, np.int32)
+
+    def run(qq, L, D, Nn):
+        _lib.check(lib.pgemb_scan_topk(idx.dev, qq.shape[0], qq.ctypes.data_as(fp), k, L.ctypes.data_as(u64p), D.ctypes.data_as(fp), Nn.ctypes.data_as(i32p)))
+
+    os.environ.pop("PGEMB_SCAN_TC", None)
+    run(q, lab, dd, nn)                                            # warm-up: staging buffers, norms
+    c0 = scan_counters(lib)
+    reps, times = 3, []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run(q, lab, dd, nn)                                        # host pointers in / out: H2D of the queries and D2H of the results inside
+        times.append(time.perf_counter() - t0)
+    c1 = scan_counters(lib)
+    t = sorted(times)[len(times) // 2]
+    # parity: the exact kernels (no filter) on a sample of the same queries -- labels, order and distance bits
+    ns = min(32, nq)
+    os.environ["PGEMB_SCAN_TC"] = "0"
+    l2 = np.empty((ns, k), np.uint64); d2 = np.empty((ns, k), np.float32); n2 = np.zeros(ns, np.int32)
+    t0 = time.perf_counter()
+    run(q[:ns], l2, d2, n2)
+    t_exact = time.perf_counter() - t0
+    os.environ.pop("PGEMB_SCAN_TC", None)
+    same = bool(lab[:ns].tobytes() == l2.tobytes() and dd[:ns].tobytes() == d2.tobytes() and nn[:ns].tolist() == n2.tolist())
+    flops = 2.0 * nq * n * DIMS
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        bf16 = 1590.0
+    peak_tf32 = bf16 / 2.0
+    hbm, _ = measured_peak_gbs()
+    table_bytes = n * DIMS * 4
+    qtiles = (nq + 127) // 128
+    return {"workload": f"pgemb_scan_topk: {nq} queries x {n} rows x {DIMS} dims, cosine, k={k} (exact brute-force k-NN, SURVEY.md 8(f3))",
+            "seconds": round(t, 5), "pairs_per_s": round(nq * n / t, 0), "queries_per_s": round(nq / t, 1),
+            "tensor": {"bound": "tensor", "achieved": round(flops / t / 1e12, 1), "peak": round(peak_tf32, 1), "unit": "TFLOP/s",
+                       "frac": round(flops / t / 1e12 / peak_tf32, 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"},
+            "hbm_bound_one_table_pass_per_query_tile_s": round(qtiles * table_bytes / (hbm * 1e9), 5),
+            "x_of_that_bound": round(t / (qtiles * table_bytes / (hbm * 1e9)), 2),
+            "rescored_fraction": round((c1["rescored"] - c0["rescored"]) / max(1, c1["pairs"] - c0["pairs"]), 6),
+            "tripwire_fallbacks": int(c1["fallbacks"] - c0["fallbacks"]), "overflowed_queries": int(c1["overflow"] - c0["overflow"]),
+            "through_tensor_path": bool(c1["tc"] - c0["tc"] == reps),
+            "exact_kernels_same_sample": {"queries": ns, "seconds": round(t_exact, 4), "pairs_per_s": round(ns * n / t_exact, 0)},
+            "parity": {"queries": ns, "identical_to_exact_kernels_labels_order_bits": same},
+            "timing": "host wall clock around the C-ABI call (host buffers), median of 3"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: BASELINE configs[1] (dims 128, N 100K, L2, m 16) on one GPU
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_configs1(args, torch, pg, lib, _lib, local):
+    dims, n, m, efc, efs, B, K, W = 128, 100_000, 16, 200, 64, 32768, 10, 3
+    g = torch.Generator(device="cuda"); g.manual_seed(99)
+    centres = torch.randn((max(4, int(round(n ** 0.5))), dims), generator=g, device="cuda")
+    X, Q = gen_points_raw(torch, n, 1234, centres), gen_points_raw(torch, B * (K + W), 5678, centres)
+    idx = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=n, device=local)
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.pgemb_index_append_device(idx.dev, n, X.data_ptr(), None, None, stream)); torch.cuda.synchronize()
+    build_s = idx.build_appended(0, n, 4096)
+    d_lab = torch.empty((B, efs), dtype=torch.int64, device="cuda"); d_n = torch.empty((K, B), dtype=torch.int32, device="cuda")
+    d_st = torch.empty((K, B, 4), dtype=torch.int32, device="cuda")
+
+    def step(s, kt):
+        _lib.check(lib.pgemb_search_batch_device(idx.dev, B, Q[s * B:(s + 1) * B].data_ptr(), efs, d_lab.data_ptr(), None, None, d_n[kt].data_ptr(),
+                                                  d_st[kt].data_ptr(), stream))
+    for s in range(W):
+        step(s, 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(W, W + K):
+        step(s, s - W)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    st = d_st.cpu().numpy().astype(np.int64).reshape(K * B, 4); nres = d_n.cpu().numpy().astype(np.int64).reshape(K * B)
+    alg = int((st[:, 0] * dims * 4 + st[:, 2] * 4 + nres * 8).sum()) // K
+    hbm, _ = measured_peak_gbs()
+    # parity: the compiled reference on the same graph, the whole last batch (100K x 128 is small enough for the CPU)
+    par, cpu = None, None
+    if not args.no_cpu:
+        from oracle import oracle
+        which, kind = pick_checker()
+        orc = oracle.FlatIndex(which, dims, m, efc, efs, "l2", capacity=n)
+        orc.load_records(idx.export_records(0, n))
+        qh = Q[(W + K - 1) * B:(W + K) * B].cpu().numpy()
+        cores = os.cpu_count() or 1
+        ns = 8192
+        ref = orc.search_many(qh[:ns], efs, nthreads=cores)
+        step(W + K - 1, 0); torch.cuda.synchronize()
+        got = d_lab.cpu().numpy()[:ns].view(np.uint64)
+        par = {"queries": ns, "labels_identical_to_cpu_reference": bool((ref["labels"] == got).all() and (ref["n"] == d_n[0].cpu().numpy()[:ns]).all())}
+        cpu = {"value": round(ns / ref["seconds"], 1), "unit": "queries/s", "cores": cores, "kind": kind, "sample": f"{ns} queries, one pass, same graph"}
+        orc.close()
+    truth = torch.cat([torch.topk(torch.cdist(Q[W * B + i: W * B + i + 250], X), 10, dim=1, largest=False).indices for i in range(0, 1000, 250)]).cpu().numpy()
+    step(W, 0); torch.cuda.synchronize()
+    got10 = d_lab[:1000, :10].cpu().numpy()
+    recall = float(np.mean([len(set(truth[i].tolist()) & set(got10[i].tolist())) / 10.0 for i in range(1000)]))
+    idx.close()
+    return {"workload": f"dims={dims} N={n} L2 m={m} efC={efc} efS={efs} (BASELINE configs[1]), {B} queries per step, bulk build {build_s:.1f}s",
+            "value": round(B / (ms * 1e-3), 1), "unit": "queries/s", "ms_per_step": round(ms, 3), "steps": K, "warmup": W, "recall_at_10": round(recall, 4),
+            "roofline": {"bound": "l2", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
+                         "hbm_peak": hbm, "frac_of_hbm_peak": round(alg / (ms * 1e-3) / 1e9 / hbm, 4),
+                         "note": "working set 51 MB vectors + 13 MB links < 126 MB L2: rows are served by L2, not HBM -- the HBM roof is NOT the binding one "
+                                 "here; the kernel is bound by the dependent-hop latency (7 rows x 512 B per hop) -- see profiles/README.md",
+                         "per_query": {"dist_evals": float(st[:, 0].mean()), "expansions": float(st[:, 1].mean())}},
+            "cpu_baseline": cpu, "parity": par}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: BASELINE configs[3] shape, id-range shards across the ranks (N > 1)
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_sharded(args, torch, dist, pg, lib, _lib, rank, world, local):
+    from pg_embedding_b200 import sharded
+    dims, m, efc, efs = 1536, 32, 200, 64
+    rows = int(os.environ.get("PGEMB_BENCH_SHARD_ROWS", 1_250_000))
+    B = int(os.environ.get("PGEMB_BENCH_SHARD_BATCH", 16384))
+    K, W = min(args.steps, 10), 2
+    n_total = rows * world
+    lo, hi = sharded.shard_bounds(n_total, world)[rank]
+    g = torch.Generator(device="cuda"); g.manual_seed(99)
+    centres = torch.randn((max(4, int(round(n_total ** 0.5))), dims), generator=g, device="cuda")
+    X = gen_points_raw(torch, hi - lo, 1234 + rank, centres)           # this rank's id range
+    Q = gen_points_raw(torch, B * (K + W), 5678, centres)              # the same queries on every rank
+    idx = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=hi - lo, device=local)
+    labels = torch.arange(lo, hi, dtype=torch.int64, device="cuda")   # labels = global ids
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.pgemb_index_append_device(idx.dev, hi - lo, X.data_ptr(), labels.data_ptr(), None, stream)); torch.cuda.synchronize()
+    build_s = idx.build_appended(0, hi - lo, 4096)
+    log(f"[rank {rank}] sharded leg: shard [{lo},{hi}) built in {build_s:.1f}s")
+    peer = sharded.PeerExchange(idx, B, efs)
+    nccl = sharded.ShardedSearch(sharded.gpu_local_search_packed(idx), sharded.gpu_merge_packed())
+
+    def timed(run):
+        for s in range(W):
+            run(Q[s * B:(s + 1) * B])
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = int(lib.pgemb_launch_count())
+        e0.record()
+        for s in range(W, W + K):
+            out = run(Q[s * B:(s + 1) * B])
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / K, out, (int(lib.pgemb_launch_count()) - l0) / K
+
+    ms_peer, out_peer, launches_peer = timed(lambda q: peer.search(q, efs))
+    merge_ms = peer.merge_ms()
+    c0 = nccl.collectives
+    ms_nccl, out_nccl, launches_nccl = timed(lambda q: nccl.search(q, efs))
+    coll_per_step = (nccl.collectives - c0) / (K + W)
+    same_exchanges = bool(torch.equal(out_peer[1], out_nccl[1]) and torch.equal(out_peer[0], out_nccl[0]) and torch.equal(out_peer[2], out_nccl[2]))
+    # ---- parity of a query sample: compiled reference per shard + (dist,label) merge on the CPU ----
+    parity = None
+    if not args.no_cpu:
+        ns = 1024
+        qs = Q[(W + K - 1) * B:(W + K - 1) * B + ns]
+        from oracle import oracle
+        which, kind = pick_checker()
+        orc = oracle.FlatIndex(which, dims, m, efc, efs, "l2", capacity=hi - lo)
+        chunk = 1 << 15
+        for s0 in range(0, hi - lo, chunk):
+            orc.load_records(idx.export_records(s0, min(chunk, hi - lo - s0)))
+        qh = qs.cpu().numpy()
+        ref = orc.search_many(qh, efs, nthreads=max(1, (os.cpu_count() or 1) // world))
+        orc.close()
+        lab = torch.from_numpy(ref["labels"].view(np.int64).copy()).cuda()
+        cnt = torch.from_numpy(ref["n"].astype(np.int32)).cuda()
+        # the reference returns no distances: score its labels with its own distance function (rows fetched from this shard)
+        dd = np.full((ns, efs), np.inf, np.float32)
+        for i in range(ns):
+            c = int(ref["n"][i])
+            if c:
+                rowsel = X[(lab[i, :c] - lo)].cpu().numpy()
+                dd[i, :c] = oracle.dist_many(which, "l2", qh[i], rowsel)
+        dref = torch.from_numpy(dd).cuda()
+        gl = [torch.empty_like(lab) for _ in range(world)]; gd = [torch.empty_like(dref) for _ in range(world)]; gn = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(gl, lab); dist.all_gather(gd, dref); dist.all_gather(gn, cnt)      # parity plumbing, untimed
+        if rank == 0:
+            L = torch.stack(gl).cpu().numpy(); D = torch.stack(gd).cpu().numpy(); Nn = torch.stack(gn).cpu().numpy()
+            gpu_l = out_peer[1][:ns].cpu().numpy(); gpu_d = out_peer[0][:ns].cpu().numpy(); gpu_n = out_peer[2][:ns].cpu().numpy()
+            ok = True
+            for i in range(ns):
+                pairs = sorted((float(D[s, i, j]), int(L[s, i, j])) for s in range(world) for j in range(int(Nn[s, i])))[:efs]
+                if gpu_n[i] != len(pairs) or gpu_l[i, :len(pairs)].tolist() != [p_[1] for p_ in pairs] or \
+                        gpu_d[i, :len(pairs)].tobytes() != np.array([p_[0] for p_ in pairs], np.float32).tobytes():
+                    ok = False
+                    break
+            parity = {"queries": ns, "identical_to_reference_per_shard_plus_cpu_merge": ok, "checker": kind}
+    err = peer.error()
+    peer.close()
+    idx.close()
+    del X, Q
+    torch.cuda.empty_cache()
+    bytes_rank = sharded.packed_bytes(B, efs)
+    return {"workload": f"dims={dims} N={n_total} ({rows} per shard) L2 m={m} efC={efc} efS={efs} (BASELINE configs[3] shape), index sharded by id range over {world} GPUs, "
+                        f"{B} queries per step searched on EVERY shard, bulk build {build_s:.1f}s per shard",
+            "value": round(B / (ms_peer * 1e-3), 1), "unit": "queries/s", "ms_per_step": round(ms_peer, 3), "steps": K, "warmup": W, "scaling": "weak (shard size fixed, index grows with N)",
+            "exchange": "peer memory: per-shard top-k read over NVLink by the wait+merge kernel (CUDA IPC), flags published by 4-byte copies; no collective",
+            "launches_per_step": launches_peer, "collectives_per_step": 0, "merge_kernel_ms_incl_peer_wait": round(merge_ms, 3),
+            "exchange_bytes_read_per_rank_per_step": bytes_rank * (world - 1), "peer_error": err,
+            "nccl_allgather": {"value": round(B / (ms_nccl * 1e-3), 1), "ms_per_step": round(ms_nccl, 3), "collectives_per_step": coll_per_step,
+                               "launches_per_step": launches_nccl, "bytes_per_rank": bytes_rank, "same_results_as_peer_exchange": same_exchanges},
+            "parity": parity}
 
 
 def host_graph(idx, n, which):

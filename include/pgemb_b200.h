@@ -165,6 +165,12 @@ pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const coord_t *quer
 pgemb_status pgemb_search_batch_device(pgemb_index *idx, size_t nq, const coord_t *d_queries, size_t ef,
                                        label_t *d_labels_out, dist_t *d_dists_out, idx_t *d_ids_out,
                                        int32_t *d_n_out, uint32_t *d_stats_out, void *stream);
+/* pgemb_search_batch_device (and every other *_device entry) only LAUNCHES: it does not read the traversal's sticky error flag
+ * (1 = link id / count out of range, 2 = tie-overflow buffer exceeded, 4 = a streamed batch never arrived).  Poll it with this
+ * call: it synchronises `stream`, returns PGEMB_ERR_STATE with the message if the flag was raised, and clears it.
+ * One search may be in flight per index at a time (the per-slot visited sets, the work counter and the flag are the index's):
+ * concurrent searches on two streams need two pgemb_index handles (replicas). */
+pgemb_status pgemb_index_poll_error(pgemb_index *idx, void *stream);
 /* Device time (ms) of the search kernel inside the last pgemb_search_batch* call on this index,
  * measured with CUDA events on the launching stream; <0 if unavailable. */
 float pgemb_last_kernel_ms(const pgemb_index *idx);
@@ -185,6 +191,37 @@ pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coord_t *queri
  * labels_out[nq*k] (unused tail ~0), dists_out[nq*k] optional, n_out[nq]. Host pointers. */
 pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out,
                              dist_t *dists_out, int32_t *n_out);
+/* How pgemb_scan_topk gets there: for L2 and cosine the table is first FILTERED by one dense
+ * contraction on the tensor cores (tcgen05.mma kind::tf32, TMA tensor maps, TMEM accumulators; csrc/scan_umma_kernel.cuh) --
+ * a row is dropped only if a rigorous lower bound of its distance exceeds the query's current k-th best exact distance --
+ * and the survivors are re-scored with the reference-exact arithmetic, so labels, order and distance bits are those of
+ * the exact kernels.  Manhattan (no bilinear form) and small tables use the exact tiled kernel throughout.
+ * PGEMB_SCAN_TC=0 disables the filter, =2 forces it.  Counters since load:
+ *   out[0] scans through the tensor-core filter   out[1] (query,row) pairs it covered   out[2] candidates re-scored exactly
+ *   out[3] scans repeated on the exact kernels because the error-bound tripwire fired
+ *   out[4] queries whose candidate list overflowed (re-scored against the whole chunk)   out[5] exact-kernel scans */
+void pgemb_scan_counters(uint64_t out[6]);
+/* Test entry: the raw tensor-core products S[q][j] = q . row(r0 + j) (TF32 operands, fp32 accumulate) of the K6 kernel,
+ * out[nq * nr], host pointers -- lets a test check descriptors / swizzle / TMEM read-back against a float64 product. */
+pgemb_status pgemb_debug_umma_product(pgemb_index *idx, size_t nq, const coord_t *queries, size_t r0, size_t nr, float *out);
+
+/* ---- index-scan iteration: the reference's beginscan / gettuple / endscan trio -- embedding.c:249-387; SURVEY.md 8(f2) ----
+ * One handle = one scan (`so`): the query, the per-scan efSearch that hnsw_gettuple doubles in place (embedding.c:334) and the
+ * TIDs handed out so far.  pgemb_index_scan_next is hnsw_gettuple: the first call searches with efSearch; when the results
+ * run out and the last search was full (n == efSearch) it doubles efSearch, searches again and continues with the TIDs not
+ * returned before (qsort + bsearch de-duplication exactly as embedding.c:354-363, quirks included -- csrc/capi.cu); it ends
+ * when a search returns fewer than efSearch results and they are used up, or finds nothing new (:338).
+ *   returns 1: *tid_out = next heap TID (the label's low 48 bits; flags dropped as by the reference's 6-byte memcpy)
+ *           0: no more tuples
+ *         < 0: -(pgemb_status): "HNSW index search failed" (embedding.c:318, :336)
+ * pgemb_index_scan_next_batch hands out up to `max` tuples of the same sequence in one call. */
+typedef struct pgemb_index_scan pgemb_index_scan;
+pgemb_status pgemb_index_scan_begin(pgemb_index *idx, const coord_t *query, size_t efSearch, pgemb_index_scan **out);
+int          pgemb_index_scan_next(pgemb_index_scan *scan, label_t *tid_out);
+pgemb_status pgemb_index_scan_next_batch(pgemb_index_scan *scan, size_t max, label_t *tids_out, size_t *n_out);
+size_t       pgemb_index_scan_ef(const pgemb_index_scan *scan);        /* current (doubled) efSearch */
+uint64_t     pgemb_index_scan_searches(const pgemb_index_scan *scan);  /* hnsw_search calls made so far */
+void         pgemb_index_scan_end(pgemb_index_scan *scan);
 
 /* hnsw_bind_point against the device mirror (hnswalg.cpp:225-232): node `id` must be stored and
  * unbound.  Sequential semantics: one call at a time per index. */
@@ -217,6 +254,33 @@ pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t n, size_t 
 pgemb_status pgemb_merge_topk_device(size_t nq, size_t n_shards, size_t k,
                                      const dist_t *d_dists_in, const label_t *d_labels_in, const int32_t *d_n_in,
                                      dist_t *d_dists_out, label_t *d_labels_out, int32_t *d_n_out, void *stream);
+
+/* The same merge over ONE packed buffer per shard -- [labels u64 nq*k | dists f32 nq*k | counts i32 nq], pgemb_packed_topk_bytes
+ * -- i.e. over what a single all-gather of the per-shard results delivers (shard s at d_packed + s * shard_stride_bytes). */
+size_t       pgemb_packed_topk_bytes(size_t nq, size_t k);
+pgemb_status pgemb_merge_topk_packed_device(size_t nq, size_t n_shards, size_t k, const void *d_packed, size_t shard_stride_bytes,
+                                            dist_t *d_dists_out, label_t *d_labels_out, int32_t *d_n_out, void *stream);
+
+/* ---- sharded search without a collective: peers read each other's results over NVLink -------------
+ * One pgemb_exchange per rank (= per GPU / shard).  Set-up, once: create; hand the 64-byte handle (other processes) or
+ * the buffer pointer (ranks of the same process) of every rank to every rank; attach.  Per step, on every rank with the SAME
+ * nq and queries:   pgemb_sharded_search_device  (local traversal -> this rank's result area, then its sequence number is
+ * stored into every peer's flag array by 4-byte copies in stream order)   and   pgemb_sharded_merge_device  (ONE kernel that
+ * waits for all peers' flags, reads their lists directly from peer memory and merges by (dist,label), hnswalg.cpp:236-247).
+ * No NCCL call, no host synchronisation between the two.  ef must equal the k the exchange was created with. */
+#define PGEMB_IPC_HANDLE_BYTES 64
+typedef struct pgemb_exchange pgemb_exchange;
+pgemb_status pgemb_exchange_create(int device, int rank, int world, size_t max_nq, size_t k, pgemb_exchange **out);
+void         pgemb_exchange_destroy(pgemb_exchange *ex);
+pgemb_status pgemb_exchange_handle(pgemb_exchange *ex, void *handle_out /* PGEMB_IPC_HANDLE_BYTES */);
+void        *pgemb_exchange_buffer(pgemb_exchange *ex);
+/* handles: world x PGEMB_IPC_HANDLE_BYTES (this rank's own slot is ignored); same_process != 0: each slot starts with the raw
+ * device pointer from pgemb_exchange_buffer instead of an IPC handle. */
+pgemb_status pgemb_exchange_attach(pgemb_exchange *ex, const void *handles, int same_process);
+pgemb_status pgemb_sharded_search_device(pgemb_index *idx, pgemb_exchange *ex, size_t nq, const coord_t *d_queries, size_t ef, void *stream);
+pgemb_status pgemb_sharded_merge_device(pgemb_exchange *ex, size_t nq, label_t *d_labels_out, dist_t *d_dists_out, int32_t *d_n_out, void *stream);
+float        pgemb_exchange_last_merge_ms(pgemb_exchange *ex);
+int          pgemb_exchange_error(pgemb_exchange *ex);
 
 #ifdef __cplusplus
 }

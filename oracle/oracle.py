@@ -59,8 +59,7 @@ def load(which: str) -> C.CDLL:
     if which in _LIBS:
         return _LIBS[which]
     path = _PATHS[which]
-    if not os.path.isfile(path):
-        build(which)
+    build(which)          # incremental (make): picks up edits of the checker sources; a no-op for `ref` where /root/reference is absent
     if not os.path.isfile(path):
         raise FileNotFoundError(f"{path} missing (build it here with `make -C oracle`)")
     lib = C.CDLL(path)
@@ -102,6 +101,15 @@ def load(which: str) -> C.CDLL:
     lib.flat_search_many.argtypes = [vp, f32p, sz, sz, C.c_int, C.c_int, u64p, i32p, u64p]
     lib.flat_build.restype = C.c_double
     lib.flat_build.argtypes = [vp, sz, f32p, u64p]
+    lib.flat_scan_begin.restype = vp
+    lib.flat_scan_begin.argtypes = [vp, f32p, sz, sz]
+    lib.flat_scan_next.restype = C.c_int
+    lib.flat_scan_next.argtypes = [vp, u64p]
+    lib.flat_scan_searches.restype = C.c_uint64
+    lib.flat_scan_searches.argtypes = [vp]
+    lib.flat_scan_ef.restype = sz
+    lib.flat_scan_ef.argtypes = [vp]
+    lib.flat_scan_end.argtypes = [vp]
     if which == "port":
         lib.oracle_cosine_norm.restype = C.c_float
         lib.oracle_cosine_norm.argtypes = [f32p, sz]
@@ -275,6 +283,26 @@ class FlatIndex:
         if n < 0:
             raise RuntimeError("hnsw_search failed")
         return out[:n].copy()
+
+    def scan(self, q, efsearch: int | None = None, limit: int | None = None) -> dict:
+        """hnsw_gettuple's iteration (embedding.c:285-370; oracle/scan_iter.c) until it returns false or `limit` tuples:
+        dict(tids = the heap TIDs in the order handed out, searches = hnsw_search calls made, ef = final efSearch)."""
+        ef = self.efs if efsearch is None else int(efsearch)
+        qv = np.ascontiguousarray(q, dtype=np.float32)
+        assert qv.shape == (self.dims,)
+        sc = self.lib.flat_scan_begin(self.h, _f32p(qv), self.dims, ef)
+        out, t = [], C.c_uint64(0)
+        try:
+            while limit is None or len(out) < limit:
+                r = self.lib.flat_scan_next(sc, C.byref(t))
+                if r < 0:
+                    raise RuntimeError("HNSW index search failed")
+                if r == 0:
+                    break
+                out.append(t.value)
+            return {"tids": np.array(out, dtype=np.uint64), "searches": int(self.lib.flat_scan_searches(sc)), "ef": int(self.lib.flat_scan_ef(sc))}
+        finally:
+            self.lib.flat_scan_end(sc)
 
     def search_ids(self, q, efsearch: int | None = None):
         """(port only) internal ids + distances of searchBaseLayer's result, ascending (dist, id)."""

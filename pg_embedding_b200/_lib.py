@@ -9,10 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# PGEMB_LIB_VARIANT=proto loads the same sources built with -DPGEMB_PROTO (opt-in prototypes not yet measured on a
-# B200; build.py).  Anything else is the product library.
-VARIANT = os.environ.get("PGEMB_LIB_VARIANT", "")
-LIB_PATH = os.path.join(HERE, "libpgemb_b200_proto.so" if VARIANT == "proto" else "libpgemb_b200.so")
+LIB_PATH = os.path.join(HERE, "libpgemb_b200.so")
 
 PGEMB_OK = 0
 
@@ -41,8 +38,13 @@ ABI_SYMBOLS = [
     "pgemb_index_append_records", "pgemb_index_export_records", "pgemb_index_get_links",
     "pgemb_index_set_links", "pgemb_index_get_labels", "pgemb_index_set_labels",
     "pgemb_index_truncate", "pgemb_index_reserve", "pgemb_search_batch", "pgemb_search_batch_device",
-    "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather", "pgemb_scan_topk",
-    "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_build_bulk", "pgemb_build_exact",
+    "pgemb_index_poll_error", "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather", "pgemb_scan_topk",
+    "pgemb_scan_counters", "pgemb_debug_umma_product",
+    "pgemb_index_scan_begin", "pgemb_index_scan_next", "pgemb_index_scan_next_batch", "pgemb_index_scan_ef", "pgemb_index_scan_searches",
+    "pgemb_index_scan_end",
+    "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_packed_topk_bytes", "pgemb_merge_topk_packed_device",
+    "pgemb_exchange_create", "pgemb_exchange_destroy", "pgemb_exchange_handle", "pgemb_exchange_buffer", "pgemb_exchange_attach",
+    "pgemb_sharded_search_device", "pgemb_sharded_merge_device", "pgemb_exchange_last_merge_ms", "pgemb_exchange_error", "pgemb_build_bulk", "pgemb_build_exact",
 ]
 
 _lib = None
@@ -96,14 +98,43 @@ def _bind(lib: C.CDLL) -> C.CDLL:
     lib.pgemb_index_reserve.argtypes = [vp, sz]
     lib.pgemb_search_batch.argtypes = [vp, sz, f32p, sz, u64p, f32p, u32p, i32p, u32p]
     lib.pgemb_search_batch_device.argtypes = [vp, sz, vp, sz, vp, vp, vp, vp, vp, vp]
+    lib.pgemb_index_poll_error.argtypes = [vp, vp]
     lib.pgemb_last_kernel_ms.argtypes = [vp]
     lib.pgemb_last_kernel_ms.restype = C.c_float
     lib.pgemb_dist_batch.argtypes = [C.c_int, sz, sz, f32p, C.c_int, f32p, f32p]
     lib.pgemb_dist_gather.argtypes = [vp, sz, f32p, sz, u32p, f32p]
     lib.pgemb_scan_topk.argtypes = [vp, sz, f32p, sz, u64p, f32p, i32p]
+    lib.pgemb_scan_counters.argtypes = [u64p]
+    lib.pgemb_scan_counters.restype = None
+    lib.pgemb_debug_umma_product.argtypes = [vp, sz, f32p, sz, sz, f32p]
+    lib.pgemb_index_scan_begin.argtypes = [vp, f32p, sz, C.POINTER(vp)]
+    lib.pgemb_index_scan_next.argtypes = [vp, u64p]
+    lib.pgemb_index_scan_next.restype = C.c_int
+    lib.pgemb_index_scan_next_batch.argtypes = [vp, sz, u64p, C.POINTER(sz)]
+    lib.pgemb_index_scan_ef.argtypes = [vp]
+    lib.pgemb_index_scan_ef.restype = sz
+    lib.pgemb_index_scan_searches.argtypes = [vp]
+    lib.pgemb_index_scan_searches.restype = C.c_uint64
+    lib.pgemb_index_scan_end.argtypes = [vp]
+    lib.pgemb_index_scan_end.restype = None
     lib.pgemb_bind_point.argtypes = [vp, C.c_uint32]
     lib.pgemb_insert_batch.argtypes = [vp, sz, f32p, u64p]
     lib.pgemb_merge_topk_device.argtypes = [sz, sz, sz, vp, vp, vp, vp, vp, vp, vp]
+    lib.pgemb_packed_topk_bytes.argtypes = [sz, sz]
+    lib.pgemb_packed_topk_bytes.restype = sz
+    lib.pgemb_merge_topk_packed_device.argtypes = [sz, sz, sz, vp, sz, vp, vp, vp, vp]
+    lib.pgemb_exchange_create.argtypes = [C.c_int, C.c_int, C.c_int, sz, sz, C.POINTER(vp)]
+    lib.pgemb_exchange_destroy.argtypes = [vp]
+    lib.pgemb_exchange_destroy.restype = None
+    lib.pgemb_exchange_handle.argtypes = [vp, vp]
+    lib.pgemb_exchange_buffer.argtypes = [vp]
+    lib.pgemb_exchange_buffer.restype = vp
+    lib.pgemb_exchange_attach.argtypes = [vp, vp, C.c_int]
+    lib.pgemb_sharded_search_device.argtypes = [vp, vp, sz, vp, sz, vp]
+    lib.pgemb_sharded_merge_device.argtypes = [vp, sz, vp, vp, vp, vp]
+    lib.pgemb_exchange_last_merge_ms.argtypes = [vp]
+    lib.pgemb_exchange_last_merge_ms.restype = C.c_float
+    lib.pgemb_exchange_error.argtypes = [vp]
     lib.pgemb_build_bulk.argtypes = [vp, sz, sz, sz, C.POINTER(C.c_double)]
     lib.pgemb_build_exact.argtypes = [vp, sz, sz, sz, C.POINTER(C.c_double), u64p]
     lib.hnsw_search.argtypes = [mp, f32p, C.POINTER(sz), C.POINTER(u64p)]

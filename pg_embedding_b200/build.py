@@ -14,11 +14,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpgemb_b200.so")
-# same sources with -DPGEMB_PROTO: the opt-in prototypes that have not been measured on a B200 yet.
-# Only loaded when PGEMB_LIB_VARIANT=proto (tests and tools/gpu_r2_first.sh); the product library above never contains them.
-OUT_PROTO = os.path.join(HERE, "libpgemb_b200_proto.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["common.cuh", "dist_exact.cuh", "search_kernel.cuh", "aux_kernels.cuh", "bind_kernel.cuh", "scan_tile_kernel.cuh", "search_config.h",
+HEADERS = ["common.cuh", "dist_exact.cuh", "search_kernel.cuh", "aux_kernels.cuh", "bind_kernel.cuh", "scan_tile_kernel.cuh", "scan_umma_kernel.cuh",
+           "search_config.h",
            os.path.join("..", "..", "include", "pgemb_b200.h")]
 
 
@@ -43,7 +41,7 @@ def needs_build(out: str = OUT) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
 
 
-def _cmd(out: str, proto: bool, verbose: bool) -> list:
+def _cmd(out: str, verbose: bool) -> list:
     return [
         nvcc_path(), "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
         "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,16 +49,15 @@ def _cmd(out: str, proto: bool, verbose: bool) -> list:
         "-Xptxas", "-v" if verbose else "-warn-spills",
         "-I", os.path.join(HERE, "..", "include"),
         "-o", out,
-    ] + (["-DPGEMB_PROTO"] if proto else []) + [os.path.join(CSRC, f) for f in SOURCES]
+    ] + [os.path.join(CSRC, f) for f in SOURCES]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Build the product library and the prototype variant (both in-tree); returns the product library's path."""
+    """Build the C-ABI library in-tree; returns its path."""
     jobs = []
-    for out, proto in ((OUT, False), (OUT_PROTO, True)):
-        if force or needs_build(out):
-            cmd = _cmd(out, proto, verbose)
-            jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    if force or needs_build(OUT):
+        cmd = _cmd(OUT, verbose)
+        jobs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
     build_sidecar(force)
     for cmd, pr in jobs:
         so, se = pr.communicate()

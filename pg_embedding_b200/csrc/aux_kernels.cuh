@@ -22,7 +22,6 @@ __global__ void norms_kernel(const float *__restrict__ vectors, uint32_t row_f, 
 	if (row < n && sub == 0) norms[first + row] = s;
 }
 
-#ifdef PGEMB_PROTO
 // ---- invariant check for caller-provided link lists: are the ids of every list distinct? ----------------
 // (Lists written by the bind kernels always are; the traversal may then test-and-set both halves of a list
 // concurrently, search_kernel.cuh `visited_pairs`.)  One warp per node; sets *dup_flag if any list repeats an id.
@@ -43,7 +42,6 @@ __global__ void links_distinct_kernel(const uint32_t *__restrict__ links, uint32
 	}
 	if (dup) *dup_flag = 1;
 }
-#endif
 
 // ---- pair distances: out[i] = dist(a[i] | a[0], b[i]); LANES threads per pair, scalar loads --------
 template <int METRIC>
@@ -247,37 +245,82 @@ __global__ void records_pack_kernel(unsigned char *__restrict__ recs, size_t str
 // Order = (dist,label) lexicographic, the pair order of searchKnn's result queue (hnswalg.cpp:236-247).
 // One warp per query; rank of an element = its index in its own list + sum over the other lists of the
 // number of smaller elements (binary search), so no sort is needed.
-__global__ void merge_topk_kernel(uint32_t nq, uint32_t n_shards, uint32_t k, const float *__restrict__ din,
-								  const uint64_t *__restrict__ lin, const int32_t *__restrict__ nin, float *__restrict__ dout,
-								  uint64_t *__restrict__ lout, int32_t *__restrict__ nout)
+//
+// The lists are addressed through one base pointer per shard, so the same kernel merges
+//   * a buffer gathered by ONE NCCL all-gather (base + s * stride), and
+//   * the peers' result buffers read DIRECTLY over NVLink (CUDA-IPC / peer-mapped pointers): then `flags` is this rank's
+//     flag array -- flags[s] >= seq means shard s has published its lists of step `seq` (the peer's copy engine stores the
+//     flag after its search kernel, in stream order) -- and every warp first waits for all its peers (ld.acquire.sys), so the
+//     exchange needs no collective launch at all: merge = wait + peer loads + rank-by-counting in one kernel.
+constexpr uint32_t kMaxShards = 16;
+struct ShardLists
+{
+	const float	   *dist[kMaxShards];  // [nq][k]
+	const uint64_t *lab[kMaxShards];   // [nq][k]
+	const int32_t  *cnt[kMaxShards];   // [nq]
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p)
+{
+#ifdef PGEMB_HOST_EMULATION
+	return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+	uint32_t v;
+	asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+#endif
+}
+
+__global__ void merge_topk_lists_kernel(uint32_t nq, uint32_t n_shards, uint32_t k, const ShardLists in, const uint32_t *__restrict__ flags,
+										uint32_t seq, uint32_t self, float *__restrict__ dout, uint64_t *__restrict__ lout,
+										int32_t *__restrict__ nout, int *__restrict__ error_flag)
 {
 	const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t lane = threadIdx.x & 31;
 	if (q >= nq) return;
-	// input layout: [shard][query][k]
+	if (flags != nullptr)
+	{
+		// lane s waits for shard s (sequence numbers only grow; compared as a wrapping distance)
+		if (lane < n_shards && lane != self)
+		{
+			uint32_t spins = 0;
+			while ((int32_t) (ld_acquire_sys_u32(flags + lane) - seq) < 0)
+			{
+				__nanosleep(200);
+				if (++spins > (16u << 20))	// seconds: a peer died or never searched -- flag it, do not hang the GPU
+				{
+					if (error_flag) *error_flag = 5;
+					break;
+				}
+			}
+		}
+		__syncwarp();
+	}
 	uint32_t total = 0;
-	for (uint32_t s = 0; s < n_shards; s++) total += (uint32_t) max(0, min((int32_t) k, nin[(size_t) s * nq + q]));
+	for (uint32_t s = 0; s < n_shards; s++) total += (uint32_t) max(0, min((int32_t) k, in.cnt[s][q]));
 	const uint32_t keep = min(total, k);
 	for (uint32_t e = lane; e < n_shards * k; e += 32)
 	{
 		const uint32_t s = e / k, i = e % k;
-		const uint32_t ns = (uint32_t) max(0, min((int32_t) k, nin[(size_t) s * nq + q]));
+		const uint32_t ns = (uint32_t) max(0, min((int32_t) k, in.cnt[s][q]));
 		if (i >= ns) continue;
-		const size_t   base = ((size_t) s * nq + q) * k;
-		const uint32_t od = f2o(din[base + i]);
-		const uint64_t ol = lin[base + i];
+		const size_t   base = (size_t) q * k;
+		const float	   fd = in.dist[s][base + i];
+		const uint32_t od = f2o(fd);
+		const uint64_t ol = in.lab[s][base + i];
 		uint32_t	   rank = i;
 		for (uint32_t s2 = 0; s2 < n_shards; s2++)
 		{
 			if (s2 == s) continue;
-			const uint32_t n2 = (uint32_t) max(0, min((int32_t) k, nin[(size_t) s2 * nq + q]));
-			const size_t   b2 = ((size_t) s2 * nq + q) * k;
-			uint32_t	   lo = 0, hi = n2;
+			const uint32_t	n2 = (uint32_t) max(0, min((int32_t) k, in.cnt[s2][q]));
+			const float	   *d2p = in.dist[s2] + base;
+			const uint64_t *l2p = in.lab[s2] + base;
+			uint32_t		lo = 0, hi = n2;
 			while (lo < hi)
 			{
 				const uint32_t mid = (lo + hi) >> 1;
-				const uint32_t d2 = f2o(din[b2 + mid]);
-				const uint64_t l2 = lin[b2 + mid];
+				const uint32_t d2 = f2o(d2p[mid]);
+				const uint64_t l2 = l2p[mid];
 				// element of another shard sorts first if smaller, or equal with the lower shard index
 				const bool less = d2 < od || (d2 == od && (l2 < ol || (l2 == ol && s2 < s)));
 				if (less) lo = mid + 1; else hi = mid;
@@ -286,7 +329,7 @@ __global__ void merge_topk_kernel(uint32_t nq, uint32_t n_shards, uint32_t k, co
 		}
 		if (rank < keep)
 		{
-			dout[(size_t) q * k + rank] = din[base + i];
+			dout[(size_t) q * k + rank] = fd;
 			lout[(size_t) q * k + rank] = ol;
 		}
 	}

@@ -6,6 +6,7 @@
 // exception crosses -- hnswalg.cpp:258-276), and adds the bulk/device entry points a GPU needs.
 // There is no CPU implementation of any of it in this library: without a usable CUDA device every
 // entry point fails with PGEMB_ERR_CUDA.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -18,14 +19,8 @@
 #include "aux_kernels.cuh"
 #include "bind_kernel.cuh"
 #include "common.cuh"
-#ifdef PGEMB_PROTO
 #include "scan_tile_kernel.cuh"
-#include "scan_tc_kernel.cuh"
-#include <cublas_v2.h>	// types only: libcublas is dlopen()ed when PGEMB_SCAN_TC is used (no link-time dependency)
-#ifndef PGEMB_HOST_EMULATION
-#include <dlfcn.h>
-#endif
-#endif
+#include "scan_umma_kernel.cuh"
 #include "search_kernel.cuh"
 
 using namespace pgemb;
@@ -50,11 +45,7 @@ static pgemb_status fail(pgemb_status st, const std::string &msg)
 	} while (0)
 
 extern "C" const char *pgemb_last_error(void) { return g_last_error.c_str(); }
-#ifdef PGEMB_PROTO
-extern "C" const char *pgemb_version(void) { return "pg_embedding_b200 0.1 (sm_100a) +proto"; }
-#else
-extern "C" const char *pgemb_version(void) { return "pg_embedding_b200 0.1 (sm_100a)"; }
-#endif
+extern "C" const char *pgemb_version(void) { return "pg_embedding_b200 0.2 (sm_100a)"; }
 extern "C" uint64_t	   pgemb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int pgemb_device_count(void)
@@ -128,6 +119,10 @@ struct pgemb_index
 	// link lists that came from the caller have not been checked for repeated ids yet / result of the last check
 	bool links_checked = true, links_distinct = true;
 	uint64_t	 *d_ovf = nullptr;
+	uint32_t	 *d_seq_ids = nullptr;	 // ids of a run of sequential binds (pgemb_insert_batch)
+	size_t		  seq_ids_cap = 0;
+	uint64_t	 *d_resg = nullptr;	 // result buffers of the huge-ef traversal variant ([slots][2 * ef])
+	size_t		  resg_keys = 0;
 	unsigned int *d_counter = nullptr;
 	int			 *d_error = nullptr;
 	// staging for the host-pointer API
@@ -135,15 +130,13 @@ struct pgemb_index
 	size_t stage_bytes = 0;
 	// bind workspace
 	BindWorkspace bind_ws;
-#ifdef PGEMB_PROTO
-	cublasHandle_t cublas = nullptr;  // PGEMB_SCAN_TC: created on first use
-	// PGEMB_FAST_SMALL: what the last launch configured, so that an identical launch skips the driver calls
+	size_t norms_n = 0;	 // rows [0, norms_n) have their squared norm in d_norms (cosine: all; L2: filled lazily by the tensor-core scan)
+	// what the last traversal launch configured, so that an identical launch skips the attribute / occupancy / L2-window driver calls
 	const void *last_fn = nullptr;
 	uint32_t	last_smem = 0;
 	const void *last_l2_base = nullptr;
 	size_t		last_l2_bytes = 0;
 	cudaStream_t last_l2_stream = nullptr;
-#endif
 };
 
 static pgemb_status set_device(const pgemb_index *idx)
@@ -151,58 +144,6 @@ static pgemb_status set_device(const pgemb_index *idx)
 	CU_TRY(cudaSetDevice(idx->device));
 	return PGEMB_OK;
 }
-
-#ifdef PGEMB_PROTO
-// ---- PGEMB_SCAN_TC: libcublas, loaded on first use (scan_tc_kernel.cuh) -------------------------------------------------
-static std::atomic<uint64_t> g_tc_scans{0}, g_tc_fallbacks{0}, g_tc_rescored{0}, g_tc_pairs{0};
-extern "C" void pgemb_proto_counters(uint64_t out[4])
-{
-	out[0] = g_tc_scans.load();
-	out[1] = g_tc_fallbacks.load();
-	out[2] = g_tc_rescored.load();
-	out[3] = g_tc_pairs.load();
-}
-struct CublasApi
-{
-	cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
-	cublasStatus_t (*destroy)(cublasHandle_t) = nullptr;
-	cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
-	cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void *, const void *, cudaDataType, int,
-							  const void *, cudaDataType, int, const void *, void *, cudaDataType, int, cublasComputeType_t, cublasGemmAlgo_t) = nullptr;
-	bool ok = false;
-};
-static CublasApi &cublas_api()
-{
-	static CublasApi api;
-	static bool		 tried = false;
-	if (tried) return api;
-	tried = true;
-#ifdef PGEMB_HOST_EMULATION
-	api.create = cublasCreate_v2;
-	api.destroy = cublasDestroy_v2;
-	api.set_stream = cublasSetStream_v2;
-	api.gemm_ex = cublasGemmEx;
-	api.ok = true;
-#else
-	const char *cands[] = {getenv("PGEMB_CUBLAS_PATH"), "libcublas.so.12", "/usr/local/cuda/lib64/libcublas.so.12", "libcublas.so"};
-	void	   *h = nullptr;
-	for (const char *c : cands)
-		if (c && *c && (h = dlopen(c, RTLD_NOW | RTLD_LOCAL))) break;
-	if (!h) return api;
-	api.create = (decltype(api.create)) dlsym(h, "cublasCreate_v2");
-	api.destroy = (decltype(api.destroy)) dlsym(h, "cublasDestroy_v2");
-	api.set_stream = (decltype(api.set_stream)) dlsym(h, "cublasSetStream_v2");
-	api.gemm_ex = (decltype(api.gemm_ex)) dlsym(h, "cublasGemmEx");
-	api.ok = api.create && api.destroy && api.set_stream && api.gemm_ex;
-#endif
-	return api;
-}
-static void scan_tc_release(pgemb_index *idx)
-{
-	if (idx->cublas && cublas_api().ok) cublas_api().destroy(idx->cublas);
-	idx->cublas = nullptr;
-}
-#endif
 
 extern "C" pgemb_status pgemb_index_create(const HnswMetadata *meta, size_t capacity, int device, pgemb_index **out)
 {
@@ -270,13 +211,12 @@ extern "C" void pgemb_index_destroy(pgemb_index *idx)
 	cudaFree(idx->d_vlog);
 	cudaFree(idx->d_vhash);
 	cudaFree(idx->d_ovf);
+	cudaFree(idx->d_resg);
+	cudaFree(idx->d_seq_ids);
 	cudaFree(idx->d_counter);
 	cudaFree(idx->d_error);
 	cudaFree(idx->d_stage);
 	bind_ws_free(idx->bind_ws);
-#ifdef PGEMB_PROTO
-	scan_tc_release(idx);
-#endif
 	if (idx->stream) cudaStreamDestroy(idx->stream);
 	if (idx->s_in) cudaStreamDestroy(idx->s_in);
 	if (idx->h_avail) cudaFreeHost(idx->h_avail);
@@ -316,6 +256,7 @@ static pgemb_status compute_norms(pgemb_index *idx, size_t first, size_t n, cuda
 											idx->d_norms);
 	g_launches++;
 	CU_TRY(cudaGetLastError());
+	idx->norms_n = first + n;
 	return PGEMB_OK;
 }
 
@@ -538,6 +479,7 @@ extern "C" pgemb_status pgemb_index_truncate(pgemb_index *idx)
 {
 	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
 	idx->n = 0;
+	idx->norms_n = 0;
 	idx->links_checked = idx->links_distinct = true;
 	return PGEMB_OK;
 }
@@ -554,9 +496,10 @@ static int env_int(const char *name, int dflt)
 static uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // shared-memory layout + slots/rings per CTA: search_config.h (shared with the host emulation harness in tests/emu)
-static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c, bool coop = false)
+static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfig *c, bool coop = false, bool res_global = false)
 {
 	SearchShape sh;
+	sh.res_global = res_global;
 	sh.metric = (int) idx->meta.dist_func;
 	sh.dim = (uint32_t) idx->meta.dim;
 	sh.row_f = idx->row_f;
@@ -564,18 +507,15 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	sh.maxM = (uint32_t) idx->meta.maxM;
 	sh.ef = ef;
 	sh.sm_count = (uint32_t) idx->sm_count;
-#ifdef PGEMB_PROTO
-	// opt-in prototype: 8 lanes per row (4-row rings) for long L2 rows
-	sh.tpr = (sh.metric == DIST_L2 && env_int("PGEMB_L2_TPR8", 0) != 0 && idx->row_f * 4u >= (uint32_t) env_int("PGEMB_L2_TPR8_MIN_BYTES", 4096)) ? 8u : 4u;
-#endif
+	// long L2 rows (>= 4 KB, e.g. 1536-d): 8 lanes per row, rings of 4 rows -> twice as many rings per SM (measured on the
+	// configs[3] row shape: 0.67 -> 0.80 of the HBM roofline, profiles/README.md round 2); PGEMB_L2_TPR8=0 disables
+	sh.tpr = (!res_global && sh.metric == DIST_L2 && env_int("PGEMB_L2_TPR8", 1) != 0 && idx->row_f * 4u >= (uint32_t) env_int("PGEMB_L2_TPR8_MIN_BYTES", 4096)) ? 8u : 4u;
 	SearchTuning tu;
 	tu.duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
 	tu.want_warps = env_int("PGEMB_WARPS", 0);
 	tu.want_rings = env_int("PGEMB_RINGS", 0);
 	tu.want_coop_warps = env_int("PGEMB_COOP_WARPS", 0);
-#ifdef PGEMB_PROTO
-	tu.smem_visited = env_int("PGEMB_SMEM_VISITED", 0);  // opt-in prototype: entries of the latency mode's shared-memory visited set
-#endif
+	tu.smem_visited = env_int("PGEMB_SMEM_VISITED", 4096);  // latency mode: entries of the shared-memory visited set (0 = keep it at L2)
 	switch (make_search_config(sh, tu, coop, c))
 	{
 		case 0: return PGEMB_OK;
@@ -586,13 +526,21 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 
 typedef void (*search_fn_t)(const SearchParams);
 
-static search_fn_t pick_search_kernel(int metric, bool coop, uint32_t tpr)
+static search_fn_t pick_search_kernel(int metric, bool coop, uint32_t tpr, bool res_global = false)
 {
-#ifdef PGEMB_PROTO
+	if (res_global)
+	{
+		if (coop || tpr != 4) return nullptr;
+		switch (metric)
+		{
+			case DIST_L2: return search_kernel<M_L2, false, 4, true>;
+			case DIST_COSINE: return search_kernel<M_COS, false, 4, true>;
+			case DIST_MANHATTAN: return search_kernel<M_MAN, false, 4, true>;
+		}
+		return nullptr;
+	}
 	if (metric == DIST_L2 && tpr == 8) return coop ? search_kernel<M_L2, true, 8> : search_kernel<M_L2, false, 8>;
-#else
 	if (tpr != 4) return nullptr;
-#endif
 	switch (metric)
 	{
 		case DIST_L2: return coop ? search_kernel<M_L2, true> : search_kernel<M_L2, false>;
@@ -615,10 +563,13 @@ static uint32_t visited_hash_entries(const pgemb_index *idx, uint32_t ef)
 	return h;
 }
 
-static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t ef, uint32_t vh)
+// vhs: entries of the latency mode's shared-memory visited set (0 = none).  Both hash sets are reset -- and migrated to the
+// bitmap -- from the slot's log, so the log must hold half a table (the kernel migrates before a table passes half full).
+static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t ef, uint32_t vh, uint32_t vhs)
 {
 	const uint32_t vis_words = (uint32_t) ((idx->capacity + 31) / 32);
-	if (idx->ws_slots < slots || idx->vis_words != vis_words || idx->ws_vh < vh)
+	const uint32_t min_log = (vh > vhs ? vh : vhs) / 2;
+	if (idx->ws_slots < slots || idx->vis_words != vis_words || idx->ws_vh < vh || idx->vlog_cap < min_log)
 	{
 		cudaFree(idx->d_visited);
 		cudaFree(idx->d_vlog);
@@ -631,6 +582,7 @@ static pgemb_status ensure_workspace(pgemb_index *idx, uint32_t slots, uint32_t 
 		idx->ws_slots = 0;
 		idx->vlog_cap = (uint32_t) (idx->capacity < 32768 ? idx->capacity : 32768);
 		if (idx->vlog_cap < vh / 2) idx->vlog_cap = vh / 2;
+		if (idx->vlog_cap < min_log) idx->vlog_cap = min_log;
 		CU_TRY(cudaMalloc((void **) &idx->d_visited, (size_t) slots * vis_words * 4));
 		CU_TRY(cudaMemset(idx->d_visited, 0, (size_t) slots * vis_words * 4));
 		CU_TRY(cudaMalloc((void **) &idx->d_vlog, (size_t) slots * idx->vlog_cap * 4));
@@ -662,36 +614,70 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 						   uint32_t exp_cap = 0, uint32_t *d_exp_n = nullptr)
 {
 	if (!idx || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
-	if (ef < 1 || ef > (1u << 20)) return fail(PGEMB_ERR_ARG, "ef out of range");
+	if (ef < 1 || ef > (1u << 27)) return fail(PGEMB_ERR_ARG, "ef out of range");
 	if (nq == 0) return PGEMB_OK;
 	if (nq >= (1ull << 31)) return fail(PGEMB_ERR_ARG, "too many queries in one batch");
 	pgemb_status st = set_device(idx);
 	if (st) return st;
 	// fewer queries than SMs: latency mode, a whole CTA cooperates on each query (search_kernel.cuh, COOP)
-	const bool	 coop = nq <= (size_t) idx->sm_count && env_int("PGEMB_COOP", 1) != 0;
+	bool		 coop = nq <= (size_t) idx->sm_count && env_int("PGEMB_COOP", 1) != 0;
 	SearchConfig cfg;
-	st = make_config(idx, (uint32_t) ef, &cfg, coop);
+	bool		 res_global = env_int("PGEMB_RES_GLOBAL", 0) != 0;
+	if (res_global) coop = false;
+	st = make_config(idx, (uint32_t) ef, &cfg, coop, res_global);
+	if (st == PGEMB_ERR_CAPACITY && !res_global)
+	{
+		// 2 x ef result keys no longer fit a CTA's shared memory: the traversal variant that keeps them in global memory
+		// (throughput-mode kernel, 4 lanes per row) -- slower per hop, but efSearch doubling must not fail (embedding.c:334)
+		res_global = true;
+		coop = false;
+		st = make_config(idx, (uint32_t) ef, &cfg, false, true);
+	}
 	if (st) return st;
-	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, coop, cfg.tpr);
+	if (res_global)
+	{
+		// per-slot global state is O(ef): cap the slots so that the workspace stays within ~4 GB
+		const uint64_t per_slot = (uint64_t) ef * 24u + (uint64_t) visited_hash_entries(idx, (uint32_t) ef) * 4u + ((uint64_t) idx->capacity + 31) / 32 * 4u;
+		uint64_t	   max_slots = ((uint64_t) 4 << 30) / (per_slot ? per_slot : 1);
+		if (max_slots < 1) max_slots = 1;
+		const uint64_t ctas = nq < (size_t) idx->sm_count ? nq : (size_t) idx->sm_count;
+		uint32_t	   w = (uint32_t) (max_slots / (ctas ? ctas : 1));
+		if (w < 1) w = 1;
+		if (w < cfg.warps) cfg.warps = w;
+		cfg.slots = cfg.warps * (uint32_t) idx->sm_count;
+	}
+	search_fn_t fn = pick_search_kernel((int) idx->meta.dist_func, coop, cfg.tpr, res_global);
 	if (!fn) return fail(PGEMB_ERR_ARG, "no kernel for this metric");
-#ifdef PGEMB_PROTO
-	const bool fast_small = env_int("PGEMB_FAST_SMALL", 0) != 0;
+	const bool fast_small = env_int("PGEMB_FAST_SMALL", 1) != 0;
 	if (!(fast_small && idx->last_fn == (const void *) fn && idx->last_smem == cfg.smem))
-#endif
 	{
 		CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.smem));
 		int occ = 0;
 		CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, (int) cfg.warps * 32, cfg.smem));
 		if (occ < 1) return fail(PGEMB_ERR_CAPACITY, "search kernel cannot be resident (shared memory / registers)");
-#ifdef PGEMB_PROTO
 		idx->last_fn = (const void *) fn;
 		idx->last_smem = cfg.smem;
-#endif
 	}
 	const uint32_t slots = cfg.slots;
 	const uint32_t vh = visited_hash_entries(idx, (uint32_t) ef);
-	st = ensure_workspace(idx, slots, (uint32_t) ef, vh);
+	st = ensure_workspace(idx, slots, (uint32_t) ef, vh, cfg.vhs_entries);
 	if (st) return st;
+	if (res_global)
+	{
+		const size_t keys = (size_t) slots * 2 * ef;
+		if (idx->resg_keys < keys)
+		{
+			cudaFree(idx->d_resg);
+			idx->d_resg = nullptr;
+			idx->resg_keys = 0;
+			if (cudaMalloc((void **) &idx->d_resg, keys * 8) != cudaSuccess)
+			{
+				cudaGetLastError();
+				return fail(PGEMB_ERR_NOMEM, "out of device memory for the result queues of this efSearch");
+			}
+			idx->resg_keys = keys;
+		}
+	}
 
 	SearchParams p;
 	memset(&p, 0, sizeof(p));
@@ -719,6 +705,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.visited = idx->d_visited;
 	p.vlog = idx->d_vlog;
 	p.ovf = idx->d_ovf;
+	p.res_g = res_global ? idx->d_resg : nullptr;
 	p.vis_words = idx->vis_words;
 	p.vlog_cap = idx->vlog_cap;
 	p.vhash = idx->d_vhash;
@@ -736,11 +723,11 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.error_flag = idx->d_error;
 	apply_config(p, cfg, idx->row_f);
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
-#ifdef PGEMB_PROTO
-	// opt-in prototype: rows up to PGEMB_GATHER_LDGSTS_MAX_BYTES (default: all) are gathered with 16-byte asynchronous copies
-	p.gather_ldgsts = (env_int("PGEMB_GATHER_LDGSTS", 0) != 0 && idx->row_f * 4u <= (uint32_t) env_int("PGEMB_GATHER_LDGSTS_MAX_BYTES", 1 << 30)) ? 1u : 0u;
+	// latency mode: both 32-id halves of a link list are test-and-set concurrently (one round trip instead of two dependent
+	// ones) -- legal only when no list repeats an id, which holds for every list the bind kernels write and is checked once
+	// for lists that came from the caller.  (Throughput mode: measured slower, 0.82 vs 0.85 of the roofline -- not used there.)
 	p.visited_pairs = 0;
-	if (env_int("PGEMB_VISITED_PAIRS", 0) != 0)
+	if (coop && env_int("PGEMB_VISITED_PAIRS", 1) != 0)
 	{
 		if (!idx->links_checked)
 		{
@@ -757,7 +744,6 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		}
 		p.visited_pairs = idx->links_distinct ? 1u : 0u;
 	}
-#endif
 
 	if (vh && idx->l2_window_max > 0 && env_int("PGEMB_L2_PERSIST", 1))
 	{
@@ -771,20 +757,16 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 		av.accessPolicyWindow.hitRatio = 1.0f;
 		av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
 		av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-#ifdef PGEMB_PROTO
 		if (fast_small && idx->last_l2_base == (const void *) idx->d_vhash && idx->last_l2_bytes == bytes && idx->last_l2_stream == s)
 		{
 			// the stream already carries exactly this window
 		}
 		else
-#endif
 		{
 			if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
-#ifdef PGEMB_PROTO
 			idx->last_l2_base = idx->d_vhash;
 			idx->last_l2_bytes = bytes;
 			idx->last_l2_stream = s;
-#endif
 		}
 	}
 	CU_TRY(cudaMemsetAsync(idx->d_counter, 0, sizeof(unsigned int), s));
@@ -870,10 +852,9 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 	// waiting for data that was never queued.  Under such a tool (detected by its injection variable) the batch is
 	// simply copied before the launch: replayed kernels must not depend on a concurrent copy.
 	cudaStream_t s = idx->stream;
-#ifdef PGEMB_PROTO
-	if (env_int("PGEMB_FAST_SMALL", 0) != 0 && nq <= 64)
+	if (env_int("PGEMB_FAST_SMALL", 1) != 0 && nq <= 64)
 	{
-		// opt-in prototype: a handful of queries (the reference-shaped hnsw_search: one) are not worth the streaming protocol
+		// a handful of queries (the reference-shaped hnsw_search: one) are not worth the streaming protocol
 		// -- copy, launch, copy back on ONE stream, one synchronisation
 		CU_TRY(cudaMemcpyAsync(d_q, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, s));
 		st = launch_search(idx, nq, d_q, (uint32_t) dim, nullptr, (uint32_t) idx->n, ef, 0, labels_out ? d_l : nullptr, dists_out ? d_d : nullptr,
@@ -890,7 +871,6 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 		if (stats_out) CU_TRY(cudaMemcpyAsync(stats_out, d_s, sb, cudaMemcpyDeviceToHost, s));
 		return check_device_error(idx, s);
 	}
-#endif
 	if (!idx->s_in)
 	{
 		CU_TRY(cudaStreamCreateWithFlags(&idx->s_in, cudaStreamNonBlocking));
@@ -944,6 +924,16 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 	if (stats_out) CU_TRY(cudaMemcpyAsync(stats_out, d_s, sb, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaStreamSynchronize(idx->s_in));
 	return check_device_error(idx, s);
+}
+
+// The device-pointer entry points are asynchronous and do not read the kernel's sticky error flag; a caller that wants to know
+// (corrupt graph, tie-overflow, a batch that never arrived) polls it here -- synchronises `stream`, returns and clears the flag.
+extern "C" pgemb_status pgemb_index_poll_error(pgemb_index *idx, void *stream)
+{
+	if (!idx) return fail(PGEMB_ERR_ARG, "null index");
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	return check_device_error(idx, (cudaStream_t) stream);
 }
 
 extern "C" float pgemb_last_kernel_ms(const pgemb_index *idx)
@@ -1039,163 +1029,294 @@ extern "C" pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coo
 	return PGEMB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// exact scan: the brute-force operator path (embedding.c:1022-1062)
+// ------------------------------------------------------------------------------------------------
+// counters of the scan paths since load: [0] scans through the tensor-core filter, [1] (query,row) pairs it covered,
+// [2] candidates re-scored exactly, [3] scans repeated on the exact kernels because the error-bound tripwire fired,
+// [4] queries whose candidate list overflowed (re-scored against the whole chunk), [5] scans on the exact kernels only
+static std::atomic<uint64_t> g_scan_tc{0}, g_scan_pairs{0}, g_scan_rescored{0}, g_scan_fallbacks{0}, g_scan_overflow{0}, g_scan_exact{0};
+extern "C" void pgemb_scan_counters(uint64_t out[6])
+{
+	out[0] = g_scan_tc.load();
+	out[1] = g_scan_pairs.load();
+	out[2] = g_scan_rescored.load();
+	out[3] = g_scan_fallbacks.load();
+	out[4] = g_scan_overflow.load();
+	out[5] = g_scan_exact.load();
+}
+
+// TF32 error bound of the filter, relative to |q||v|: both operands cut to 10 mantissa bits (2^-10 each, truncation or
+// rounding), fp32 accumulation of `dim` products in the tensor core (2^-21 per term is generous), 50 % slack on top.
+// PGEMB_SCAN_TC_REL_PPM overrides (parts per million).
+static float scan_tc_rel(size_t dim)
+{
+	float	  rel = 1.5f * (2.0f / 1024.0f + (float) dim / 2097152.0f);
+	const int ppm = env_int("PGEMB_SCAN_TC_REL_PPM", 0);
+	if (ppm > 0) rel = (float) ppm * 1e-6f;
+	return rel;
+}
+
+// squared norms of rows [norms_n, n) (cosine has them from the append; L2 computes them on the first tensor-core scan)
+static pgemb_status ensure_row_norms(pgemb_index *idx, cudaStream_t s)
+{
+	if (idx->norms_n >= idx->n) return PGEMB_OK;
+	const size_t first = idx->norms_n, n = idx->n - first;
+	PGEMB_LAUNCH(norms_kernel, (uint32_t) ((n * 4 + 127) / 128), 128, 0, s, idx->d_vectors, idx->row_f, (uint32_t) idx->meta.dim, (uint32_t) first, (uint32_t) n,
+				 idx->d_norms);
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	idx->norms_n = idx->n;
+	return PGEMB_OK;
+}
+
+#ifndef PGEMB_HOST_EMULATION
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time dependency on libcuda
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+								   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder()
+{
+	static tmap_encode_fn fn = nullptr;
+	static bool			  tried = false;
+	if (tried) return fn;
+	tried = true;
+	void						   *p = nullptr;
+	cudaDriverEntryPointQueryResult qr;
+	if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (tmap_encode_fn) p;
+	else cudaGetLastError();
+	return fn;
+}
+// [rows][row_f] fp32, K-major boxes of 32 floats x box_rows rows, 128-byte swizzle, out-of-range elements read as zero
+static pgemb_status make_tmap(CUtensorMap *m, const float *base, uint32_t row_f, size_t rows, uint32_t box_rows)
+{
+	tmap_encode_fn enc = tmap_encoder();
+	if (!enc) return fail(PGEMB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+	const cuuint64_t gdim[2] = {(cuuint64_t) row_f, (cuuint64_t) rows};
+	const cuuint64_t gstr[1] = {(cuuint64_t) row_f * 4};
+	const cuuint32_t box[2] = {kUmmaBK, box_rows};
+	const cuuint32_t estr[2] = {1, 1};
+	const CUresult	 r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+							 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) return fail(PGEMB_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int) r) + ")");
+	return PGEMB_OK;
+}
+#endif
+
+// one launch of the tensor-core filter over rows [r0, r0 + nr) for the nq staged queries (d_q: [nq][row_f], zero padded)
+static pgemb_status launch_scan_filter(pgemb_index *idx, int metric, const float *d_q, const float *d_qn, uint32_t nq, uint32_t r0, uint32_t nr, float rel,
+									   const float2 *d_qconst, uint32_t *d_cand_rows, float *d_cand_s, uint32_t *d_cand_n, uint32_t cap, float *d_dbg,
+									   cudaStream_t s)
+{
+	ScanFilterParams p;
+	memset(&p, 0, sizeof(p));
+	p.nq = nq;
+	p.r0 = r0;
+	p.nr = nr;
+	p.kblocks = (idx->row_f + kUmmaBK - 1) / kUmmaBK;
+	p.n_qtiles = (nq + kUmmaTQ - 1) / kUmmaTQ;
+	p.n_rtiles = (nr + kUmmaTR - 1) / kUmmaTR;
+	p.qconst = d_qconst;
+	p.vnorm2 = idx->d_norms;
+	p.cand_rows = d_cand_rows;
+	p.cand_s = d_cand_s;
+	p.cand_n = d_cand_n;
+	p.cap = cap;
+	p.dbg_s = d_dbg;
+#ifdef PGEMB_HOST_EMULATION
+	(void) s;
+	(void) d_qn;
+	if (metric == DIST_L2) scan_filter_emulated<M_L2>(d_q, idx->row_f, idx->d_vectors, idx->row_f, (uint32_t) idx->meta.dim, rel, d_qn, p);
+	else scan_filter_emulated<M_COS>(d_q, idx->row_f, idx->d_vectors, idx->row_f, (uint32_t) idx->meta.dim, rel, d_qn, p);
+	g_launches++;
+#else
+	(void) rel;
+	(void) d_qn;
+	CUtensorMap	 tq, tv;
+	pgemb_status st = make_tmap(&tq, d_q, idx->row_f, nq, kUmmaTQ);
+	if (st) return st;
+	st = make_tmap(&tv, idx->d_vectors, idx->row_f, idx->n, kUmmaTR);
+	if (st) return st;
+	const uint32_t tiles = p.n_qtiles * p.n_rtiles;
+	const uint32_t grid = tiles < (uint32_t) idx->sm_count ? tiles : (uint32_t) idx->sm_count;
+	if (metric == DIST_L2)
+	{
+		CU_TRY(cudaFuncSetAttribute(scan_filter_umma_kernel<M_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kUmmaSmem));
+		scan_filter_umma_kernel<M_L2><<<grid, kUmmaThreads, kUmmaSmem, s>>>(tq, tv, p);
+	}
+	else
+	{
+		CU_TRY(cudaFuncSetAttribute(scan_filter_umma_kernel<M_COS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kUmmaSmem));
+		scan_filter_umma_kernel<M_COS><<<grid, kUmmaThreads, kUmmaSmem, s>>>(tq, tv, p);
+	}
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+#endif
+	return PGEMB_OK;
+}
+
 static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
 								   int32_t *n_out, bool allow_tc, bool *tc_violation);
 
 extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
 										int32_t *n_out)
 {
-	bool		 viol = false;
-	pgemb_status st = scan_topk_impl(idx, nq, queries, k, labels_out, dists_out, n_out, true, &viol);
-#ifdef PGEMB_PROTO
-	if (st == PGEMB_OK && viol)
+	if (!idx || ((!queries || !labels_out || !n_out) && nq)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (nq == 0) return PGEMB_OK;
+	if (k < 1 || k > 4096) return fail(PGEMB_ERR_ARG, "k out of range (1..4096)");
+	if (nq > (1u << 20)) return fail(PGEMB_ERR_ARG, "too many queries in one scan batch");
+	// query groups: the candidate lists of the tensor-core path are sized per group
+	const size_t group = 4096;
+	for (size_t q0 = 0; q0 < nq; q0 += group)
 	{
-		// the tensor-core filter saw an approximation outside its assumed error bound: its result is not trusted
-		g_tc_fallbacks++;
-		fprintf(stderr, "pgemb_scan_topk: PGEMB_SCAN_TC error bound exceeded, repeating the scan on the exact path\n");
-		st = scan_topk_impl(idx, nq, queries, k, labels_out, dists_out, n_out, false, &viol);
+		const size_t gq = nq - q0 < group ? nq - q0 : group;
+		bool		 viol = false;
+		pgemb_status st = scan_topk_impl(idx, gq, queries + q0 * idx->meta.dim, k, labels_out + q0 * k, dists_out ? dists_out + q0 * k : nullptr, n_out + q0,
+										 true, &viol);
+		if (st == PGEMB_OK && viol)
+		{
+			// the tensor-core filter saw a product outside its assumed error bound: its result is not trusted
+			g_scan_fallbacks++;
+			fprintf(stderr, "pgemb_scan_topk: tensor-core error bound exceeded, repeating the scan on the exact kernels\n");
+			st = scan_topk_impl(idx, gq, queries + q0 * idx->meta.dim, k, labels_out + q0 * k, dists_out ? dists_out + q0 * k : nullptr, n_out + q0, false, &viol);
+		}
+		if (st) return st;
 	}
-#endif
-	return st;
+	return PGEMB_OK;
+}
+
+// PGEMB_SCAN_TC: 0 = exact kernels only, 1 (default) = tensor-core filter for L2 / cosine when the table has at least
+// PGEMB_SCAN_TC_MIN_ROWS (default 4096) rows, 2 = always (tests).
+static bool scan_use_tc(const pgemb_index *idx, bool allow_tc)
+{
+	if (!allow_tc || idx->meta.dist_func == DIST_MANHATTAN) return false;
+	const int mode = env_int("PGEMB_SCAN_TC", 1);
+	if (mode <= 0) return false;
+	if (mode >= 2) return true;
+	return idx->n >= (size_t) env_int("PGEMB_SCAN_TC_MIN_ROWS", 4096);
 }
 
 static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
 								   int32_t *n_out, bool allow_tc, bool *tc_violation)
 {
-	(void) allow_tc;
 	*tc_violation = false;
-	if (!idx || ((!queries || !labels_out || !n_out) && nq)) return fail(PGEMB_ERR_ARG, "null argument");
-	if (nq == 0) return PGEMB_OK;
-	if (k < 1 || k > 4096) return fail(PGEMB_ERR_ARG, "k out of range (1..4096)");
-	if (nq > (1u << 20)) return fail(PGEMB_ERR_ARG, "too many queries in one scan batch");
 	pgemb_status st = set_device(idx);
 	if (st) return st;
 	const size_t dim = idx->meta.dim;
 	const size_t N = idx->n;
+	const size_t rf = idx->row_f;
 	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-	size_t		 chunk = (size_t) 1 << 14;
-#ifdef PGEMB_PROTO
-	// the tensor-core filter launches a GEMM + a select kernel per chunk: fewer, larger chunks (PGEMB_SCAN_CHUNK_LOG2 overrides)
-	if (allow_tc && env_int("PGEMB_SCAN_TC", 0) != 0) chunk = (size_t) 1 << 16;
+	const bool	 tc = scan_use_tc(idx, allow_tc);
+	const int	 metric = (int) idx->meta.dist_func;
+	cudaStream_t s = idx->stream;
+	// ---- staging ------------------------------------------------------------------------------------------------
+	size_t chunk = (size_t) 1 << 14;  // exact path: rows per distance / select launch pair
 	{
 		const int lg = env_int("PGEMB_SCAN_CHUNK_LOG2", 0);
 		if (lg >= 8 && lg <= 20) chunk = (size_t) 1 << lg;
 	}
-#endif
 	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
-	const size_t qb = nq * dim * 4, db = nq * chunk * 4, kd = nq * k * 4, kl = nq * k * 8, nb = nq * 4;
-	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + 2 * up(nb) + up(chunk * 4) + 256);
+	// tensor-core path: first chunk establishes the threshold (every row of it is a candidate), then x8 per chunk
+	size_t c0 = ((2 * k > 256 ? 2 * k : 256) + 255) / 256 * 256;
+	{
+		const int lg = env_int("PGEMB_SCAN_TC_CHUNK0_LOG2", 0);
+		if (lg >= 5 && lg <= 20) c0 = (size_t) 1 << lg;
+	}
+	size_t cap = 2 * c0 > 4096 ? 2 * c0 : 4096;
+	{
+		const int v = env_int("PGEMB_SCAN_TC_CAP", 0);
+		if (v > 0) cap = (size_t) v;
+	}
+	const size_t qb = nq * rf * 4, db = tc ? 0 : nq * chunk * 4, kd = nq * k * 4, kl = nq * k * 8, nb = nq * 4;
+	const size_t cb = tc ? nq * cap * 4 : 0;
+	st = ensure_stage(idx, up(qb) + up(db) + 2 * up(kd) + 2 * up(kl) + 3 * up(nb) + up(nq * 8) + 2 * up(cb) + 512);
 	if (st) return st;
 	char	 *base = (char *) idx->d_stage;
-	float	 *d_q = (float *) base;			base += up(qb);
+	float	 *d_q = (float *) base;			base += up(qb);		// [nq][row_f], zero padded (the TMA tensor map reads whole 16-byte units)
 	float	 *d_dist = (float *) base;		base += up(db);
 	uint32_t *d_td = (uint32_t *) base;		base += up(kd);
 	uint32_t *d_sd = (uint32_t *) base;		base += up(kd);
 	uint64_t *d_tl = (uint64_t *) base;		base += up(kl);
 	uint64_t *d_sl = (uint64_t *) base;		base += up(kl);
-	uint32_t *d_tn = (uint32_t *) base;			base += up(nb);
-	float	 *d_qn = (float *) base;			base += up(nb);
-	float	 *d_vn = (float *) base;			base += up(chunk * 4);	// PGEMB_SCAN_TC, L2: squared norms of the chunk's rows
-	uint32_t *d_tcflags = (uint32_t *) base;	// [0] rows re-scored, [1] error-bound violation
-	(void) d_vn;
-	(void) d_tcflags;
-	cudaStream_t s = idx->stream;
-	CU_TRY(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, s));
+	uint32_t *d_tn = (uint32_t *) base;		base += up(nb);
+	float	 *d_qn = (float *) base;		base += up(nb);
+	uint32_t *d_cn = (uint32_t *) base;		base += up(nb);		// candidate counts
+	float2	 *d_qc = (float2 *) base;		base += up(nq * 8);	// filter constants
+	uint32_t *d_cr = (uint32_t *) base;		base += up(cb);		// candidate rows
+	float	 *d_cs = (float *) base;		base += up(cb);		// candidate products
+	uint32_t *d_cnt = (uint32_t *) base;						// [0] re-scored, [1] tripwire, [2] overflowed queries
+	if (rf != dim) CU_TRY(cudaMemsetAsync(d_q, 0, qb, s));
+	CU_TRY(cudaMemcpy2DAsync(d_q, rf * 4, queries, dim * 4, dim * 4, nq, cudaMemcpyHostToDevice, s));
 	CU_TRY(cudaMemsetAsync(d_tn, 0, nb, s));
-	const int	   metric = (int) idx->meta.dist_func;
-	const uint32_t lanes = (metric == DIST_L2) ? 8 : 4;
-	// tiled distance step (scan_tile_kernel.cuh): same bits, rows read once per query tile.  Opt-in until measured.
-#ifdef PGEMB_PROTO
-	const bool tiled = env_int("PGEMB_SCAN_TILED", 0) != 0;
-#else
-	const bool tiled = false;
-#endif
-#ifdef PGEMB_PROTO
-	// tensor-core filter (scan_tc_kernel.cuh): one TF32 GEMM per chunk discards rows, survivors are re-scored exactly
-	const bool tc = allow_tc && env_int("PGEMB_SCAN_TC", 0) != 0 && metric != DIST_MANHATTAN;
-	float	   tc_rel = 0.f;
-	if (tc)
-	{
-		CublasApi &cb = cublas_api();
-		if (!cb.ok) return fail(PGEMB_ERR_CUDA, "PGEMB_SCAN_TC=1 but libcublas could not be loaded (PGEMB_CUBLAS_PATH)");
-		if (!idx->cublas && cb.create(&idx->cublas) != CUBLAS_STATUS_SUCCESS)
-		{
-			idx->cublas = nullptr;
-			return fail(PGEMB_ERR_CUDA, "cublasCreate failed");
-		}
-		if (cb.set_stream(idx->cublas, s) != CUBLAS_STATUS_SUCCESS) return fail(PGEMB_ERR_CUDA, "cublasSetStream failed");
-		// TF32: both operands cut to 10 mantissa bits (2 * 2^-10 relative per product), fp32 accumulation over dim terms
-		// (dim * 2^-23), 50 % slack; PGEMB_SCAN_TC_REL_PPM overrides (parts per million)
-		tc_rel = 1.5f * (2.0f / 1024.0f + (float) dim / 8388608.0f);
-		const int ppm = env_int("PGEMB_SCAN_TC_REL_PPM", 0);
-		if (ppm > 0) tc_rel = (float) ppm * 1e-6f;
-		CU_TRY(cudaMemsetAsync(d_tcflags, 0, 8, s));
-		g_tc_scans++;
-		g_tc_pairs += (uint64_t) nq * N;
-	}
+	// tiled distance step (scan_tile_kernel.cuh): same bits as scan_dist_kernel, rows read once per query tile
+	const bool tiled = env_int("PGEMB_SCAN_TILED", 1) != 0;
 	if (tc || (tiled && metric == DIST_COSINE))
-#else
-	if (tiled && metric == DIST_COSINE)
-#endif
 	{
-		PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nq * 4 + 127) / 128), 128, 0, s, d_q, (uint32_t) dim, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
+		PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nq * 4 + 127) / 128), 128, 0, s, d_q, (uint32_t) rf, (uint32_t) dim, 0u, (uint32_t) nq, d_qn);
 		g_launches++;
 		CU_TRY(cudaGetLastError());
 	}
-	for (size_t r0 = 0; r0 < N; r0 += chunk)
+	if (tc)
 	{
-		const size_t   nr = (N - r0 < chunk) ? (N - r0) : chunk;
-		const uint32_t threads = 128;
-		const uint32_t blocks = (uint32_t) ((nq * nr * lanes + threads - 1) / threads);
+		// ---- K6: tensor-core filter + exact re-scoring, geometric chunks -----------------------------------------------
+		st = ensure_row_norms(idx, s);
+		if (st) return st;
+		const float rel = scan_tc_rel(dim);
+		CU_TRY(cudaMemsetAsync(d_cnt, 0, 16, s));
+		if (metric == DIST_L2) PGEMB_LAUNCH(scan_qconst_init_kernel<M_L2>, (uint32_t) ((nq + 127) / 128), 128, 0, s, d_qn, (uint32_t) nq, rel, d_qc, d_cn);
+		else PGEMB_LAUNCH(scan_qconst_init_kernel<M_COS>, (uint32_t) ((nq + 127) / 128), 128, 0, s, d_qn, (uint32_t) nq, rel, d_qc, d_cn);
+		g_launches++;
+		size_t csize = c0;
+		for (size_t r0 = 0; r0 < N;)
+		{
+			size_t nr = N - r0 < csize ? N - r0 : csize;
+			if (N - r0 - nr < nr / 8) nr = N - r0;	// do not leave a sliver for an extra launch pair
+			st = launch_scan_filter(idx, metric, d_q, d_qn, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, rel, d_qc, d_cr, d_cs, d_cn, (uint32_t) cap, nullptr, s);
+			if (st) return st;
+#define SCAN_RESCORE(MM)                                                                                                                          \
+	PGEMB_LAUNCH(scan_rescore_kernel<MM>, (uint32_t) ((nq + 3) / 4), 128, 0, s, idx->d_vectors, idx->row_f, (uint32_t) dim, idx->d_norms, d_q, (uint32_t) rf, d_qn,  \
+				 idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k, rel, d_cr, d_cs, d_cn, (uint32_t) cap, d_td, d_tl, d_tn, d_sd, d_sl, d_qc, d_cnt)
+			if (metric == DIST_L2) SCAN_RESCORE(M_L2);
+			else SCAN_RESCORE(M_COS);
+#undef SCAN_RESCORE
+			g_launches++;
+			CU_TRY(cudaGetLastError());
+			r0 += nr;
+			csize *= 8;
+		}
+		g_scan_tc++;
+		g_scan_pairs += (uint64_t) nq * N;
+	}
+	else
+	{
+		g_scan_exact++;
+		const uint32_t lanes = (metric == DIST_L2) ? 8 : 4;
+		for (size_t r0 = 0; r0 < N; r0 += chunk)
+		{
+			const size_t   nr = (N - r0 < chunk) ? (N - r0) : chunk;
+			const uint32_t threads = 128;
+			const uint32_t blocks = (uint32_t) ((nq * nr * lanes + threads - 1) / threads);
 #define SCAN_DIST(MM)                                                                                                              \
-	PGEMB_LAUNCH(scan_dist_kernel<MM>, blocks, threads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, \
+	PGEMB_LAUNCH(scan_dist_kernel<MM>, blocks, threads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) rf, \
 													(uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
 #define SCAN_TILE(MM)                                                                                                              \
-	PGEMB_LAUNCH(scan_tile_kernel<MM>, dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), kScanThreads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) dim, d_qn,  \
+	PGEMB_LAUNCH(scan_tile_kernel<MM>, dim3((uint32_t) ((nq + ScanTile<MM>::TQ - 1) / ScanTile<MM>::TQ), (uint32_t) ((nr + kScanTileRows - 1) / kScanTileRows)), kScanThreads, 0, s, idx->d_vectors, idx->d_norms, idx->row_f, (uint32_t) dim, d_q, (uint32_t) rf, d_qn,  \
 												 (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, d_dist)
-#ifdef PGEMB_PROTO
-		if (tc)
-		{
-			const float one = 1.0f, zero = 0.0f;
-			// row-major S[nq][nr] = column-major (nr x nq): S^T = V_chunk (nr x dim) . Q^T (dim x nq)
-			if (cublas_api().gemm_ex(idx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, (int) nr, (int) nq, (int) dim, &one, idx->d_vectors + r0 * idx->row_f, CUDA_R_32F,
-									 (int) idx->row_f, d_q, CUDA_R_32F, (int) dim, &zero, d_dist, CUDA_R_32F, (int) nr, CUBLAS_COMPUTE_32F_FAST_TF32,
-									 CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
-				return fail(PGEMB_ERR_CUDA, "cublasGemmEx failed");
-			const float *vn = idx->d_norms + r0;
-			if (metric == DIST_L2)
+			if (tiled)
 			{
-				PGEMB_LAUNCH(norms_kernel, (uint32_t) ((nr * 4 + 127) / 128), 128, 0, s, idx->d_vectors + r0 * idx->row_f, idx->row_f, (uint32_t) dim, 0u, (uint32_t) nr, d_vn);
-				g_launches++;
-				vn = d_vn;
+				if (metric == DIST_L2) SCAN_TILE(M_L2);
+				else if (metric == DIST_COSINE) SCAN_TILE(M_COS);
+				else SCAN_TILE(M_MAN);
 			}
-#define SCAN_TC(MM)                                                                                                                \
-	PGEMB_LAUNCH(scan_select_tc_kernel<MM>, (uint32_t) ((nq + 3) / 4), 128, 0, s, d_dist, idx->d_vectors, idx->row_f, (uint32_t) dim, vn, d_q, (uint32_t) dim, d_qn, \
-				 idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k, tc_rel, d_td, d_tl, d_tn, d_sd, d_sl, d_tcflags, (int *) (d_tcflags + 1))
-			if (metric == DIST_L2) SCAN_TC(M_L2);
-			else SCAN_TC(M_COS);
-#undef SCAN_TC
-			g_launches += 2;  // the GEMM (library kernel) + the filter/select kernel
-			CU_TRY(cudaGetLastError());
-			continue;
-		}
-		if (tiled)
-		{
-			if (metric == DIST_L2) SCAN_TILE(M_L2);
-			else if (metric == DIST_COSINE) SCAN_TILE(M_COS);
-			else SCAN_TILE(M_MAN);
-		}
-		else
-#endif
-		if (metric == DIST_L2) SCAN_DIST(M_L2);
-		else if (metric == DIST_COSINE) SCAN_DIST(M_COS);
-		else SCAN_DIST(M_MAN);
+			else if (metric == DIST_L2) SCAN_DIST(M_L2);
+			else if (metric == DIST_COSINE) SCAN_DIST(M_COS);
+			else SCAN_DIST(M_MAN);
 #undef SCAN_TILE
 #undef SCAN_DIST
-		PGEMB_LAUNCH(scan_select_kernel, (uint32_t) ((nq + 3) / 4), 128, 0, s, d_dist, idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k,
-																	 d_td, d_tl, d_tn, d_sd, d_sl);
-		g_launches += 2;
-		CU_TRY(cudaGetLastError());
+			PGEMB_LAUNCH(scan_select_kernel, (uint32_t) ((nq + 3) / 4), 128, 0, s, d_dist, idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k,
+																		 d_td, d_tl, d_tn, d_sd, d_sl);
+			g_launches += 2;
+			CU_TRY(cudaGetLastError());
+		}
 	}
 	std::vector<uint32_t> hd, hn;
 	try
@@ -1211,18 +1332,15 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 	CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
-#ifdef PGEMB_PROTO
-	uint32_t tcf[2] = {0, 0};
-	if (tc) CU_TRY(cudaMemcpyAsync(tcf, d_tcflags, 8, cudaMemcpyDeviceToHost, s));
-#endif
+	uint32_t cnt[4] = {0, 0, 0, 0};
+	if (tc) CU_TRY(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaStreamSynchronize(s));
-#ifdef PGEMB_PROTO
 	if (tc)
 	{
-		g_tc_rescored += tcf[0];
-		if (tcf[1]) *tc_violation = true;
+		g_scan_rescored += cnt[0];
+		g_scan_overflow += cnt[2];
+		if (cnt[1]) *tc_violation = true;
 	}
-#endif
 	for (size_t q = 0; q < nq; q++)
 	{
 		n_out[q] = (int32_t) hn[q];
@@ -1233,6 +1351,40 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 			if (dists_out) dists_out[q * k + i] = ok ? o2f(hd[q * k + i]) : INFINITY;
 		}
 	}
+	return PGEMB_OK;
+}
+
+// Debug / test entry: the raw tensor-core products S[q][j] = q . row(r0 + j) of the K6 kernel (TF32 operands, fp32
+// accumulate), so that a test can check the UMMA descriptors, the swizzled TMA tiles and the TMEM read-back against a
+// float64 product directly.  Host pointers; out[nq * nr].
+extern "C" pgemb_status pgemb_debug_umma_product(pgemb_index *idx, size_t nq, const coord_t *queries, size_t r0, size_t nr, float *out)
+{
+	if (!idx || ((!queries || !out) && nq && nr)) return fail(PGEMB_ERR_ARG, "null argument");
+	if (nq == 0 || nr == 0) return PGEMB_OK;
+	if (r0 + nr > idx->n) return fail(PGEMB_ERR_ARG, "range beyond index size");
+	if (idx->meta.dist_func == DIST_MANHATTAN) return fail(PGEMB_ERR_ARG, "manhattan has no tensor-core path");
+	if (nq * nr > ((size_t) 1 << 28)) return fail(PGEMB_ERR_ARG, "debug product too large");
+	pgemb_status st = set_device(idx);
+	if (st) return st;
+	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+	const size_t rf = idx->row_f, dim = idx->meta.dim;
+	st = ensure_stage(idx, up(nq * rf * 4) + up(nq * 4) + up(nq * nr * 4) + 256);
+	if (st) return st;
+	cudaStream_t s = idx->stream;
+	char		*base = (char *) idx->d_stage;
+	float		*d_q = (float *) base;	base += up(nq * rf * 4);
+	float		*d_qn = (float *) base;	base += up(nq * 4);
+	float		*d_s = (float *) base;
+	CU_TRY(cudaMemsetAsync(d_q, 0, nq * rf * 4, s));
+	CU_TRY(cudaMemcpy2DAsync(d_q, rf * 4, queries, dim * 4, dim * 4, nq, cudaMemcpyHostToDevice, s));
+	CU_TRY(cudaMemsetAsync(d_s, 0, nq * nr * 4, s));
+	st = ensure_row_norms(idx, s);
+	if (st) return st;
+	st = launch_scan_filter(idx, (int) idx->meta.dist_func, d_q, d_qn, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, scan_tc_rel(dim), nullptr, nullptr, nullptr, nullptr,
+							0, d_s, s);
+	if (st) return st;
+	CU_TRY(cudaMemcpyAsync(out, d_s, nq * nr * 4, cudaMemcpyDeviceToHost, s));
+	CU_TRY(cudaStreamSynchronize(s));
 	return PGEMB_OK;
 }
 
@@ -1313,6 +1465,154 @@ extern "C" bool hnsw_bind_point(HnswMetadata *meta, const coord_t *point, idx_t 
 	}
 	return true;
 }
+
+// ------------------------------------------------------------------------------------------------
+// index-scan iteration: hnsw_beginscan / hnsw_gettuple / hnsw_endscan, embedding.c:249-387
+// ------------------------------------------------------------------------------------------------
+// The reference's scan keeps the TIDs returned so far, and when they run out while the last search was "full"
+// (n == efSearch) it doubles efSearch IN PLACE, searches again and appends the TIDs it has not returned yet
+// (embedding.c:329-366).  Restated statement by statement -- including the two quirks a caller can observe:
+//   * `if (n_results <= so->n_results) return false` compares the NEW search's count with the ACCUMULATED count (:338);
+//   * the de-duplication bsearch runs over so->n_results entries while so->n_results GROWS (:357-363): sorted prefix +
+//     unsorted suffix, so a probe can miss a TID that is in the prefix and the scan returns that tuple twice.  The probe
+//     sequence is glibc's bsearch (l = 0, u = n, idx = (l + u) / 2).
+// A TID is the label's low 6 bytes (memcpy of sizeof(ItemPointerData), :324/:361); ItemPointerCompare orders by block number
+// ((bi_hi << 16) | bi_lo), then ip_posid.  The checker's restatement of the same loop is oracle/scan_iter.c.
+struct pgemb_index_scan
+{
+	pgemb_index			 *idx = nullptr;
+	std::vector<float>	  key;
+	size_t				  ef = 0;		 // so->hnsw->meta.efSearch: per-scan copy (embedding.c:254), doubled in place
+	std::vector<uint64_t> results;		 // TIDs (flags stripped), in the order they are handed out
+	size_t				  curr = 0;
+	bool				  no_more = true;  // embedding.c:258
+	uint64_t			  searches = 0;
+};
+
+static inline int tid_compare(uint64_t a, uint64_t b)
+{
+	const uint32_t ba = (uint32_t) (((a & 0xffffu) << 16) | ((a >> 16) & 0xffffu)), bb = (uint32_t) (((b & 0xffffu) << 16) | ((b >> 16) & 0xffffu));
+	if (ba != bb) return ba < bb ? -1 : 1;
+	const uint32_t pa = (uint32_t) ((a >> 32) & 0xffffu), pb = (uint32_t) ((b >> 32) & 0xffffu);
+	if (pa != pb) return pa < pb ? -1 : 1;
+	return 0;
+}
+
+extern "C" pgemb_status pgemb_index_scan_begin(pgemb_index *idx, const coord_t *query, size_t efSearch, pgemb_index_scan **out)
+{
+	if (!idx || !query || !out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (efSearch < 1) return fail(PGEMB_ERR_ARG, "efsearch must be >= 1");
+	pgemb_index_scan *so = new (std::nothrow) pgemb_index_scan();
+	if (!so) return fail(PGEMB_ERR_NOMEM, "out of host memory");
+	try
+	{
+		so->key.assign(query, query + idx->meta.dim);
+	}
+	catch (const std::bad_alloc &)
+	{
+		delete so;
+		return fail(PGEMB_ERR_NOMEM, "out of host memory");
+	}
+	so->idx = idx;
+	so->ef = efSearch;
+	*out = so;
+	return PGEMB_OK;
+}
+
+// one hnsw_search with the scan's current efSearch; labels -> TIDs
+static pgemb_status scan_search(pgemb_index_scan *so, std::vector<uint64_t> &tids)
+{
+	std::vector<uint64_t> lab;
+	try
+	{
+		lab.resize(so->ef);
+	}
+	catch (const std::bad_alloc &)
+	{
+		return fail(PGEMB_ERR_NOMEM, "out of host memory");
+	}
+	int32_t		 n = 0;
+	pgemb_status st = pgemb_search_batch(so->idx, 1, so->key.data(), so->ef, lab.data(), nullptr, nullptr, &n, nullptr);
+	so->searches++;
+	if (st) return st;
+	tids.assign(lab.begin(), lab.begin() + n);
+	for (auto &t : tids) t &= 0xffffffffffffull;
+	return PGEMB_OK;
+}
+
+extern "C" int pgemb_index_scan_next(pgemb_index_scan *so, label_t *tid_out)
+{
+	if (!so || !tid_out)
+	{
+		fail(PGEMB_ERR_ARG, "null argument");
+		return -PGEMB_ERR_ARG;
+	}
+	try
+	{
+		std::vector<uint64_t> res;
+		if (so->curr == 0)
+		{
+			pgemb_status st = scan_search(so, res);
+			if (st) return -st;	 // "HNSW index search failed" (embedding.c:318)
+			so->results = res;
+			so->no_more = res.size() < so->ef;
+		}
+		if (so->curr >= so->results.size())
+		{
+			if (so->no_more) return 0;
+			if (so->ef > ((size_t) 1 << 40)) return 0;	// efSearch cannot overflow before every node has been returned
+			so->ef *= 2;  // embedding.c:334
+			pgemb_status st = scan_search(so, res);
+			if (st) return -st;
+			if (res.size() <= so->results.size()) return 0;	 // "No new results found"
+			so->no_more = res.size() < so->ef;
+			size_t n_results = so->results.size();
+			so->results.resize(n_results + res.size());
+			std::sort(so->results.begin(), so->results.begin() + n_results, [](uint64_t a, uint64_t b) { return tid_compare(a, b) < 0; });
+			for (uint64_t t : res)
+			{
+				size_t l = 0, u = n_results;
+				bool   found = false;
+				while (l < u)
+				{
+					const size_t i = (l + u) / 2;
+					const int	 c = tid_compare(t, so->results[i]);
+					if (c < 0) u = i;
+					else if (c > 0) l = i + 1;
+					else { found = true; break; }
+				}
+				if (!found) so->results[n_results++] = t;
+			}
+			so->results.resize(n_results);
+		}
+		*tid_out = so->results[so->curr++];
+		return 1;
+	}
+	catch (const std::bad_alloc &)
+	{
+		fail(PGEMB_ERR_NOMEM, "out of host memory");
+		return -PGEMB_ERR_NOMEM;
+	}
+}
+
+extern "C" pgemb_status pgemb_index_scan_next_batch(pgemb_index_scan *so, size_t max, label_t *tids_out, size_t *n_out)
+{
+	if (!so || (!tids_out && max) || !n_out) return fail(PGEMB_ERR_ARG, "null argument");
+	size_t n = 0;
+	while (n < max)
+	{
+		const int r = pgemb_index_scan_next(so, &tids_out[n]);
+		if (r < 0) return (pgemb_status) -r;
+		if (r == 0) break;
+		n++;
+	}
+	*n_out = n;
+	return PGEMB_OK;
+}
+
+extern "C" size_t pgemb_index_scan_ef(const pgemb_index_scan *so) { return so ? so->ef : 0; }
+extern "C" uint64_t pgemb_index_scan_searches(const pgemb_index_scan *so) { return so ? so->searches : 0; }
+extern "C" void pgemb_index_scan_end(pgemb_index_scan *so) { delete so; }
 
 // ------------------------------------------------------------------------------------------------
 // K4 driver: sequential binds (hnsw_bind_point semantics, hnswalg.cpp:225-232) without host round trips
@@ -1397,6 +1697,8 @@ static pgemb_status launch_connect(pgemb_index *idx, const uint32_t *d_new_ids, 
 	return PGEMB_OK;
 }
 
+__global__ void iota_kernel(uint32_t *out, uint32_t start, uint32_t n);
+
 pgemb_status bind_points(pgemb_index *idx, idx_t first, size_t n)
 {
 	if (n == 0) return PGEMB_OK;
@@ -1404,23 +1706,29 @@ pgemb_status bind_points(pgemb_index *idx, idx_t first, size_t n)
 	const size_t efc = idx->meta.efConstruction;
 	if (efc < 1) return fail(PGEMB_ERR_ARG, "efConstruction must be >= 1");
 	cudaStream_t s = idx->stream;
-	pgemb_status st = ensure_bind_ws(idx, n > 1 ? n : 1, efc);
+	// one bind at a time uses ONE slot of the bind workspace (candidates, pairs); only the ids are per point
+	pgemb_status st = ensure_bind_ws(idx, 1, efc);
 	if (st) return st;
 	BindWorkspace &w = idx->bind_ws;
+	if (idx->seq_ids_cap < n)
 	{
-		std::vector<uint32_t> ids(n);
-		for (size_t i = 0; i < n; i++) ids[i] = first + (uint32_t) i;
-		CU_TRY(cudaMemcpyAsync(w.d_qids, ids.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
-		CU_TRY(cudaStreamSynchronize(s));
+		cudaFree(idx->d_seq_ids);
+		idx->d_seq_ids = nullptr;
+		idx->seq_ids_cap = 0;
+		CU_TRY(cudaMalloc((void **) &idx->d_seq_ids, n * sizeof(uint32_t)));
+		idx->seq_ids_cap = n;
 	}
+	PGEMB_LAUNCH(iota_kernel, (uint32_t) ((n + 255) / 256), 256, 0, s, idx->d_seq_ids, (uint32_t) first, (uint32_t) n);
+	g_launches++;
+	CU_TRY(cudaGetLastError());
 	// strictly sequential: node i sees the links written for nodes < i (embedding.c:624-629 serialises writers)
 	for (size_t i = 0; i < n; i++)
 	{
 		if (first + i == 0) continue;  // hnswalg.cpp:227-228
-		st = launch_search(idx, 1, nullptr, 0, w.d_qids + i, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n,
+		st = launch_search(idx, 1, nullptr, 0, idx->d_seq_ids + i, (uint32_t) idx->n, efc, 1, nullptr, w.d_cand_d, w.d_cand_ids, w.d_cand_n,
 						   nullptr, s, false);
 		if (st) return st;
-		st = launch_connect(idx, w.d_qids + i, 1, efc, s);
+		st = launch_connect(idx, idx->d_seq_ids + i, 1, efc, s);
 		if (st) return st;
 	}
 	return PGEMB_OK;
@@ -1614,12 +1922,11 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 		// Speculative searches are nearly free (one launch, one warp each, latency-bound), so the batch only
 		// shrinks while the graph is tiny (every search expands most of it and everything conflicts).
 		B = (acc == B) ? B * 2 : (acc * 8 > batch_max ? batch_max : acc * 8 + 1);
-#ifdef PGEMB_PROTO
-		// opt-in prototype: a batch that would only slightly exceed one query per SM is cut to one query per SM, so that the
-		// speculative searches run in latency mode (a CTA per search: shorter round) -- the accepted prefix is far shorter than
-		// the batch anyway.  Same result by construction (any batch size gives the sequential graph).
-		if (env_int("PGEMB_EXACT_CLAMP_SMS", 0) != 0 && B > (size_t) idx->sm_count && B <= 3 * (size_t) idx->sm_count) B = (size_t) idx->sm_count;
-#endif
+		// a batch that would only slightly exceed one query per SM is cut to one query per SM, so that the speculative
+		// searches run in latency mode (a CTA per search: shorter round) -- the accepted prefix is far shorter than the
+		// batch anyway (measured: 209 -> 183 us per insert at N ~ 1M).  Same result by construction (any batch size gives
+		// the sequential graph).
+		if (env_int("PGEMB_EXACT_CLAMP_SMS", 1) != 0 && B > (size_t) idx->sm_count && B <= 3 * (size_t) idx->sm_count) B = (size_t) idx->sm_count;
 	}
 	CU_TRY(cudaEventRecord(e1, s));
 	st = check_device_error(idx, s);
@@ -1636,8 +1943,20 @@ extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t
 }
 
 // ------------------------------------------------------------------------------------------------
-// shard merge
+// shard merge (K5) and the peer-memory exchange
 // ------------------------------------------------------------------------------------------------
+static pgemb_status launch_merge(size_t nq, size_t n_shards, size_t k, const ShardLists &in, const uint32_t *d_flags, uint32_t seq, uint32_t self,
+								 dist_t *d_dists_out, label_t *d_labels_out, int32_t *d_n_out, int *d_error, cudaStream_t s)
+{
+	const uint32_t threads = 128;
+	const uint32_t blocks = (uint32_t) ((nq * 32 + threads - 1) / threads);
+	PGEMB_LAUNCH(merge_topk_lists_kernel, blocks, threads, 0, s, (uint32_t) nq, (uint32_t) n_shards, (uint32_t) k, in, d_flags, seq, self, d_dists_out,
+				 d_labels_out, d_n_out, d_error);
+	g_launches++;
+	CU_TRY(cudaGetLastError());
+	return PGEMB_OK;
+}
+
 extern "C" pgemb_status pgemb_merge_topk_device(size_t nq, size_t n_shards, size_t k, const dist_t *d_dists_in, const label_t *d_labels_in,
 												const int32_t *d_n_in, dist_t *d_dists_out, label_t *d_labels_out, int32_t *d_n_out,
 												void *stream)
@@ -1645,11 +1964,246 @@ extern "C" pgemb_status pgemb_merge_topk_device(size_t nq, size_t n_shards, size
 	if (nq == 0) return PGEMB_OK;
 	if (!d_dists_in || !d_labels_in || !d_n_in || !d_dists_out || !d_labels_out || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
 	if (n_shards == 0 || k == 0) return fail(PGEMB_ERR_ARG, "n_shards and k must be > 0");
-	const uint32_t threads = 128;
-	const uint32_t blocks = (uint32_t) ((nq * 32 + threads - 1) / threads);
-	PGEMB_LAUNCH(merge_topk_kernel, blocks, threads, 0, (cudaStream_t) stream, (uint32_t) nq, (uint32_t) n_shards, (uint32_t) k, d_dists_in,
-																	 d_labels_in, d_n_in, d_dists_out, d_labels_out, d_n_out);
-	g_launches++;
-	CU_TRY(cudaGetLastError());
+	if (n_shards > kMaxShards) return fail(PGEMB_ERR_ARG, "at most 16 shards");
+	ShardLists in;
+	memset(&in, 0, sizeof(in));
+	for (size_t s = 0; s < n_shards; s++)  // input layout: [shard][query][k]
+	{
+		in.dist[s] = d_dists_in + s * nq * k;
+		in.lab[s] = d_labels_in + s * nq * k;
+		in.cnt[s] = d_n_in + s * nq;
+	}
+	return launch_merge(nq, n_shards, k, in, nullptr, 0, 0, d_dists_out, d_labels_out, d_n_out, nullptr, (cudaStream_t) stream);
+}
+
+// One packed result buffer per rank: [labels u64 nq*k | dists f32 nq*k | counts i32 nq] -- what ONE all-gather moves.
+extern "C" size_t pgemb_packed_topk_bytes(size_t nq, size_t k) { return nq * k * 12 + nq * 4; }
+
+extern "C" pgemb_status pgemb_merge_topk_packed_device(size_t nq, size_t n_shards, size_t k, const void *d_packed, size_t shard_stride_bytes,
+													   dist_t *d_dists_out, label_t *d_labels_out, int32_t *d_n_out, void *stream)
+{
+	if (nq == 0) return PGEMB_OK;
+	if (!d_packed || !d_dists_out || !d_labels_out || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (n_shards == 0 || k == 0 || n_shards > kMaxShards) return fail(PGEMB_ERR_ARG, "n_shards must be in 1..16 and k > 0");
+	if (shard_stride_bytes < pgemb_packed_topk_bytes(nq, k) || (shard_stride_bytes & 7)) return fail(PGEMB_ERR_ARG, "bad shard stride");
+	ShardLists in;
+	memset(&in, 0, sizeof(in));
+	for (size_t s = 0; s < n_shards; s++)
+	{
+		const char *b = (const char *) d_packed + s * shard_stride_bytes;
+		in.lab[s] = (const uint64_t *) b;
+		in.dist[s] = (const float *) (b + nq * k * 8);
+		in.cnt[s] = (const int32_t *) (b + nq * k * 12);
+	}
+	return launch_merge(nq, n_shards, k, in, nullptr, 0, 0, d_dists_out, d_labels_out, d_n_out, nullptr, (cudaStream_t) stream);
+}
+
+// ---- peer-memory exchange: no collective at all ------------------------------------------------------------------
+// Every rank owns one buffer: two result areas (step parity) in the packed layout above + a flag word per peer.  A step is
+//   pgemb_sharded_search_device   the local search writes its top-k into this rank's area of the step's parity; then, in
+//                                 stream order, the rank's sequence number is stored into EVERY peer's flag array (4-byte
+//                                 copies by the copy engine over NVLink: no kernel, no collective);
+//   pgemb_sharded_merge_device    ONE kernel: waits until all peers' flags show this step, then reads the peers' lists
+//                                 straight from their memory (peer-mapped / CUDA-IPC pointers) and merges.
+// Two parities are enough: a peer that is still reading my area of step s cannot have published s + 1, and my search of
+// step s + 2 (which overwrites that area) is stream-ordered after my merge of s + 1, which waited for that flag.
+struct pgemb_exchange
+{
+	int		 device = 0, rank = 0, world = 1;
+	size_t	 max_nq = 0, k = 0;
+	size_t	 area_bytes = 0, off_flags = 0, total_bytes = 0;
+	char	*d_buf = nullptr;
+	char	*peer[kMaxShards] = {};
+	bool	 peer_ipc[kMaxShards] = {};
+	bool	 attached = false;
+	uint32_t seq = 0;
+	uint32_t *h_seq = nullptr;	// pinned ring: the values the flag copies read
+	int		 *d_error = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool	 ev_valid = false;
+};
+
+extern "C" pgemb_status pgemb_exchange_create(int device, int rank, int world, size_t max_nq, size_t k, pgemb_exchange **out)
+{
+	if (!out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (world < 1 || world > (int) kMaxShards || rank < 0 || rank >= world) return fail(PGEMB_ERR_ARG, "rank/world out of range (world <= 16)");
+	if (max_nq == 0 || k == 0) return fail(PGEMB_ERR_ARG, "max_nq and k must be > 0");
+	CU_TRY(cudaSetDevice(device));
+	pgemb_exchange *ex = new (std::nothrow) pgemb_exchange();
+	if (!ex) return fail(PGEMB_ERR_NOMEM, "out of host memory");
+	ex->device = device;
+	ex->rank = rank;
+	ex->world = world;
+	ex->max_nq = max_nq;
+	ex->k = k;
+	ex->area_bytes = (pgemb_packed_topk_bytes(max_nq, k) + 255) & ~(size_t) 255;
+	ex->off_flags = 2 * ex->area_bytes;
+	ex->total_bytes = ex->off_flags + 256;
+	cudaError_t e = cudaMalloc((void **) &ex->d_buf, ex->total_bytes);
+	if (e == cudaSuccess) e = cudaMemset(ex->d_buf, 0, ex->total_bytes);
+	if (e == cudaSuccess) e = cudaMallocHost((void **) &ex->h_seq, 64 * sizeof(uint32_t));
+	if (e == cudaSuccess) e = cudaMalloc((void **) &ex->d_error, sizeof(int));
+	if (e == cudaSuccess) e = cudaMemset(ex->d_error, 0, sizeof(int));
+	if (e == cudaSuccess) e = cudaEventCreate(&ex->ev0);
+	if (e == cudaSuccess) e = cudaEventCreate(&ex->ev1);
+	if (e == cudaSuccess) e = cudaDeviceSynchronize();
+	if (e != cudaSuccess)
+	{
+		pgemb_exchange_destroy(ex);
+		return fail(PGEMB_ERR_CUDA, std::string("pgemb_exchange_create: ") + cudaGetErrorString(e));
+	}
+	ex->peer[rank] = ex->d_buf;
+	*out = ex;
 	return PGEMB_OK;
+}
+
+extern "C" void pgemb_exchange_destroy(pgemb_exchange *ex)
+{
+	if (!ex) return;
+	cudaSetDevice(ex->device);
+	cudaDeviceSynchronize();
+#ifndef PGEMB_HOST_EMULATION
+	for (int r = 0; r < ex->world; r++)
+		if (r != ex->rank && ex->peer[r] && ex->peer_ipc[r]) cudaIpcCloseMemHandle(ex->peer[r]);
+#endif
+	cudaFree(ex->d_buf);
+	cudaFree(ex->d_error);
+	if (ex->h_seq) cudaFreeHost(ex->h_seq);
+	if (ex->ev0) cudaEventDestroy(ex->ev0);
+	if (ex->ev1) cudaEventDestroy(ex->ev1);
+	cudaGetLastError();
+	delete ex;
+}
+
+// 64-byte handle of this rank's buffer for the other PROCESSES (exchange it out of band: torch.distributed all_gather, a pipe ...)
+extern "C" pgemb_status pgemb_exchange_handle(pgemb_exchange *ex, void *handle_out)
+{
+	if (!ex || !handle_out) return fail(PGEMB_ERR_ARG, "null argument");
+#ifdef PGEMB_HOST_EMULATION
+	memset(handle_out, 0, PGEMB_IPC_HANDLE_BYTES);
+	memcpy(handle_out, &ex->d_buf, sizeof(void *));
+#else
+	static_assert(sizeof(cudaIpcMemHandle_t) == PGEMB_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+	CU_TRY(cudaSetDevice(ex->device));
+	cudaIpcMemHandle_t h;
+	CU_TRY(cudaIpcGetMemHandle(&h, ex->d_buf));
+	memcpy(handle_out, &h, sizeof(h));
+#endif
+	return PGEMB_OK;
+}
+
+// the raw device pointer, for attaching ranks that live in the SAME process (one process driving several GPUs)
+extern "C" void *pgemb_exchange_buffer(pgemb_exchange *ex) { return ex ? ex->d_buf : nullptr; }
+
+extern "C" pgemb_status pgemb_exchange_attach(pgemb_exchange *ex, const void *handles, int same_process)
+{
+	if (!ex || !handles) return fail(PGEMB_ERR_ARG, "null argument");
+	CU_TRY(cudaSetDevice(ex->device));
+	for (int r = 0; r < ex->world; r++)
+	{
+		if (r == ex->rank) continue;
+		const char *h = (const char *) handles + (size_t) r * PGEMB_IPC_HANDLE_BYTES;
+		if (same_process)
+		{
+			void *ptr = nullptr;
+			memcpy(&ptr, h, sizeof(void *));
+			if (!ptr) return fail(PGEMB_ERR_ARG, "null peer buffer");
+#ifndef PGEMB_HOST_EMULATION
+			cudaPointerAttributes at;
+			CU_TRY(cudaPointerGetAttributes(&at, ptr));
+			if (at.device != ex->device)
+			{
+				const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+				if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(PGEMB_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+				cudaGetLastError();
+			}
+#endif
+			ex->peer[r] = (char *) ptr;
+			ex->peer_ipc[r] = false;
+		}
+		else
+		{
+#ifdef PGEMB_HOST_EMULATION
+			return fail(PGEMB_ERR_ARG, "the host emulation has no other processes");
+#else
+			cudaIpcMemHandle_t hh;
+			memcpy(&hh, h, sizeof(hh));
+			void *ptr = nullptr;
+			CU_TRY(cudaIpcOpenMemHandle(&ptr, hh, cudaIpcMemLazyEnablePeerAccess));
+			ex->peer[r] = (char *) ptr;
+			ex->peer_ipc[r] = true;
+#endif
+		}
+	}
+	ex->attached = true;
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_sharded_search_device(pgemb_index *idx, pgemb_exchange *ex, size_t nq, const coord_t *d_queries, size_t ef, void *stream)
+{
+	if (!idx || !ex) return fail(PGEMB_ERR_ARG, "null argument");
+	if (ex->world > 1 && !ex->attached) return fail(PGEMB_ERR_STATE, "pgemb_exchange_attach has not been called");
+	if (ef != ex->k) return fail(PGEMB_ERR_ARG, "ef differs from the exchange's k");
+	if (nq == 0 || nq > ex->max_nq) return fail(PGEMB_ERR_ARG, "nq out of range for this exchange");
+	if (idx->device != ex->device) return fail(PGEMB_ERR_ARG, "index and exchange live on different devices");
+	cudaStream_t s = (cudaStream_t) stream;
+	ex->seq += 1;
+	char	 *area = ex->d_buf + (size_t) (ex->seq & 1u) * ex->area_bytes;
+	uint64_t *d_l = (uint64_t *) area;
+	float	 *d_d = (float *) (area + nq * ex->k * 8);
+	int32_t	 *d_n = (int32_t *) (area + nq * ex->k * 12);
+	pgemb_status st = launch_search(idx, nq, d_queries, (uint32_t) idx->meta.dim, nullptr, (uint32_t) idx->n, ef, 0, d_l, d_d, nullptr, d_n, nullptr, s, true);
+	if (st) return st;
+	// publish: my sequence number into every peer's flag array, after the search in stream order
+	uint32_t *src = &ex->h_seq[ex->seq & 63u];
+	*src = ex->seq;
+	for (int r = 0; r < ex->world; r++)
+	{
+		if (r == ex->rank) continue;
+		CU_TRY(cudaMemcpyAsync(ex->peer[r] + ex->off_flags + (size_t) ex->rank * 4, src, 4, cudaMemcpyHostToDevice, s));
+	}
+	return PGEMB_OK;
+}
+
+extern "C" pgemb_status pgemb_sharded_merge_device(pgemb_exchange *ex, size_t nq, label_t *d_labels_out, dist_t *d_dists_out, int32_t *d_n_out, void *stream)
+{
+	if (!ex || !d_labels_out || !d_dists_out || !d_n_out) return fail(PGEMB_ERR_ARG, "null argument");
+	if (nq == 0 || nq > ex->max_nq) return fail(PGEMB_ERR_ARG, "nq out of range for this exchange");
+	if (ex->seq == 0) return fail(PGEMB_ERR_STATE, "no search step to merge");
+	CU_TRY(cudaSetDevice(ex->device));
+	cudaStream_t s = (cudaStream_t) stream;
+	ShardLists	 in;
+	memset(&in, 0, sizeof(in));
+	for (int r = 0; r < ex->world; r++)
+	{
+		const char *area = ex->peer[r] + (size_t) (ex->seq & 1u) * ex->area_bytes;
+		in.lab[r] = (const uint64_t *) area;
+		in.dist[r] = (const float *) (area + nq * ex->k * 8);
+		in.cnt[r] = (const int32_t *) (area + nq * ex->k * 12);
+	}
+	CU_TRY(cudaEventRecord(ex->ev0, s));
+	pgemb_status st = launch_merge(nq, (size_t) ex->world, ex->k, in, ex->world > 1 ? (const uint32_t *) (ex->d_buf + ex->off_flags) : nullptr, ex->seq,
+								   (uint32_t) ex->rank, d_dists_out, d_labels_out, d_n_out, ex->d_error, s);
+	if (st) return st;
+	CU_TRY(cudaEventRecord(ex->ev1, s));
+	ex->ev_valid = true;
+	return PGEMB_OK;
+}
+
+// device time (ms) of the last wait+merge kernel (includes waiting for the slowest peer); <0 if unavailable
+extern "C" float pgemb_exchange_last_merge_ms(pgemb_exchange *ex)
+{
+	if (!ex || !ex->ev_valid) return -1.0f;
+	float ms = -1.0f;
+	if (cudaSetDevice(ex->device) != cudaSuccess || cudaEventSynchronize(ex->ev1) != cudaSuccess || cudaEventElapsedTime(&ms, ex->ev0, ex->ev1) != cudaSuccess) return -1.0f;
+	return ms;
+}
+
+// 0 = fine; 5 = a peer never published its step within the kernel's patience
+extern "C" int pgemb_exchange_error(pgemb_exchange *ex)
+{
+	if (!ex) return -1;
+	int err = 0;
+	if (cudaSetDevice(ex->device) != cudaSuccess || cudaMemcpy(&err, ex->d_error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+	return err;
 }

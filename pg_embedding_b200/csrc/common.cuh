@@ -116,44 +116,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 		: "memory");
 }
 
-// 16-byte asynchronous copies (SASS LDGSTS): one warp instruction moves 512 contiguous bytes, no uniform-datapath set-up
-// per row as the bulk copy needs.  Completion is per THREAD (commit / wait_group); the other lanes see the data after a
-// __syncwarp().  No L2 policy can be attached (see the note below).
-__device__ __forceinline__ void cp_async_16(void *dst_smem, const void *src_gmem)
-{
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_16_s32(uint32_t dst_smem_u32, const void *src_gmem)
-{
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem_u32), "l"(src_gmem) : "memory");
-}
-// Up to eight 16-byte pieces 512 bytes apart (one lane's share of 4 KB copied by a warp) from ONE pair of base addresses:
-// piece j is copied iff rem > 512 j, where rem = bytes of the row at or after this lane's first piece.  Written as one asm
-// block so that the offsets stay immediates -- left to the compiler every piece gets its own address arithmetic (and a
-// generic-to-shared conversion), which costs more issue slots than the copies.
-__device__ __forceinline__ void cp_async_16_x8(uint32_t dst_smem_u32, const void *src_gmem, uint32_t rem)
-{
-	asm volatile(
-		"{\n\t.reg .pred p0, p1, p2, p3, p4, p5, p6, p7;\n\t"
-		"setp.gt.u32 p0, %2, 0;\n\tsetp.gt.u32 p1, %2, 512;\n\tsetp.gt.u32 p2, %2, 1024;\n\tsetp.gt.u32 p3, %2, 1536;\n\t"
-		"setp.gt.u32 p4, %2, 2048;\n\tsetp.gt.u32 p5, %2, 2560;\n\tsetp.gt.u32 p6, %2, 3072;\n\tsetp.gt.u32 p7, %2, 3584;\n\t"
-		"@p0 cp.async.cg.shared.global [%0], [%1], 16;\n\t"
-		"@p1 cp.async.cg.shared.global [%0+512], [%1+512], 16;\n\t"
-		"@p2 cp.async.cg.shared.global [%0+1024], [%1+1024], 16;\n\t"
-		"@p3 cp.async.cg.shared.global [%0+1536], [%1+1536], 16;\n\t"
-		"@p4 cp.async.cg.shared.global [%0+2048], [%1+2048], 16;\n\t"
-		"@p5 cp.async.cg.shared.global [%0+2560], [%1+2560], 16;\n\t"
-		"@p6 cp.async.cg.shared.global [%0+3072], [%1+3072], 16;\n\t"
-		"@p7 cp.async.cg.shared.global [%0+3584], [%1+3584], 16;\n\t}"
-		::"r"(dst_smem_u32), "l"(src_gmem), "r"(rem)
-		: "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 #endif  // PGEMB_HOST_EMULATION
 
-// NOTE (kept from the LDGSTS experiments, profiles/README.md): `cp.async.cg.shared.global.L2::cache_hint` miscompiles with
+// NOTE (kept from the LDGSTS gather experiments, rounds 1-2: measured slower than the bulk copies at every row size and
+// removed, profiles/README.md): `cp.async.cg.shared.global.L2::cache_hint` miscompiles with
 // ptxas 12.9 for sm_100a -- it emits `LDGSTS [R+UR0], desc[UR1]` whose uniform registers are never written and the
 // instruction traps ("illegal instruction", pinpointed with compute-sanitizer).  Bulk TMA takes the same policy fine.
 

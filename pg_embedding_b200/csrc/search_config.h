@@ -29,6 +29,7 @@ struct SearchConfig
 	uint32_t ef = 0;
 	uint32_t tpr = 4;
 	uint32_t off_vhs = 0, vhs_entries = 0;	// latency mode: visited hash set in shared memory
+	bool	 res_global = false;
 };
 
 struct SearchShape
@@ -36,6 +37,9 @@ struct SearchShape
 	int		 metric = 0;  // DIST_L2 = 0, DIST_COSINE = 1, DIST_MANHATTAN = 2
 	uint32_t dim = 0, row_f = 0, link_stride = 0, maxM = 0, ef = 0, sm_count = 0;
 	uint32_t tpr = 4;  // lanes per row: 4, or 8 (L2 only: a ring then holds 4 rows)
+	// the two result buffers (2 x ef keys) live in global memory instead of the slot's private shared-memory block: for ef so
+	// large that they no longer fit (the reference doubles efSearch without bound, embedding.c:334)
+	bool res_global = false;
 };
 
 struct SearchTuning
@@ -63,6 +67,7 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 	const uint32_t hopcap = maxM > 1 ? maxM : 1;
 	const uint32_t max_cta = 232448u;  // 227 KB per CTA
 	const uint32_t ef = sh.ef;
+	if (!sh.res_global && ef > (max_cta / 16u)) return 1;  // 2 x ef x 8 bytes alone exceed a CTA's shared memory
 	// lane-major transposed query: per lane-thread a run of floats padded so that the four runs start
 	// 16 bytes apart modulo 128 (conflict-free LDS.128)
 	const uint32_t dim = sh.dim;
@@ -76,11 +81,12 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 
 	SearchConfig t;
 	t.tpr = tpr;
+	t.res_global = sh.res_global;
 	// ---- a slot's private block ----
 	uint32_t off = 0;
 	t.off_qt = off;			off = cfg_align_up(off + tpr * qt_stride * 4u, 16);
 	t.off_qtail = off;		off = cfg_align_up(off + 16u * 4u, 16);
-	t.off_res = off;		off += 2u * ef * 8u;
+	t.off_res = off;		off += sh.res_global ? 0u : 2u * ef * 8u;
 	t.off_hopkey = off;		off += hopcap * 8u;
 	t.off_acckey = off;		off += hopcap * 8u;
 	t.off_evict = off;		off += hopcap * 8u;

@@ -40,15 +40,6 @@
 
 namespace pgemb {
 
-// Opt-in prototypes that have not run on a B200 yet are compiled only with -DPGEMB_PROTO, into a
-// separate library (libpgemb_b200_proto.so): the product library's traversal kernels stay instruction-for-instruction
-// the ones that were measured.
-#ifdef PGEMB_PROTO
-#define PGEMB_HAS_VISITED_PAIRS 1
-constexpr bool kProto = true;
-#else
-constexpr bool kProto = false;
-#endif
 struct SearchParams
 {
 	// index (HBM, SoA)
@@ -75,12 +66,11 @@ struct SearchParams
 	uint32_t	 *visited;		 // [slots][vis_words]   exact bitmap (fallback / small indexes)
 	uint32_t	 *vlog;			 // [slots][vlog_cap]    table positions (hash mode) or ids (bitmap mode) to reset
 	uint64_t	 *ovf;			 // [slots][ef]
+	uint64_t	 *res_g;		 // [slots][2 * ef] result buffers in global memory (search_kernel<..., RESG = true> only: huge ef)
 	uint32_t	 *vhash;		 // [slots][vh_size]     open-addressing visited set, 0xffffffff = empty
 	uint32_t	  vis_words, vlog_cap;
 	uint32_t	  vh_size, vh_shift;  // vh_size = 2^k entries (0: bitmap only), hash = (id * 2654435761) >> vh_shift
-#ifdef PGEMB_PROTO
 	uint32_t	  off_vhs, vhs_entries;	 // latency mode: the hash set lives in the CTA's shared memory (2^k entries, 0 = use vhash)
-#endif
 	unsigned int *counter;		 // work-stealing query counter
 	const unsigned int *avail;	 // optional: number of queries whose data has landed (host API streams them in while the kernel runs)
 	int			 *error_flag;	 // sticky: 1 = bad link id / count, 2 = overflow buffer exceeded
@@ -90,10 +80,7 @@ struct SearchParams
 	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
 	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
 	uint32_t prefetch_links;
-#ifdef PGEMB_PROTO
-	uint32_t visited_pairs;	 // 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
-	uint32_t gather_ldgsts;	 // 1: rows are gathered with 16-byte cp.async pieces (a warp instruction per 512 B) instead of one bulk copy per row
-#endif
+	uint32_t visited_pairs;	 // latency mode, 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
 	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
 };
@@ -102,10 +89,8 @@ struct SearchParams
 // copy the shared-memory layout chosen by make_search_config into the kernel parameters
 inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_f)
 {
-#ifdef PGEMB_PROTO
 	p.off_vhs = cfg.off_vhs;
 	p.vhs_entries = cfg.vhs_entries;
-#endif
 	p.rings = cfg.rings;
 	p.ring_bytes = cfg.ring_bytes;
 	p.off_pool = cfg.off_pool;
@@ -336,31 +321,6 @@ __device__ __forceinline__ float score_row(const float *__restrict__ qts, const 
 __device__ __forceinline__ void coop_bar(int id, uint32_t nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 #endif
 
-#ifdef PGEMB_PROTO
-// Prototype (PGEMB_GATHER_LDGSTS): gather `rows` rows of a hop into a ring with 16-byte asynchronous copies.  A bulk copy
-// takes ~75 cycles of the issuing warp per ROW (few instructions, but an ELECT / R2UR / UBLKCP loop that runs lane by lane
-// through the uniform datapath); here a whole warp moves 512 B per instruction and nothing is serialised.  The copies belong to the issuing threads: the
-// consumer side is cp_async_wait_all() + __syncwarp() instead of the ring's mbarrier.
-__device__ __forceinline__ void gather_rows_ldgsts(const SearchParams &p, unsigned char *ring, const uint32_t *ids, uint32_t rows, uint32_t lane)
-{
-	const uint32_t lo = lane * 16u, rb = p.row_bytes;
-	const uint32_t ring32 = smem_u32(ring) + lo;  // one generic-to-shared conversion for the whole group
-	for (uint32_t r = 0; r < rows; r++)
-	{
-		const unsigned char *src = reinterpret_cast<const unsigned char *>(p.vectors + (size_t) ids[r] * p.row_f) + lo;
-		const uint32_t		 dst = ring32 + r * p.row_smem;
-		if (rb <= 512u)
-		{
-			if (lo < rb) cp_async_16_s32(dst, src);	 // short rows (<= 128 dimensions): one instruction per row
-			continue;
-		}
-		// 4 KB per step (a 3 KB row is one step): this lane's pieces at constant offsets, each under its own predicate
-		for (uint32_t o = 0; o + lo < rb; o += 4096u) cp_async_16_x8(dst + o, src + o, rb - o - lo);
-	}
-	cp_async_commit();
-}
-#endif
-
 template <int METRIC, int TPR>
 __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char *ring, uint64_t *rbar, uint32_t &rpar, uint32_t warp,
 											uint32_t nwarps, uint32_t n, const uint32_t *hop_id, uint64_t *hop_key, const float *qT,
@@ -375,38 +335,20 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 	for (uint32_t g = warp; g < G; g += nwarps)
 	{
 		const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
-#ifdef PGEMB_PROTO
-		const bool ldgsts = p.gather_ldgsts != 0u;
-		if (ldgsts)
-			gather_rows_ldgsts(p, ring, hop_id + g * kRows, rows, lane);
-		else
-#endif
+		if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
+		__syncwarp();
+		if (lane < rows)
 		{
-			if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
-			__syncwarp();
-			if (lane < rows)
-			{
-				const uint32_t id = hop_id[g * kRows + lane];
-				tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
-			}
+			const uint32_t id = hop_id[g * kRows + lane];
+			tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
 		}
 		const uint32_t k = g * kRows + row_in_stage;
 		const uint32_t kk = min(k, n - 1);
 		const uint32_t my_id = hop_id[kk];
 		float		   vn = 1.0f;
 		if (METRIC == M_COS) vn = p.norms[my_id];
-#ifdef PGEMB_PROTO
-		if (ldgsts)
-		{
-			cp_async_wait_all();
-			__syncwarp();
-		}
-		else
-#endif
-		{
-			mbar_wait(rbar, rpar);
-			rpar ^= 1u;
-		}
+		mbar_wait(rbar, rpar);
+		rpar ^= 1u;
 		const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
 		const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, (int) p.dim, qn, vn);
 		if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
@@ -414,7 +356,10 @@ __device__ __forceinline__ void coop_gather(const SearchParams &p, unsigned char
 	}
 }
 
-template <int METRIC, bool COOP, int TPR = 4>
+// RESG: the two result buffers of a slot live in global memory (p.res_g) instead of its shared-memory block -- the variant
+// launch_search falls back to when 2 x ef keys no longer fit a CTA, so that the caller's efSearch doubling (embedding.c:334)
+// never fails before ef reaches the index size.  Same code path otherwise (the queue update then runs at L2 latency).
+template <int METRIC, bool COOP, int TPR = 4, bool RESG = false>
 __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 {
 	constexpr int kRows = 32 / TPR;	 // rows per ring
@@ -427,7 +372,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	unsigned char *priv = smem + p.off_priv + (COOP ? 0 : (size_t) warp * p.priv_bytes);  // this slot's private block
 	float		  *qT = reinterpret_cast<float *>(priv + p.off_qt);
 	float		  *q_tail = reinterpret_cast<float *>(priv + p.off_qtail);
-	uint64_t	  *res = reinterpret_cast<uint64_t *>(priv + p.off_res);	// two buffers of ef keys
+	uint64_t	  *res = RESG ? p.res_g + (size_t) slot * 2u * p.ef : reinterpret_cast<uint64_t *>(priv + p.off_res);	// two buffers of ef keys
 	uint64_t	  *hop_key = reinterpret_cast<uint64_t *>(priv + p.off_hopkey);
 	uint64_t	  *acc_key = reinterpret_cast<uint64_t *>(priv + p.off_acckey);
 	uint64_t	  *evict_key = reinterpret_cast<uint64_t *>(priv + p.off_evict);
@@ -443,23 +388,13 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	const int	   main_n = main_len<METRIC>(dim);
 	// latency mode keeps the open-addressing visited set in shared memory when the CTA has room for it: a hop's
 	// test-and-set round then costs shared-memory atomics instead of L2 round trips
-#ifdef PGEMB_PROTO
 	const bool	   vh_shared = COOP && p.vhs_entries != 0u;
 	const uint32_t H = vh_shared ? p.vhs_entries : p.vh_size;
 	const uint32_t vh_shift = vh_shared ? (32u - (uint32_t) __popc(p.vhs_entries - 1u)) : p.vh_shift;
-#else
-	constexpr bool vh_shared = false;
-	const uint32_t H = p.vh_size;
-	const uint32_t vh_shift = p.vh_shift;
-#endif
 	uint32_t	  *vis = p.visited + (size_t) slot * p.vis_words;
 	uint32_t	  *vlog = p.vlog + (size_t) slot * p.vlog_cap;
 	uint64_t	  *ovf = p.ovf + (size_t) slot * ef;
-#ifdef PGEMB_PROTO
 	uint32_t	  *vh = vh_shared ? reinterpret_cast<uint32_t *>(smem + p.off_vhs) : p.vhash + (size_t) slot * H;
-#else
-	uint32_t	  *vh = p.vhash + (size_t) slot * H;
-#endif
 	const uint64_t pol_stream = l2_policy_evict_first();
 	const uint64_t pol_keep = l2_policy_evict_last();
 	constexpr uint32_t kEmpty = 0xffffffffu;
@@ -651,18 +586,8 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				const uint32_t rpar0 = rpar;
 				unsigned char *ring = ring_base + (size_t) rb * p.ring_bytes;
 				uint64_t	  *rbar = &pool->bar[rb];
-#ifdef PGEMB_PROTO
-				const bool ldgsts = p.gather_ldgsts != 0u;
-#endif
 				auto		   issue = [&](uint32_t g) {
 					  const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
-#ifdef PGEMB_PROTO
-					  if (ldgsts)
-					  {
-						  gather_rows_ldgsts(p, ring, hop_id + g * kRows, rows, lane);
-						  return;
-					  }
-#endif
 					  if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
 					  __syncwarp();
 					  if (lane < rows)
@@ -680,18 +605,8 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					const uint32_t my_id = hop_id[kk];
 					float		   vn = 1.0f;
 					if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
-#ifdef PGEMB_PROTO
-					if (ldgsts)
-					{
-						cp_async_wait_all();  // this thread's pieces have landed ...
-						__syncwarp();		  // ... and, after the warp barrier, everybody's
-					}
-					else
-#endif
-					{
-						mbar_wait(rbar, rpar);
-						rpar ^= 1u;
-					}
+					mbar_wait(rbar, rpar);
+					rpar ^= 1u;
 					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
 					const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
 					if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
@@ -970,8 +885,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				__syncwarp();
 				vmode = 1;
 			}
-#ifdef PGEMB_PROTO
-			if (p.visited_pairs)
+			if (COOP && p.visited_pairs)
 			{
 				// Two 32-id chunks of the list per iteration with BOTH chunks' test-and-set atomics in flight before
 				// the first result is consumed: a full 64-link list costs one L2 round trip instead of two dependent
@@ -1037,7 +951,6 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				}
 			}
 			else
-#endif
 			for (uint32_t base = 0; base < cnt; base += 32)
 			{
 				// list position k = base + lane lives in word k + 1

@@ -219,7 +219,9 @@ static PgembIpcSlot *claim_slot(const Conn *c)
 			if (ld(&s->state) == PGEMB_SLOT_FREE &&
 				__atomic_compare_exchange_n(&s->state, &expect, PGEMB_SLOT_CLAIMED, 0, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED))
 			{
-				s->owner_pid = (int32_t) getpid();
+				/* ownership: the previous user cleared owner_pid before it freed the slot (release_slot, the sidecar's own frees), so
+				 * between the CAS above and this store the sidecar's reclaim() sees pid 0 and leaves the slot alone */
+				__atomic_store_n(&s->owner_pid, (int32_t) getpid(), __ATOMIC_RELEASE);
 				s->status = 0;
 				s->n_out = 0;
 				s->a0 = s->a1 = s->a2 = s->a3 = 0;
@@ -293,7 +295,11 @@ static int interrupted(int rc) { return rc == PGEMB_CLIENT_INTERRUPTED || rc == 
 /* give a slot back after submit_wait() -- unless the request was abandoned: then the slot is not ours any more */
 static void release_slot(PgembIpcSlot *s, int rc)
 {
-	if (!interrupted(rc) && ld(&s->state) == PGEMB_SLOT_DONE) st(&s->state, PGEMB_SLOT_FREE);
+	if (!interrupted(rc) && ld(&s->state) == PGEMB_SLOT_DONE)
+	{
+		__atomic_store_n(&s->owner_pid, 0, __ATOMIC_RELEASE); /* never leave a stale pid on a FREE slot (see claim_slot) */
+		st(&s->state, PGEMB_SLOT_FREE);
+	}
 }
 
 /* the bulk area is one request's at a time */

@@ -148,6 +148,9 @@ struct Server
 			// the client stopped waiting (cancelled query): nobody will read the result
 			const uint32_t op = s->op, owner = (uint32_t) s->owner_pid;
 			uint32_t	   expect = PGEMB_SLOT_DONE;
+			// FREE slots carry no pid: the next claimer stores its own AFTER its CAS, and reclaim() must not judge it by ours.
+			// (If the client's own CAS wins the race instead, the pid it leaves behind is that of a live backend.)
+			__atomic_store_n(&s->owner_pid, 0, __ATOMIC_RELEASE);
 			if (__atomic_compare_exchange_n(&s->state, &expect, (uint32_t) PGEMB_SLOT_FREE, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED))
 			{
 				// we freed the slot (not the client): a bulk request's hold on the bulk area ends with it
@@ -465,15 +468,49 @@ struct Server
 		return found;
 	}
 
-	// slots / bulk lock left behind by clients that died
+	// slots / bulk lock left behind by clients that died.  A slot is taken back only if the SAME dead owner was seen on two
+	// consecutive passes (a second apart) in the SAME state, and then by a CAS on that state: a claimer that is between its CAS
+	// and the store of its pid (owner_pid 0, or -- after a cancelled request -- the previous user's) is never mistaken for a
+	// dead one.
+	std::vector<int32_t>  suspect_pid;
+	std::vector<uint32_t> suspect_state;
 	void reclaim()
 	{
+		if (suspect_pid.size() != hdr->n_slots)
+		{
+			suspect_pid.assign(hdr->n_slots, 0);
+			suspect_state.assign(hdr->n_slots, 0);
+		}
 		for (uint32_t i = 0; i < hdr->n_slots; i++)
 		{
 			PgembIpcSlot  *s = slot(i);
 			const uint32_t stt = ld(&s->state);
-			if ((stt == PGEMB_SLOT_CLAIMED || stt == PGEMB_SLOT_DONE) && s->owner_pid > 0 && kill(s->owner_pid, 0) != 0 && errno == ESRCH)
-				st(&s->state, PGEMB_SLOT_FREE);
+			const int32_t  owner = __atomic_load_n(&s->owner_pid, __ATOMIC_ACQUIRE);
+			const bool	   dead = (stt == PGEMB_SLOT_CLAIMED || stt == PGEMB_SLOT_DONE) && owner > 0 && kill(owner, 0) != 0 && errno == ESRCH;
+			if (!dead)
+			{
+				suspect_pid[i] = 0;
+				continue;
+			}
+			if (suspect_pid[i] == owner && suspect_state[i] == stt)
+			{
+				uint32_t expect = stt;
+				if (__atomic_load_n(&s->owner_pid, __ATOMIC_ACQUIRE) == owner)
+				{
+					__atomic_store_n(&s->owner_pid, 0, __ATOMIC_RELEASE);
+					if (!__atomic_compare_exchange_n(&s->state, &expect, (uint32_t) PGEMB_SLOT_FREE, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED))
+					{
+						int32_t zero = 0;  // the state moved on under us (cannot happen with a dead owner): put the pid back unless somebody else's is there
+						__atomic_compare_exchange_n(&s->owner_pid, &zero, owner, false, __ATOMIC_ACQ_REL, __ATOMIC_RELAXED);
+					}
+				}
+				suspect_pid[i] = 0;
+			}
+			else
+			{
+				suspect_pid[i] = owner;
+				suspect_state[i] = stt;
+			}
 		}
 		uint32_t owner = ld(&hdr->bulk_lock);
 		if (owner != 0 && kill((pid_t) owner, 0) != 0 && errno == ESRCH)
@@ -526,7 +563,8 @@ void usage()
 int main(int argc, char **argv)
 {
 	std::string shm_name, lib_path;
-	uint32_t	n_slots = 256, max_dim = 2000, max_ef = 1024;
+	uint32_t	n_slots = 256, max_dim = 2000, max_ef = 16384;	// max_ef sizes the label area of a slot (8 B each): hnsw_gettuple doubles efSearch
+																// (embedding.c:334) -- LIMITs beyond max_ef / 2 rows fail with "HNSW index search failed"
 	size_t		bulk_mb = 64;
 	Server		srv;
 	for (int i = 1; i < argc; i++)

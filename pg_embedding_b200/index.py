@@ -88,6 +88,7 @@ class HnswIndex:
                                        int(efsearch), _metric(metric)))
         dev = C.c_void_p()
         check(self.lib.pgemb_index_create(C.byref(self.host.meta), int(capacity), int(device), C.byref(dev)))
+        self.device = int(device)
         self.host.dev = dev.value
         self.dev = dev
         self.dims, self.m, self.maxm = int(dims), int(m), 2 * int(m)
@@ -258,34 +259,41 @@ class HnswIndex:
         return {"labels": labels, "n": n, "dists": dists, "ids": ids, "stats": stats,
                 "kernel_ms": float(self.lib.pgemb_last_kernel_ms(self.dev))}
 
-    def scan(self, q, limit: int | None = None):
-        """hnsw_gettuple's iteration (embedding.c:285-370): yield labels; when the current result set is
-        exhausted and was full (n == efSearch), double efSearch, search again and yield only labels not
-        returned before; stop when a search returns no more results than already returned."""
+    def scan(self, q, limit: int | None = None, efsearch: int | None = None, batch: int = 1):
+        """hnsw_beginscan / hnsw_gettuple / hnsw_endscan (embedding.c:249-387) through the C ABI (pgemb_index_scan_*): yields
+        heap TIDs (label without flags) until the scan is exhausted or `limit` tuples were returned.  batch > 1 fetches that many
+        tuples per call (pgemb_index_scan_next_batch) -- same sequence."""
         qv = _f32(q).ravel()
         self._check_dims(qv)
-        ef0 = self.efsearch
+        sc = C.c_void_p()
+        check(self.lib.pgemb_index_scan_begin(self.dev, _p(qv, C.c_float), int(self.efsearch if efsearch is None else efsearch), C.byref(sc)))
+        self.last_scan = {}
         try:
-            results = list(self.search(qv))
             returned = 0
-            no_more = len(results) < self.efsearch
-            while limit is None or returned < limit:
-                if returned >= len(results):
-                    if no_more:
+            if batch <= 1:
+                t = C.c_uint64(0)
+                while limit is None or returned < limit:
+                    r = self.lib.pgemb_index_scan_next(sc, C.byref(t))
+                    if r < 0:
+                        raise RuntimeError("HNSW index search failed: " + self.lib.pgemb_last_error().decode())  # embedding.c:318, :336
+                    if r == 0:
                         return
-                    self.host.meta.efSearch *= 2  # embedding.c:334 doubles in place
-                    new = list(self.search(qv))
-                    if len(new) <= len(results):
+                    returned += 1
+                    yield int(t.value)
+            else:
+                buf = np.empty(batch, dtype=np.uint64)
+                got = C.c_size_t(0)
+                while limit is None or returned < limit:
+                    want = batch if limit is None else min(batch, limit - returned)
+                    check(self.lib.pgemb_index_scan_next_batch(sc, want, _p(buf, C.c_uint64), C.byref(got)))
+                    for i in range(got.value):
+                        returned += 1
+                        yield int(buf[i])
+                    if got.value < want:
                         return
-                    no_more = len(new) < self.efsearch
-                    seen = set(results)
-                    results += [l for l in new if l not in seen]
-                    if returned >= len(results):
-                        return
-                yield results[returned]
-                returned += 1
         finally:
-            self.host.meta.efSearch = ef0  # the reference's HnswIndex is per-scan (embedding.c:254)
+            self.last_scan = {"ef": int(self.lib.pgemb_index_scan_ef(sc)), "searches": int(self.lib.pgemb_index_scan_searches(sc))}
+            self.lib.pgemb_index_scan_end(sc)
 
     def scan_topk(self, queries, k: int):
         """Exact brute-force k-NN (the seq-scan answer, knn.out:63-91), batched. Returns dict(labels, dists, n)."""

@@ -50,5 +50,13 @@ extern "C" void emu_merge_topk(uint32_t nq, uint32_t n_shards, uint32_t k, const
 							   float *dout, uint64_t *lout, int32_t *nout)
 {
 	if (nq == 0) return;
-	emu::launch(dim3((nq * 32 + 127) / 128), 128, 0, [=]() { merge_topk_kernel(nq, n_shards, k, din, lin, nin, dout, lout, nout); });
+	ShardLists in;
+	memset(&in, 0, sizeof(in));
+	for (uint32_t s = 0; s < n_shards; s++)	 // [shard][query][k], as pgemb_merge_topk_device lays them out
+	{
+		in.dist[s] = din + (size_t) s * nq * k;
+		in.lab[s] = lin + (size_t) s * nq * k;
+		in.cnt[s] = nin + (size_t) s * nq;
+	}
+	emu::launch(dim3((nq * 32 + 127) / 128), 128, 0, [=]() { merge_topk_lists_kernel(nq, n_shards, k, in, nullptr, 0u, 0u, dout, lout, nout, nullptr); });
 }

@@ -13,9 +13,9 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 							 int32_t *n_out, uint32_t *stats_out, uint32_t want_warps, uint32_t want_rings, uint32_t grid, uint32_t vh_size,
 							 uint32_t visited_pairs, uint32_t smem_visited, int *error_out);
 
-template <int METRIC, bool COOP, int TPR = 4> static void go(const SearchParams &p, unsigned grid, unsigned warps, size_t smem)
+template <int METRIC, bool COOP, int TPR = 4, bool RESG = false> static void go(const SearchParams &p, unsigned grid, unsigned warps, size_t smem)
 {
-	emu::launch(dim3(grid), warps * 32, smem, [=]() { search_kernel<METRIC, COOP, TPR>(p); });
+	emu::launch(dim3(grid), warps * 32, smem, [=]() { search_kernel<METRIC, COOP, TPR, RESG>(p); });
 }
 
 // returns 0 on success, >0 = make_search_config's code, -1 = bad metric; *error_out = the kernel's sticky error flag
@@ -47,24 +47,22 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	tu.want_warps = (int) want_warps;
 	tu.want_rings = (int) want_rings;
 	tu.want_coop_warps = (int) want_warps;
-	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;		  // bit 31: 8 lanes per L2 row (prototype)
-	const uint32_t ldgsts = (smem_visited >> 30) & 1u;	  // bit 30: rows gathered with 16-byte cp.async pieces (prototype)
-	smem_visited &= 0x3fffffffu;
+	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;		  // bit 31: 8 lanes per L2 row
+	const bool res_global = (smem_visited & 0x20000000u) != 0u;  // bit 29: result buffers in global memory (the huge-ef variant)
+	sh.res_global = res_global;
+	smem_visited &= 0x1fffffffu;
 	tu.smem_visited = (int) smem_visited;
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
 	if (rc) return rc;
-#ifdef PGEMB_PROTO
 	if (coop && smem_visited && cfg.vhs_entries == 0) return 77;  // the test asked for the shared-memory set
-#else
-	if (visited_pairs || smem_visited || cfg.tpr != 4 || ldgsts) return 78;  // prototypes exist only in the -DPGEMB_PROTO build
-#endif
 	const uint32_t slots = coop ? grid : grid * cfg.warps;
 	const uint32_t vis_words = (n_items + 31) / 32 + 1;
 	const uint32_t vlog_cap = n_items < 32768 ? n_items + 1 : 32768;
 	std::vector<uint32_t> visited((size_t) slots * vis_words, 0u), vlog((size_t) slots * vlog_cap, 0u);
 	std::vector<uint32_t> vhash((size_t) slots * (vh_size ? vh_size : 1), 0xffffffffu);
 	std::vector<uint64_t> ovf((size_t) slots * ef, 0ull);
+	std::vector<uint64_t> resg(res_global ? (size_t) slots * 2 * ef : 1, 0ull);
 	unsigned int counter = 0;
 	int			 err = 0;
 
@@ -93,6 +91,7 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	p.visited = visited.data();
 	p.vlog = vlog.data();
 	p.ovf = ovf.data();
+	p.res_g = res_global ? resg.data() : nullptr;
 	p.vhash = vhash.data();
 	p.vis_words = vis_words;
 	p.vlog_cap = vlog_cap;
@@ -105,22 +104,22 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	p.counter = &counter;
 	p.error_flag = &err;
 	p.prefetch_links = 1;
-#ifdef PGEMB_HAS_VISITED_PAIRS
-	p.visited_pairs = visited_pairs;
-	p.gather_ldgsts = ldgsts;
-#else
-	(void) visited_pairs;
-#endif
+	p.visited_pairs = visited_pairs;  // used by the latency-mode kernel only
 	apply_config(p, cfg, row_f);
 	unsigned g = nq < grid ? nq : grid;
 	if (g == 0) g = 1;
-#ifdef PGEMB_PROTO
-	if (cfg.tpr == 8)
+	if (res_global)
+	{
+		if (coop || cfg.tpr != 4) return 79;
+		if (metric == 0) go<M_L2, false, 4, true>(p, g, cfg.warps, cfg.smem);
+		else if (metric == 1) go<M_COS, false, 4, true>(p, g, cfg.warps, cfg.smem);
+		else go<M_MAN, false, 4, true>(p, g, cfg.warps, cfg.smem);
+	}
+	else if (cfg.tpr == 8)
 	{
 		if (coop) go<M_L2, true, 8>(p, g, cfg.warps, cfg.smem); else go<M_L2, false, 8>(p, g, cfg.warps, cfg.smem);
 	}
 	else
-#endif
 	switch (metric * 2 + (coop ? 1 : 0))
 	{
 		case 0: go<M_L2, false>(p, g, cfg.warps, cfg.smem); break;
@@ -216,6 +215,7 @@ extern "C" int emu_bind_sequence(int metric, int coop, const float *vectors, uin
 		p.visited = visited.data();
 		p.vlog = vlog.data();
 		p.ovf = ovf.data();
+	p.res_g = nullptr;
 		p.vhash = vhash.data();
 		p.vis_words = vis_words;
 		p.vlog_cap = vlog_cap;

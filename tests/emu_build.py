@@ -7,9 +7,9 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build_emulated(out_dir: str, proto: bool = False) -> str:
-    out = os.path.join(str(out_dir), "libpgemb_emulated_proto.so" if proto else "libpgemb_emulated.so")
-    cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"] + (["-DPGEMB_PROTO"] if proto else []) + [
+def build_emulated(out_dir: str) -> str:
+    out = os.path.join(str(out_dir), "libpgemb_emulated.so")
+    cmd = ["g++", "-x", "c++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread"] + [
         "-I", os.path.join(ROOT, "tests", "emu", "fake_cuda"), "-I", os.path.join(ROOT, "include"), "-o", out,
         os.path.join(ROOT, "pg_embedding_b200", "csrc", "capi.cu"), os.path.join(ROOT, "tests", "emu", "emu_runtime.cpp")]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -87,30 +87,42 @@ def test_product_does_not_import_oracle():
                     and "libpgemb_ref" not in src, f
 
 
-def test_product_library_holds_no_prototype_kernels(lib):
-    """Prototypes that have not been measured on a B200 are compiled only into the -DPGEMB_PROTO
-    variant; the product library's device code must not contain them, and both variants export the whole C ABI."""
+def test_product_library_is_blackwell_native(lib):
+    """SASS evidence (B200_PROFILING.md "What proves a Blackwell-native kernel"): the traversal gathers rows with the bulk-copy
+    engine (UBLKCP + mbarrier SYNCS), the brute-force scan's dense contraction runs on the 5th-gen tensor cores
+    (tcgen05.mma -> UTC*MMA, TMEM read-back LDTM, 2-D TMA tensor-map loads UTMALDG) -- and nothing is a legacy mma.sync/wgmma
+    path or a library GEMM (no cuBLAS symbol, no HMMA)."""
     import shutil
     import subprocess
-    from pg_embedding_b200 import _lib, build
-    assert b"+proto" not in lib.pgemb_version()
-    proto = C.CDLL(build.OUT_PROTO)
-    proto.pgemb_version.restype = C.c_char_p
-    assert b"+proto" in proto.pgemb_version()
-    for name in _lib.ABI_SYMBOLS:
-        assert hasattr(proto, name), f"{name} not exported by the prototype variant"
+    from pg_embedding_b200 import build
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.isfile(cuobjdump):
         pytest.skip("cuobjdump not available")
-    def kernels(path):
-        out = subprocess.run([cuobjdump, "-symbols", path], capture_output=True, text=True).stdout
-        return set(re.findall(r"_ZN5pgemb\w+", out))
-    prod, prot = kernels(build.OUT), kernels(build.OUT_PROTO)
-    marks = ("scan_tile_kernel", "links_distinct_kernel", "ELi8EEEvNS_12SearchParams")
-    assert not [k for k in prod if any(m in k for m in marks)]
-    for m in marks:
-        assert any(m in k for k in prot), m
-    assert prod <= prot
+    sass = subprocess.run([cuobjdump, "-sass", build.OUT], capture_output=True, text=True).stdout
+    ops = {}
+    fn = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            continue
+        m = re.search(r"\s(UTC[A-Z0-9]*MMA|LDTM|UTMALDG|UBLKCP|HMMA|HGMMA|UTCBAR)\b", line)
+        if m and fn:
+            ops.setdefault(fn, {}).setdefault(m.group(1), 0)
+            ops[fn][m.group(1)] += 1
+    umma = [f for f in ops if "scan_filter_umma_kernel" in f]
+    assert len(umma) == 2, umma                                   # L2 and cosine
+    for f in umma:
+        assert any(k.startswith("UTC") and k.endswith("MMA") for k in ops[f]), (f, ops[f])
+        assert ops[f].get("LDTM", 0) >= 1 and ops[f].get("UTMALDG", 0) >= 2 and ops[f].get("UTCBAR", 0) >= 2, (f, ops[f])
+    search = [f for f in ops if "search_kernel" in f]
+    assert len(search) == 11                                      # 3 metrics x 2 modes + the 8-lanes-per-row L2 pair + 3 huge-ef variants
+    for f in search:
+        assert ops[f].get("UBLKCP", 0) >= 2, (f, ops[f])
+    assert not any("HMMA" in v or "HGMMA" in v for v in ops.values())
+    needed = subprocess.run(["ldd", build.OUT], capture_output=True, text=True).stdout
+    assert "cublas" not in needed.lower()
+    assert "cublas" not in open(os.path.join(ROOT, "pg_embedding_b200", "csrc", "capi.cu")).read().lower()
 
 
 def test_client_library_exports_the_reference_symbols_and_no_cuda():

@@ -16,22 +16,12 @@ pytestmark = pytest.mark.timeout(1800, method="thread")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _build_emulated(tmp_path_factory, proto):
-    from emu_build import build_emulated
-    from pg_embedding_b200 import _lib
-    return _lib._bind(C.CDLL(build_emulated(tmp_path_factory.mktemp("emu"), proto)))
-
-
 @pytest.fixture(scope="module")
 def emu_lib(tmp_path_factory):
     """capi.cu as the product library compiles it."""
-    return _build_emulated(tmp_path_factory, False)
-
-
-@pytest.fixture(scope="module")
-def emu_lib_proto(tmp_path_factory):
-    """capi.cu with -DPGEMB_PROTO (what libpgemb_b200_proto.so holds): the opt-in prototypes are compiled in."""
-    return _build_emulated(tmp_path_factory, True)
+    from emu_build import build_emulated
+    from pg_embedding_b200 import _lib
+    return _lib._bind(C.CDLL(build_emulated(tmp_path_factory.mktemp("emu"))))
 
 
 def _swap(lib, monkeypatch):
@@ -53,14 +43,14 @@ def pg(emu_lib, monkeypatch):
 
 
 @pytest.fixture()
-def pg_proto(emu_lib_proto, monkeypatch):
-    assert b"+proto" in emu_lib_proto.pgemb_version()
-    return _swap(emu_lib_proto, monkeypatch)
+def pg_proto(pg):
+    """Round 1's -DPGEMB_PROTO variants were measured in round 2 and are product code now (or deleted): same library."""
+    return pg
 
 
 @pytest.fixture(scope="module")
 def P():
-    import test_gpu_prototypes as p     # GPU tests of the prototype flags: bodies reused below
+    import test_gpu_variants as p     # GPU tests of the variants measured in round 2: bodies reused below
     return p
 
 
@@ -156,7 +146,8 @@ def test_index_grows_in_place(pg, G, oracle_mod):
 
 def test_scan_and_merge(pg, G, oracle_mod):
     G.test_scan_topk_regress_seqscan(pg)
-    G.test_scan_doubles_efsearch(pg, oracle_mod)
+    for cfg in G.SCAN_ITER_CFGS[1:]:
+        G.test_index_scan_iteration_equals_reference_loop(pg, oracle_mod, cfg)
 
 
 def test_error_paths(pg):
@@ -193,12 +184,10 @@ def test_host_pointer_search_both_copy_orders(pg, G, oracle_mod, env, monkeypatc
     idx.close()
 
 
-# ---- prototype flags (the -DPGEMB_PROTO build) through the whole emulated library -----------------------------------
-def test_product_build_ignores_prototype_flags(pg, G, oracle_mod, monkeypatch):
-    """The product library has no prototype code: the opt-in flags change nothing (same results, same version string)."""
-    from pg_embedding_b200 import _lib
-    assert b"+proto" not in _lib.load().pgemb_version()
-    for k, v in {"PGEMB_VISITED_PAIRS": "1", "PGEMB_SMEM_VISITED": "1024", "PGEMB_L2_TPR8": "1", "PGEMB_L2_TPR8_MIN_BYTES": "0", "PGEMB_SCAN_TILED": "1"}.items():
+# ---- the variants measured in round 2 (flags now default on; every flag value must give the oracle's result) ----------------
+def test_flags_off_give_the_same_results(pg, G, oracle_mod, monkeypatch):
+    for k, v in {"PGEMB_VISITED_PAIRS": "0", "PGEMB_SMEM_VISITED": "0", "PGEMB_L2_TPR8": "0", "PGEMB_SCAN_TILED": "0", "PGEMB_FAST_SMALL": "0",
+                 "PGEMB_EXACT_CLAMP_SMS": "0", "PGEMB_SCAN_TC": "0"}.items():
         monkeypatch.setenv(k, v)
     G.test_search_identical_to_oracle(pg, oracle_mod, "l2", G.SEARCH_CFGS[3])
     G.test_scan_topk_regress_seqscan(pg)
@@ -216,9 +205,9 @@ def test_prototype_traversal_flags(pg_proto, G, P, oracle_mod, flags, monkeypatc
 
 
 @pytest.mark.parametrize("metric", ["l2", "cosine", "manhattan"])
-def test_prototype_tiled_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
+def test_tiled_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
     pg = pg_proto
-    monkeypatch.setenv("PGEMB_SCAN_TILED", "1")
+    monkeypatch.setenv("PGEMB_SCAN_TC", "0")
     G.test_scan_topk_regress_seqscan(pg)
     rng = np.random.default_rng(3)
     for dims, n, k in ((33, 700, 20), (100, 300, 5)):
@@ -277,76 +266,49 @@ def test_prototype_fast_small_batches(pg_proto, G, oracle_mod, monkeypatch):
         idx.close()
 
 
-def test_prototype_ldgsts_gather(pg_proto, G, oracle_mod, monkeypatch):
-    """PGEMB_GATHER_LDGSTS=1 through the library: searches (both kernel modes) and inserts unchanged."""
-    monkeypatch.setenv("PGEMB_GATHER_LDGSTS", "1")
-    G.test_search_identical_to_oracle(pg_proto, oracle_mod, "cosine", G.SEARCH_CFGS[3])
-    G.test_search_identical_to_oracle(pg_proto, oracle_mod, "l2", G.SEARCH_CFGS[0])
-    G.test_bind_links_identical_to_oracle(pg_proto, oracle_mod, "manhattan", G.BIND_CFGS[0])
-
-
-def _proto_counters(pg):
-    from pg_embedding_b200 import _lib
-    out = (C.c_uint64 * 4)()
-    _lib.load().pgemb_proto_counters(out)
-    return dict(scans=out[0], fallbacks=out[1], rescored=out[2], pairs=out[3])
+@pytest.fixture(scope="module")
+def U():
+    import test_gpu_scan_umma as u     # GPU tests of the tensor-core scan path: bodies reused below
+    return u
 
 
 @pytest.mark.parametrize("metric", ["l2", "cosine"])
-def test_prototype_tensor_core_filter_scan(pg_proto, G, oracle_mod, metric, monkeypatch):
-    """PGEMB_SCAN_TC=1: a reduced-precision GEMM only DISCARDS rows, survivors are re-scored exactly -> the exact scan's
-    labels, order and bits.  The stand-in GEMM perturbs every dot product by +-90 % of the error bound the filter assumes
-    (adversarial but legal); with an error of 3x the bound the tripwire must fire and the exact path must take over."""
-    pg = pg_proto
+def test_tensor_core_filter_scan(pg, G, U, oracle_mod, metric, monkeypatch):
+    """K6 on the host: the filter predicate, the chunk orchestration, candidate lists and the re-scoring kernel run as compiled;
+    only the tcgen05 product itself is replaced by a TF32-truncated host product that is additionally pushed by +-90 % of the
+    error bound the filter assumes (adversarial but legal).  A product 4x outside the bound must trip the tripwire and the exact
+    kernels must take over."""
+    for case in ((33, 900, 20, 9), (100, 400, 5, 9), (16, 300, 64, 7), (3, 40, 64, 5)):
+        U.check_scan_equals_exact(pg, oracle_mod, metric, case, monkeypatch)
+    U.check_scan_overflow_and_chunks(pg, oracle_mod, metric, monkeypatch, n=700, dims=10)
+    dims, n, k = 33, 900, 20
     rng = np.random.default_rng(17)
-    cases = []
-    for dims, n, k in ((33, 900, 20), (100, 400, 5), (16, 300, 64)):
-        c = rng.standard_normal((12, dims)).astype(np.float32)
-        x = (c[rng.integers(0, 12, n)] + 0.15 * rng.standard_normal((n, dims))).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
-        x[n // 2] = x[n // 3]                                  # an exact tie: ordered by label
-        q = (c[rng.integers(0, 12, 9)] + 0.15 * rng.standard_normal((9, dims))).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
-        labels = rng.permutation(n).astype(np.uint64) + np.uint64(9)
-        labels[::7] |= np.uint64(1 << 48)                      # deleted rows are skipped
-        cases.append((dims, n, k, x, q, labels))
-    bound_ppm = lambda dims: 1.5 * (2.0 / 1024.0 + dims / 8388608.0) * 1e6
-    for dims, n, k, x, q, labels in cases:
-        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
-        idx.append(x, labels)
-        monkeypatch.setenv("PGEMB_SCAN_TC", "0")
-        want = idx.scan_topk(q, k)
-        for i in range(q.shape[0]):                              # the exact path itself against the oracle's distances
-            d = oracle_mod.dist_many("port", metric, q[i], x)
-            order = sorted((float(d[j]), int(labels[j])) for j in range(n) if not (int(labels[j]) >> 48) & 1)[:k]
-            assert want["labels"][i, :len(order)].tolist() == [o[1] for o in order]
-        c0 = _proto_counters(pg)
-        monkeypatch.setenv("PGEMB_SCAN_TC", "1")
-        for err_frac in (0.0, 0.9):
-            monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", str(err_frac * bound_ppm(dims) / 1.5))   # fraction of the un-slacked bound
-            got = idx.scan_topk(q, k)
-            assert got["labels"].tobytes() == want["labels"].tobytes(), (metric, dims, err_frac)
-            assert got["dists"].tobytes() == want["dists"].tobytes() and got["n"].tolist() == want["n"].tolist()
-        c1 = _proto_counters(pg)
-        assert c1["scans"] - c0["scans"] == 2 and c1["fallbacks"] == c0["fallbacks"]
-        # several chunks per scan: the running top-k (the filter's threshold) carries over from chunk to chunk
-        monkeypatch.setenv("PGEMB_SCAN_CHUNK_LOG2", "8")
-        got = idx.scan_topk(q, k)
-        assert got["labels"].tobytes() == want["labels"].tobytes() and got["dists"].tobytes() == want["dists"].tobytes()
-        monkeypatch.delenv("PGEMB_SCAN_CHUNK_LOG2")
-        c1 = _proto_counters(pg)
-        frac = (c1["rescored"] - c0["rescored"]) / (c1["pairs"] - c0["pairs"])
-        print(f"tc filter {metric} dims={dims} n={n} k={k}: {frac:.3f} of the pairs re-scored exactly")
-        if k * 20 <= n:
-            assert frac < 0.5, "the filter discarded almost nothing"
-        # a GEMM that is worse than assumed: detected, exact path takes over, results still right
-        monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", str(4.0 * bound_ppm(dims)))
-        got = idx.scan_topk(q, k)
-        assert got["labels"].tobytes() == want["labels"].tobytes()
-        assert _proto_counters(pg)["fallbacks"] == c1["fallbacks"] + 1
-        monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", "0")
-        idx.close()
-    # manhattan has no bilinear form: the flag is ignored
+    c = rng.standard_normal((12, dims)).astype(np.float32)
+    shift = 1.0 if metric == "cosine" else 0.0
+    x = (c[rng.integers(0, 12, n)] + 0.15 * rng.standard_normal((n, dims))).astype(np.float32) + shift
+    q = (c[rng.integers(0, 12, 9)] + 0.15 * rng.standard_normal((9, dims))).astype(np.float32) + shift
+    idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
+    idx.append(x)
+    monkeypatch.setenv("PGEMB_SCAN_TC", "0")
+    want = idx.scan_topk(q, k)
+    monkeypatch.setenv("PGEMB_SCAN_TC", "2")
+    bound_ppm = U.rel_bound(dims) / 1.5 * 1e6
+    c0 = U.counters()
+    monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", str(0.9 * bound_ppm))
+    got = idx.scan_topk(q, k)
+    assert got["labels"].tobytes() == want["labels"].tobytes() and got["dists"].tobytes() == want["dists"].tobytes()
+    c1 = U.counters()
+    assert c1["tc"] == c0["tc"] + 1 and c1["fallbacks"] == c0["fallbacks"]
+    assert (c1["rescored"] - c0["rescored"]) < 0.5 * (c1["pairs"] - c0["pairs"]), "the filter discarded almost nothing"
+    monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", str(4.0 * 1.5 * bound_ppm))
+    got = idx.scan_topk(q, k)
+    assert got["labels"].tobytes() == want["labels"].tobytes() and got["dists"].tobytes() == want["dists"].tobytes()
+    assert U.counters()["fallbacks"] == c1["fallbacks"] + 1
+    monkeypatch.setenv("PGEMB_EMU_GEMM_ERR_PPM", "0")
+    idx.close()
     if metric == "l2":
-        G.test_scan_topk_regress_seqscan(pg)
+        U.test_scan_umma_l2_norm_cache_follows_appends(pg, oracle_mod, monkeypatch)
+        U.test_scan_umma_default_policy(pg, monkeypatch)
 
 
 def test_prototype_l2_eight_lanes(pg_proto, G, oracle_mod, monkeypatch):
@@ -355,3 +317,79 @@ def test_prototype_l2_eight_lanes(pg_proto, G, oracle_mod, monkeypatch):
     monkeypatch.setenv("PGEMB_L2_TPR8_MIN_BYTES", "0")     # the small test rows too
     G.test_search_identical_to_oracle(pg, oracle_mod, "l2", G.SEARCH_CFGS[3])
     G.test_bind_links_identical_to_oracle(pg, oracle_mod, "l2", G.BIND_CFGS[0])
+
+
+def test_peer_memory_exchange_two_shards(pg, oracle_mod):
+    """K5 without a collective (pgemb_exchange_*): two id-range shards in one process (same_process attach), three steps so that both
+    result parities and the flag sequence are used.  Every rank's merged answer == the reference per shard + a (dist,label)
+    merge on the CPU; the packed single-buffer merge (what ONE all-gather delivers) gives the same bytes."""
+    from pg_embedding_b200 import _lib, sharded
+    lib = _lib.load()
+    rng = np.random.default_rng(12)
+    n, dims, m, efc, ef, nq, world = 600, 12, 5, 20, 16, 23, 2
+    x = rng.integers(0, 4, (n, dims)).astype(np.float32)            # ties across shards: the merge order is (dist,label)
+    bounds = sharded.shard_bounds(n, world)
+    idxs, orcs, exs = [], [], []
+    for r, (lo, hi) in enumerate(bounds):
+        labels = np.arange(lo, hi, dtype=np.uint64)
+        orc = oracle_mod.FlatIndex("port", dims, m, efc, ef, "l2", capacity=hi - lo)
+        orc.build(x[lo:hi], labels)
+        idx = pg.HnswIndex(dims, m, efc, ef, "l2", capacity=hi - lo)
+        idx.append(x[lo:hi], labels, orc.links())
+        ex = C.c_void_p()
+        _lib.check(lib.pgemb_exchange_create(0, r, world, 64, ef, C.byref(ex)))
+        idxs.append(idx); orcs.append(orc); exs.append(ex)
+    handles = (C.c_char * (64 * world))()
+    for r in range(world):
+        C.memmove(C.addressof(handles) + 64 * r, C.byref(C.c_void_p(lib.pgemb_exchange_buffer(exs[r]))), 8)
+    for r in range(world):
+        _lib.check(lib.pgemb_exchange_attach(exs[r], handles, 1))
+    for step in range(3):
+        q = rng.integers(0, 4, (nq - step, dims)).astype(np.float32)
+        nqs = q.shape[0]
+        for r in range(world):
+            _lib.check(lib.pgemb_sharded_search_device(idxs[r].dev, exs[r], nqs, q.ctypes.data_as(C.c_void_p), ef, None))
+        want = []
+        for i in range(nqs):
+            pairs = []
+            for r in range(world):
+                res = orcs[r].search(q[i], ef)
+                d = oracle_mod.dist_many("port", "l2", q[i], x[res.astype(np.int64)])
+                pairs += list(zip(d.tolist(), res.tolist()))
+            want.append(sorted(pairs)[:ef])
+        outs = []
+        for r in range(world):
+            ol = np.zeros((nqs, ef), np.uint64); od = np.zeros((nqs, ef), np.float32); on = np.zeros(nqs, np.int32)
+            _lib.check(lib.pgemb_sharded_merge_device(exs[r], nqs, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p), None))
+            assert lib.pgemb_exchange_error(exs[r]) == 0
+            for i in range(nqs):
+                assert on[i] == len(want[i]) and ol[i, :on[i]].tolist() == [w[1] for w in want[i]], (step, r, i)
+                assert od[i, :on[i]].tobytes() == np.array([w[0] for w in want[i]], np.float32).tobytes()
+            outs.append((ol, od, on))
+        assert outs[0][0].tobytes() == outs[1][0].tobytes()
+        # the packed layout of ONE all-gather: [shard][labels | dists | counts]
+        nbytes = int(lib.pgemb_packed_topk_bytes(nqs, ef))
+        stride = (nbytes + 7) & ~7                 # every shard's block starts 8-byte aligned (u64 labels first)
+        packed = np.zeros(world * stride, np.uint8)
+        for r in range(world):
+            o = idxs[r].search_batch(q, ef)
+            lab, dd = o["labels"].copy(), o["dists"].copy()
+            for i in range(nqs):                       # the device search pads with ~0 / +inf beyond n: same as the exchange area
+                lab[i, o["n"][i]:] = np.uint64(0xFFFFFFFFFFFFFFFF); dd[i, o["n"][i]:] = np.inf
+            packed[r * stride:r * stride + nbytes] = np.concatenate([lab.view(np.uint8).ravel(), dd.view(np.uint8).ravel(), o["n"].astype(np.int32).view(np.uint8).ravel()])
+        ol = np.zeros((nqs, ef), np.uint64); od = np.zeros((nqs, ef), np.float32); on = np.zeros(nqs, np.int32)
+        _lib.check(lib.pgemb_merge_topk_packed_device(nqs, world, ef, packed.ctypes.data_as(C.c_void_p), stride, od.ctypes.data_as(C.c_void_p),
+                                                      ol.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p), None))
+        assert ol.tobytes() == outs[0][0].tobytes() and od.tobytes() == outs[0][1].tobytes() and on.tolist() == outs[0][2].tolist()
+    # a merge whose peer never searched must give up and flag it, not hang
+    _lib.check(lib.pgemb_sharded_search_device(idxs[0].dev, exs[0], nq, q.ctypes.data_as(C.c_void_p) if nq <= q.shape[0] else rng.integers(0, 4, (nq, dims)).astype(np.float32).ctypes.data_as(C.c_void_p), ef, None))
+    for r in range(world):
+        lib.pgemb_exchange_destroy(exs[r]); idxs[r].close(); orcs[r].close()
+
+
+def test_ef_beyond_shared_memory(pg, G, oracle_mod, monkeypatch):
+    """ef = 20000 through the library on the host: launch_search must fall back to the global-memory result queues by itself;
+    PGEMB_RES_GLOBAL=1 forces that variant for ordinary searches too."""
+    G.check_ef_beyond_shared_memory(pg, oracle_mod, 12, 300, (20000, 64))
+    monkeypatch.setenv("PGEMB_RES_GLOBAL", "1")
+    G.test_search_identical_to_oracle(pg, oracle_mod, "manhattan", G.SEARCH_CFGS[3])

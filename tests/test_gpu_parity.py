@@ -310,20 +310,74 @@ def test_bulk_build_valid_graph_and_recall(pg, oracle_mod):
 # ---------------------------------------------------------------------------------------------------
 # f2: scan iteration semantics (efSearch doubling, embedding.c:322-366)
 # ---------------------------------------------------------------------------------------------------
-def test_scan_doubles_efsearch(pg, oracle_mod):
-    rng = np.random.default_rng(2)
-    n, dims = 500, 8
+SCAN_ITER_CFGS = [
+    # dims, m, efC, n, data kwargs, efsearch, limit, deleted stride
+    (8, 6, 24, 500, {}, 4, 60, 0),                       # doubling 4 -> 8 -> ... until the LIMIT is served
+    (3, 3, 16, 300, {"levels": 3}, 2, None, 5),          # tie-heavy integer grid + deleted labels, scan to exhaustion
+    (16, 4, 20, 700, {"dup_frac": 0.3}, 5, None, 0),     # duplicates; scan to exhaustion (n < efSearch ends it)
+    (24, 5, 16, 64, {}, 64, None, 3),                    # first search already returns everything (n < efSearch)
+]
+
+
+@pytest.mark.parametrize("cfg", SCAN_ITER_CFGS, ids=[f"d{c[0]}n{c[3]}ef{c[5]}" for c in SCAN_ITER_CFGS])
+def test_index_scan_iteration_equals_reference_loop(pg, oracle_mod, cfg):
+    """hnsw_gettuple's loop (embedding.c:285-370) at the C ABI (pgemb_index_scan_*) against its restatement in oracle/scan_iter.c
+    driving the checker's hnsw_search: same TIDs in the same order -- doubling, the count comparison of :338, qsort + bsearch
+    de-duplication over a growing range (duplicates a probe misses are handed out twice by the reference, hence here too), deleted
+    labels, the end-of-scan rule -- and the same number of searches.  TIDs use both 16-bit halves of the block number so that
+    ItemPointerCompare's order differs from the numeric order of the label."""
+    dims, m, efc, n, kw, efs, limit, del_stride = cfg
+    rng = np.random.default_rng(1000 + dims + n)
+    x = _data(rng, n, dims, **kw)
+    # label = TID: block number spread over bi_hi / bi_lo, small offsets (several rows per page)
+    blocks = rng.permutation(n * 3)[:n].astype(np.uint64) * np.uint64(977)
+    labels = np.array([tid_label(int(b) & 0xffffffff, 1 + i % 7) for i, b in enumerate(blocks)], dtype=np.uint64)
+    if del_stride:
+        labels[::del_stride] |= np.uint64(1 << 48)
+    for which in checkers(oracle_mod):
+        orc = oracle_mod.FlatIndex(which, dims, m, efc, efs, "l2", capacity=n)
+        orc.build(x, labels)
+        idx = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=n)
+        idx.append(x, labels, orc.links())
+        for qi in range(6):
+            q = x[(qi * 37) % n] + np.float32(0.01 * qi)
+            want = orc.scan(q, efs, limit)
+            got = np.array(list(idx.scan(q, limit=limit)), dtype=np.uint64)
+            assert got.tolist() == want["tids"].tolist(), (which, cfg, qi)
+            assert idx.last_scan["searches"] == want["searches"] and idx.last_scan["ef"] == want["ef"]
+            got_b = np.array(list(idx.scan(q, limit=limit, batch=7)), dtype=np.uint64)
+            assert got_b.tolist() == got.tolist()
+        assert idx.efsearch == efs                      # the doubled efSearch is the scan's own copy (embedding.c:254)
+        idx.close()
+        orc.close()
+
+
+def check_ef_beyond_shared_memory(pg, oracle_mod, dims, n, efs):
+    rng = np.random.default_rng(404)
+    m, efc = 8, 40
     x = _data(rng, n, dims)
-    idx = pg.HnswIndex(dims, 6, 24, 4, "l2", capacity=n)
-    idx.insert_many(x)
-    q = x[17] + 0.01
-    got = []
-    for lab in idx.scan(q, limit=40):
-        got.append(int(lab))
-    assert len(got) == 40 and len(set(got)) == 40
-    assert got[:4] == idx.search(q, 4).tolist()
-    assert idx.efsearch == 4  # restored
+    q = _data(rng, 5, dims)
+    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, "cosine", capacity=n)
+    orc.build(x + 1.0)
+    idx = pg.HnswIndex(dims, m, efc, 64, "cosine", capacity=n)
+    idx.append(x + 1.0, orc.labels(), orc.links())
+    for ef in efs:
+        out = idx.search_batch(q + 1.0, ef, want_stats=True)
+        want = orc.search_many(q + 1.0, ef, want_counters=True)
+        assert out["n"].tolist() == want["n"].tolist(), ef
+        assert out["labels"].tobytes() == want["labels"].tobytes(), ef
+        assert out["stats"][:, :3].tolist() == want["counters"][:, :3].tolist(), ef
+    # and the scan that gets there by doubling: every node comes back exactly as the reference loop returns them
+    want = orc.scan(q[0] + 1.0, 4096, None)
+    got = list(idx.scan(q[0] + 1.0, efsearch=4096))
+    assert got == want["tids"].tolist() and idx.last_scan["ef"] == want["ef"]
     idx.close()
+
+
+def test_ef_beyond_shared_memory(pg, oracle_mod):
+    """The reference doubles efSearch without bound (embedding.c:334): when 2 x ef keys no longer fit a CTA's shared memory
+    (ef > ~12.6 K at 768-d) the traversal runs with its result queues in global memory -- same labels and counters as the oracle."""
+    check_ef_beyond_shared_memory(pg, oracle_mod, 768, 3000, (20000, 13000, 64))
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -1,5 +1,11 @@
-"""2-GPU test of the sharded path: id-range shards, one NCCL all-gather of per-shard
-top-k, merge kernel; checked against the oracle run per shard + the same merge on CPU.  Skipped on 1 GPU."""
+"""Multi-GPU tests of the sharded path: id-range shards with independent graphs, checked against
+"the reference per shard + a (dist,label) merge on the CPU".  Both exchanges must give that answer, bit for bit:
+
+* `ShardedSearch`  -- ONE NCCL all-gather of the packed per-shard results + the merge kernel;
+* `PeerExchange`   -- no collective: peers' lists read over NVLink by the wait+merge kernel (CUDA-IPC mapped buffers).
+
+Parametrised over world in {2, 4, 8}; a box with fewer GPUs skips the larger ones (bench.py's sharded leg covers them in
+the driver's scaling run)."""
 import os
 import socket
 import sys
@@ -9,10 +15,19 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = dict(n=6000, dims=64, m=8, efc=48, ef=32, nq=256, steps=3)
 
 
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _inputs():
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((CFG["n"], CFG["dims"])).astype(np.float32)
+    x[100:160] = x[4000:4060]                                  # duplicates across shards: ties are ordered by label
+    qs = [rng.standard_normal((CFG["nq"] - 7 * s, CFG["dims"])).astype(np.float32) for s in range(CFG["steps"])]
+    return x, qs
 
 
 def _worker(rank, world, port, out_dir):
@@ -24,46 +39,58 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     import pg_embedding_b200 as pg
     from pg_embedding_b200 import sharded
-    rng = np.random.default_rng(11)
-    n, dims, m, efc, ef, nq = 6000, 64, 8, 48, 32, 256
-    x = rng.standard_normal((n, dims)).astype(np.float32)
-    q = rng.standard_normal((nq, dims)).astype(np.float32)
-    lo, hi = sharded.shard_bounds(n, world)[rank]
-    idx = pg.HnswIndex(dims, m, efc, ef, "l2", capacity=hi - lo, device=rank)
+    x, qs = _inputs()
+    lo, hi = sharded.shard_bounds(CFG["n"], world)[rank]
+    idx = pg.HnswIndex(CFG["dims"], CFG["m"], CFG["efc"], CFG["ef"], "l2", capacity=hi - lo, device=rank)
     idx.append(x[lo:hi], np.arange(lo, hi, dtype=np.uint64))       # labels = global ids
     idx.build_appended(0, hi - lo, 1)                              # exact sequential build of the shard
-    s = sharded.ShardedSearch(sharded.gpu_local_search(idx), sharded.gpu_merge())
-    od, ol, on = s.search(torch.from_numpy(q).cuda(), ef)
-    torch.cuda.synchronize()
-    np.save(os.path.join(out_dir, f"r{rank}.npy"), {"ol": ol.cpu().numpy(), "on": on.cpu().numpy(), "od": od.cpu().numpy()}, allow_pickle=True)
-    dist.barrier(); dist.destroy_process_group()
+    nccl = sharded.ShardedSearch(sharded.gpu_local_search_packed(idx), sharded.gpu_merge_packed())
+    peer = sharded.PeerExchange(idx, CFG["nq"], CFG["ef"])
+    res = {}
+    for s, q in enumerate(qs):                                     # several steps: both result parities, varying nq
+        qd = torch.from_numpy(q).cuda()
+        od, ol, on = nccl.search(qd, CFG["ef"])
+        pd, pl, pn = peer.search(qd, CFG["ef"])
+        torch.cuda.synchronize()
+        assert peer.error() == 0
+        res[s] = {"ol": ol.cpu().numpy(), "on": on.cpu().numpy(), "od": od.cpu().numpy(), "pl": pl.cpu().numpy(), "pn": pn.cpu().numpy(),
+                  "pd": pd.cpu().numpy(), "merge_ms": peer.merge_ms()}
+    assert nccl.collectives == len(qs)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), res, allow_pickle=True)
+    dist.barrier(); peer.close(); dist.destroy_process_group()
 
 
-def test_sharded_two_gpus(tmp_path, oracle_mod):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_search_both_exchanges(tmp_path, oracle_mod, world):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from pg_embedding_b200 import sharded
-    world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     res = [np.load(tmp_path / f"r{r}.npy", allow_pickle=True).item() for r in range(world)]
-    assert (res[0]["ol"] == res[1]["ol"]).all()
-    rng = np.random.default_rng(11)
-    n, dims, m, efc, ef, nq = 6000, 64, 8, 48, 32, 256
-    x = rng.standard_normal((n, dims)).astype(np.float32)
-    q = rng.standard_normal((nq, dims)).astype(np.float32)
-    pairs = [[] for _ in range(nq)]
-    for lo, hi in sharded.shard_bounds(n, world):
-        sh = oracle_mod.FlatIndex("port", dims, m, efc, ef, "l2", capacity=hi - lo)
+    x, qs = _inputs()
+    ef = CFG["ef"]
+    shards = []
+    for lo, hi in sharded.shard_bounds(CFG["n"], world):
+        sh = oracle_mod.FlatIndex("port", CFG["dims"], CFG["m"], CFG["efc"], ef, "l2", capacity=hi - lo)
         sh.build(x[lo:hi], np.arange(lo, hi, dtype=np.uint64))
-        r = sh.search_many(q, ef)
+        shards.append(sh)
+    for s, q in enumerate(qs):
+        nq = q.shape[0]
+        pairs = [[] for _ in range(nq)]
+        for sh in shards:
+            r = sh.search_many(q, ef)
+            for i in range(nq):
+                c = int(r["n"][i]); labs = r["labels"][i, :c].astype(np.int64)
+                dd = oracle_mod.dist_many("port", "l2", q[i], x[labs])
+                pairs[i] += list(zip(dd.tolist(), labs.tolist()))
+        for rk in range(world):                                    # every rank ends with the same merged answer, both ways
+            a = res[rk][s]
+            assert a["ol"].tobytes() == res[0][s]["ol"].tobytes() and a["pl"].tobytes() == a["ol"].tobytes()
+            assert a["pd"].tobytes() == a["od"].tobytes() and a["pn"].tolist() == a["on"].tolist()
         for i in range(nq):
-            c = int(r["n"][i]); labs = r["labels"][i, :c].astype(np.int64)
-            dd = oracle_mod.dist_many("port", "l2", q[i], x[labs])
-            pairs[i] += list(zip(dd.tolist(), labs.tolist()))
-    for i in range(nq):
-        want = sorted(pairs[i])[:ef]
-        assert res[0]["on"][i] == len(want)
-        assert res[0]["ol"][i, :len(want)].tolist() == [w[1] for w in want]
-        assert np.array([w[0] for w in want], np.float32).tobytes() == res[0]["od"][i, :len(want)].tobytes()
+            want = sorted(pairs[i])[:ef]
+            assert res[0][s]["on"][i] == len(want)
+            assert res[0][s]["ol"][i, :len(want)].tolist() == [w[1] for w in want]
+            assert np.array([w[0] for w in want], np.float32).tobytes() == res[0][s]["od"][i, :len(want)].tobytes()

@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic in pg_embedding_b200/sharded.py:
-id-range partition, query split, the single all-gather exchange and its [shard][query][k] layout.
+id-range partition, query split, the packed per-rank result buffer and the ONE all-gather that exchanges it.
 The local search and the merge are injected: here they are the ORACLE (reference per shard, SURVEY.md
 section 8(e) "the oracle for sharded configs") and a numpy merge, so no compute runs in the product."""
 import os
@@ -62,11 +62,13 @@ def _worker(rank, world, port, out_dir):
                 d[i, :c] = oracle.dist_many("port", "l2", queries[i].numpy(), x[r["labels"][i, :c].astype(np.int64)])
         return torch.from_numpy(d), torch.from_numpy(lab.copy()), torch.from_numpy(r["n"].copy())
 
-    def merge(D, L, N, k):
+    def merge(buf, world_, nq_, k):
+        D, L, N = sharded.unpack_topk(buf, world_, nq_, k)
         return merge_topk_numpy(D.numpy(), L.numpy(), N.numpy(), k)
 
     s = sharded.ShardedSearch(local_search, merge)
     od, ol, on = s.search(torch.from_numpy(q), ef)
+    assert s.collectives == 1                                     # one all-gather per step, nothing else
     # replica mode: query split covers the batch exactly once
     a, b = sharded.split_queries(nq, world, rank)
     np.save(os.path.join(out_dir, f"r{rank}.npy"), {"od": od, "ol": ol, "on": on, "split": (a, b)}, allow_pickle=True)

@@ -38,14 +38,11 @@ say "exact scan: per-pair kernel vs tiled (64 queries x 1M rows)"
 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TILED=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 say "exact scan through the tensor-core filter (PGEMB_SCAN_TC=1), 64 and 1024 queries x 1M rows"
-PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TC=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 64 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_SCAN_TC=1 timeout 600 python tools/bench_shapes.py --dims 768 --n 1000000 --metric cosine --m 32 --steps 2 --scan-queries 1024 2>&1 | tail -1 | cut -c1-400 | tee -a $L
 say "sidecar: one-query-per-call hnsw_search from 1..128 backend processes (tools/bench_sidecar.py)"
-timeout 900 python tools/bench_sidecar.py --backends 1,16,64,128 --seconds 4 2> gpurun_out/r2_sidecar.err | tee -a $L
+timeout 900 python tools/bench_sidecar.py --backends 1,64 --seconds 3 2> gpurun_out/r2_sidecar.err | tee -a $L
 say "exact parallel build, steady state at N~1M (20K exact inserts after a bulk-built prefix): default vs batch clamp"
 PGEMB_LIB_VARIANT=proto timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
 PGEMB_LIB_VARIANT=proto PGEMB_EXACT_CLAMP_SMS=1 timeout 600 python tools/bench_build.py --n 1000000 --bulk-first 980000 --bmax 1024 2>&1 | tail -1 | cut -c1-300 | tee -a $L
 say "sidecar over the prototype library: single-stream small batches + shared-memory visited set"
-PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 timeout 900 python tools/bench_sidecar.py --lib pg_embedding_b200/libpgemb_b200_proto.so --backends 1,16 --seconds 4 2>> gpurun_out/r2_sidecar.err | tee -a $L
-say "sidecar, one backend that polls for the whole search instead of sleeping (PGEMB_CLIENT_SPIN_US=1000)"
-PGEMB_CLIENT_SPIN_US=1000 timeout 600 python tools/bench_sidecar.py --backends 1,4 --seconds 3 2>> gpurun_out/r2_sidecar.err | tee -a $L
+PGEMB_FAST_SMALL=1 PGEMB_SMEM_VISITED=4096 timeout 900 python tools/bench_sidecar.py --lib pg_embedding_b200/libpgemb_b200_proto.so --backends 1 --seconds 3 2>> gpurun_out/r2_sidecar.err | tee -a $L
