@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
 			const uint32_t valid = min(kUmmaTR, p.nr - row_rel0);				 // rows of this tile inside the chunk
 			const uint32_t q = qt * kUmmaTQ + quarter * 32u + lane;
 			const bool	   q_ok = q < p.nq;
-			const float2   qc = q_ok ? p.qconst[q] : make_float2(0.f, 0.f);
+			const float2   qc = (q_ok && p.dbg_s == nullptr) ? p.qconst[q] : make_float2(0.f, 0.f);
 			// row constants of the tile -> shared memory (2 rows per thread), overlapping the MMAs of this tile
 			float2 *rc = rc_s + as * kUmmaTR;
 			for (uint32_t c = et; c < kUmmaTR; c += 128u) rc[c] = (c < valid) ? filter_rconst<METRIC>(p.vnorm2[p.r0 + row_rel0 + c]) : make_float2(0.f, 0.f);

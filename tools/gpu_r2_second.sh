@@ -29,3 +29,5 @@ say "latency (hnsw_search, one query per call)"
 timeout 600 python tools/bench_latency.py 2>&1 | tail -1 | tee -a $L
 say "1536-d L2 shape (8 lanes per row now default)"
 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c1-500 | tee -a $L
+say "gather ceiling probe (random 3 KB row gathers, no dependency chain): UBLKCP vs UTMALDG gather4"
+for cfg in "0 8 1" "0 4 2" "0 6 1" "0 9 1" "2 8 1" "2 4 2" "1 8 1"; do timeout 60 tools/probe/gather_peak $cfg 2>&1 | tail -1 | tee -a $L; done
