@@ -723,6 +723,7 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.error_flag = idx->d_error;
 	apply_config(p, cfg, idx->row_f);
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
+	p.ring2 = (uint32_t) env_int("PGEMB_RING2", 0);
 	// latency mode: both 32-id halves of a link list are test-and-set concurrently (one round trip instead of two dependent
 	// ones) -- legal only when no list repeats an id, which holds for every list the bind kernels write and is checked once
 	// for lists that came from the caller.  (Throughput mode: measured slower, 0.82 vs 0.85 of the roofline -- not used there.)

@@ -374,7 +374,11 @@ __global__ void scan_rescore_kernel(const float *__restrict__ vectors, uint32_t 
 									uint32_t *__restrict__ counters)
 {
 	static_assert(METRIC == M_L2 || METRIC == M_COS, "the filter needs a bilinear form");
-	constexpr int TPR = MetricLanes<METRIC>::LANES;	 // lanes per exact pair: 8 (L2) or 4 (cosine)
+	// ONE lane per exact pair: the lane owns all 4 (cosine) / 8 (L2) accumulator chains of its candidate and reads the row with
+	// 16-byte loads, so a warp re-scores 32 candidates at once -- the loop is a chain of dependent L2/HBM round trips (24 batches of
+	// 8 loads per 768-d row), and what matters is how many rows are in flight per warp, not lanes per row.  Same chains, same
+	// order as any other TPR (dist_exact.cuh): same bits.
+	constexpr int TPR = 1;
 	constexpr int G = 32 / TPR;						 // candidates re-scored concurrently by one warp
 	__shared__ uint32_t cd[4][kScanCand];
 	__shared__ uint64_t cl[4][kScanCand];
