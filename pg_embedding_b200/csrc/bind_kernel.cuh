@@ -157,8 +157,96 @@ __device__ __forceinline__ void write_list_desc(uint32_t *L, const uint64_t *key
 	if (threadIdx.x == 0) L[0] = n;
 }
 
-// ---- select: heuristic at NN = M over the search result, write the new node's own list --------------
+// The same heuristic with its operands STAGED in shared memory (select_kernel<METRIC, true>: one insert at a time, where the
+// heuristic -- not the search -- was the longest part of hnsw_bind_point: up to efConstruction sequential steps, each a chain of
+// ~24 dependent L2 round trips per 768-d distance; ncu: 3.3 ms of a 200K-row insert).  The rows of the kept set (<= NN x row_f
+// floats) stay in shared memory from the moment they are accepted, the next candidate's row is fetched by bulk TMA while the
+// current one is tested, so a step costs a few shared-memory passes.  Same pairs, same argument order, same arithmetic as
+// heuristic_block: same decisions, same bits.
+//   rows_s: [NN + 2][row_f] floats (16-byte aligned): NN kept rows, then two candidate buffers;  bars: two mbarriers.
 template <int METRIC>
+__device__ uint32_t heuristic_block_staged(const GraphView &g, const uint64_t *cand, uint32_t C, uint32_t NN, uint32_t *ord, uint64_t *kept,
+											float *rows_s, uint64_t *bars)
+{
+	constexpr int  L = MetricLanes<METRIC>::LANES;
+	constexpr int  NG = kBindThreads / L;
+	const uint32_t tid = threadIdx.x;
+	const int	   grp = tid / L, sub = tid % L;
+	const uint32_t row_b = g.row_f * 4u;
+	float		  *cbuf = rows_s + (size_t) NN * g.row_f;
+	__shared__ float kept_norm[256];  // squared norms of the kept rows (cosine), NN <= 256 checked by the caller
+	for (uint32_t i = tid; i < C; i += kBindThreads)
+	{
+		const uint32_t d = key_dist(cand[i]);
+		uint32_t	   gs = i, ge = i + 1;
+		while (gs > 0 && key_dist(cand[gs - 1]) == d) gs--;
+		while (ge < C && key_dist(cand[ge]) == d) ge++;
+		ord[gs + (ge - 1 - i)] = i;
+	}
+	if (tid == 0)
+	{
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+		fence_mbar_init();
+	}
+	__syncthreads();
+	const uint64_t pol = l2_policy_evict_last();
+	uint32_t	   par0 = 0, par1 = 0;
+	if (tid == 0 && C > 0)
+	{
+		mbar_arrive_expect_tx(&bars[0], row_b);
+		tma_load_1d(cbuf, g.vectors + (size_t) key_id(cand[ord[0]]) * g.row_f, row_b, &bars[0], pol);
+	}
+	uint32_t nkept = 0, i = 0;
+	for (; i < C && nkept < NN; i++)
+	{
+		const uint32_t b = i & 1u;
+		const uint64_t ck = cand[ord[i]];
+		const uint32_t cid = key_id(ck);
+		const float	   dq = o2f(key_dist(ck));
+		float		  *crow = cbuf + (size_t) b * g.row_f;
+		if (tid == 0 && i + 1 < C)
+		{
+			// the other buffer was last read in step i - 1 (all threads passed that step's final barrier)
+			mbar_arrive_expect_tx(&bars[b ^ 1u], row_b);
+			tma_load_1d(cbuf + (size_t) (b ^ 1u) * g.row_f, g.vectors + (size_t) key_id(cand[ord[i + 1]]) * g.row_f, row_b, &bars[b ^ 1u], pol);
+		}
+		float cn = 0.f;
+		if (METRIC == M_COS) cn = g.norms[cid];
+		if (b == 0) { mbar_wait(&bars[0], par0); par0 ^= 1u; } else { mbar_wait(&bars[1], par1); par1 ^= 1u; }
+		int bad = 0;
+		for (uint32_t base = 0; base < nkept; base += NG)
+		{
+			const uint32_t k = base + grp;
+			const uint32_t kk = k < nkept ? k : nkept - 1;
+			const float	   dd = distance_exact<METRIC, L>(rows_s + (size_t) kk * g.row_f, crow, (int) g.dim, kept_norm[kk], cn, sub);
+			if (k < nkept && dd < dq) bad = 1;
+		}
+		const int any = __syncthreads_or(bad);
+		if (!any)
+		{
+			float *dst = rows_s + (size_t) nkept * g.row_f;
+			for (uint32_t e = tid; e < g.row_f; e += kBindThreads) dst[e] = crow[e];
+			if (tid == 0)
+			{
+				kept[nkept] = ck;
+				kept_norm[nkept] = cn;
+			}
+			nkept++;
+		}
+		__syncthreads();
+	}
+	// a candidate row may still be in flight into the buffer (prefetched for a step that never ran): let it land
+	if (i < C)
+	{
+		if ((i & 1u) == 0) mbar_wait(&bars[0], par0); else mbar_wait(&bars[1], par1);
+	}
+	__syncthreads();
+	return nkept;
+}
+
+// ---- select: heuristic at NN = M over the search result, write the new node's own list --------------
+template <int METRIC, bool STAGED = false>
 __global__ void __launch_bounds__(kBindThreads) select_kernel(GraphView g, const uint32_t *__restrict__ new_ids,
 															   const uint32_t *__restrict__ cand_ids, const float *__restrict__ cand_d,
 															   const int32_t *__restrict__ cand_n, uint32_t ef,
@@ -168,6 +256,9 @@ __global__ void __launch_bounds__(kBindThreads) select_kernel(GraphView g, const
 	uint64_t	  *cand = reinterpret_cast<uint64_t *>(sm);			// ef
 	uint64_t	  *kept = cand + ef;								// max(M,1)
 	uint32_t	  *ord = reinterpret_cast<uint32_t *>(kept + (g.M ? g.M : 1));	// ef
+	// STAGED: [2 mbarriers][(M + 2) rows] behind the arrays above, 16-byte aligned (select_smem_bytes)
+	uint64_t	  *stage_bars = reinterpret_cast<uint64_t *>(sm + ((size_t) ef * 8 + (size_t) (g.M ? g.M : 1) * 8 + (size_t) ef * 4 + 15) / 16 * 16);
+	float		  *stage_rows = reinterpret_cast<float *>(stage_bars + 2);
 	const uint32_t b = blockIdx.x;
 	const uint32_t cur = new_ids[b];
 	uint64_t	  *my_pairs = pairs + (size_t) b * (g.M ? g.M : 1);
@@ -186,7 +277,7 @@ __global__ void __launch_bounds__(kBindThreads) select_kernel(GraphView g, const
 	}
 	else
 	{
-		nsel = heuristic_block<METRIC>(g, cand, C, g.M, ord, kept);
+		nsel = STAGED ? heuristic_block_staged<METRIC>(g, cand, C, g.M, ord, kept, stage_rows, stage_bars) : heuristic_block<METRIC>(g, cand, C, g.M, ord, kept);
 		sel = kept;
 	}
 	__syncthreads();
@@ -207,6 +298,14 @@ __global__ void __launch_bounds__(kBindThreads) select_kernel(GraphView g, const
 		if (s == cur) *g.error_flag = 3;  // "Connection to the same element" (hnswalg.cpp:183-184)
 		my_pairs[i] = ((uint64_t) s << 32) | (uint64_t) cur;
 	}
+}
+
+// dynamic shared memory of select_kernel: candidate keys, kept keys, scan order (+ the staged rows)
+inline size_t select_smem_bytes(size_t ef, size_t M, size_t row_f, bool staged)
+{
+	const size_t base = ef * 8 + (M ? M : 1) * 8 + ef * 4;
+	if (!staged) return base;
+	return (base + 15) / 16 * 16 + 16 + ((M ? M : 1) + 2) * row_f * 4;
 }
 
 // ---- back-links: one CTA per run of equal targets in the sorted (target,source) array ----------------

@@ -8,6 +8,7 @@
 // entry point fails with PGEMB_ERR_CUDA.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -128,6 +129,9 @@ struct pgemb_index
 	// staging for the host-pointer API
 	void  *d_stage = nullptr;
 	size_t stage_bytes = 0;
+	// pinned landing area of the small-batch host path: results + error flag arrive by truly asynchronous copies, one synchronisation
+	char  *h_land = nullptr;
+	size_t land_bytes = 0;
 	// bind workspace
 	BindWorkspace bind_ws;
 	size_t norms_n = 0;	 // rows [0, norms_n) have their squared norm in d_norms (cosine: all; L2: filled lazily by the tensor-core scan)
@@ -216,6 +220,7 @@ extern "C" void pgemb_index_destroy(pgemb_index *idx)
 	cudaFree(idx->d_counter);
 	cudaFree(idx->d_error);
 	cudaFree(idx->d_stage);
+	if (idx->h_land) cudaFreeHost(idx->h_land);
 	bind_ws_free(idx->bind_ws);
 	if (idx->stream) cudaStreamDestroy(idx->stream);
 	if (idx->s_in) cudaStreamDestroy(idx->s_in);
@@ -723,7 +728,6 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 	p.error_flag = idx->d_error;
 	apply_config(p, cfg, idx->row_f);
 	p.prefetch_links = (uint32_t) env_int("PGEMB_PREFETCH", 1);
-	p.ring2 = (uint32_t) env_int("PGEMB_RING2", 0);
 	// latency mode: both 32-id halves of a link list are test-and-set concurrently (one round trip instead of two dependent
 	// ones) -- legal only when no list repeats an id, which holds for every list the bind kernels write and is checked once
 	// for lists that came from the caller.  (Throughput mode: measured slower, 0.82 vs 0.85 of the roofline -- not used there.)
@@ -864,6 +868,33 @@ extern "C" pgemb_status pgemb_search_batch(pgemb_index *idx, size_t nq, const co
 		{
 			cudaStreamSynchronize(s);  // the caller's query buffer must not be read after we return
 			return st;
+		}
+		// the outputs are one contiguous range of the staging buffer [labels | dists | ids | counts | stats]: ONE copy into pinned
+		// memory + the 4-byte error flag, then one synchronisation (a copy into the caller's pageable buffers would block the host
+		// once per copy)
+		const size_t range = (size_t) ((char *) d_s - (char *) d_l) + up(sb);
+		if (range + 64 <= ((size_t) 4 << 20))
+		{
+			if (idx->land_bytes < range + 64)
+			{
+				if (idx->h_land) cudaFreeHost(idx->h_land);
+				idx->h_land = nullptr;
+				idx->land_bytes = 0;
+				CU_TRY(cudaMallocHost((void **) &idx->h_land, range + 64 + 65536));
+				idx->land_bytes = range + 64 + 65536;
+			}
+			int *h_err = (int *) (idx->h_land + ((range + 15) & ~(size_t) 15));
+			CU_TRY(cudaMemcpyAsync(idx->h_land, d_l, range, cudaMemcpyDeviceToHost, s));
+			CU_TRY(cudaMemcpyAsync(h_err, idx->d_error, sizeof(int), cudaMemcpyDeviceToHost, s));
+			CU_TRY(cudaStreamSynchronize(s));
+			const char *hb = idx->h_land;
+			if (labels_out) memcpy(labels_out, hb + ((char *) d_l - (char *) d_l), lb);
+			if (dists_out) memcpy(dists_out, hb + ((char *) d_d - (char *) d_l), db);
+			if (ids_out) memcpy(ids_out, hb + ((char *) d_i - (char *) d_l), ib);
+			memcpy(n_out, hb + ((char *) d_n - (char *) d_l), nb);
+			if (stats_out) memcpy(stats_out, hb + ((char *) d_s - (char *) d_l), sb);
+			if (*h_err != 0) return check_device_error(idx, s);	 // reads, reports and clears the flag
+			return PGEMB_OK;
 		}
 		if (labels_out) CU_TRY(cudaMemcpyAsync(labels_out, d_l, lb, cudaMemcpyDeviceToHost, s));
 		if (dists_out) CU_TRY(cudaMemcpyAsync(dists_out, d_d, db, cudaMemcpyDeviceToHost, s));
@@ -1202,6 +1233,11 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 	*tc_violation = false;
 	pgemb_status st = set_device(idx);
 	if (st) return st;
+	// PGEMB_SCAN_TIMING=1: host-side time line of one scan on stderr (where does a call spend its time besides the kernels)
+	const bool timing = env_int("PGEMB_SCAN_TIMING", 0) != 0;
+	const auto t_begin = std::chrono::steady_clock::now();
+	auto	   since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+	double	   t_staged = 0, t_enqueued = 0, t_synced = 0;
 	const size_t dim = idx->meta.dim;
 	const size_t N = idx->n;
 	const size_t rf = idx->row_f;
@@ -1216,7 +1252,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 		if (lg >= 8 && lg <= 20) chunk = (size_t) 1 << lg;
 	}
 	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
-	// tensor-core path: first chunk establishes the threshold (every row of it is a candidate), then x8 per chunk
+	// tensor-core path: first chunk establishes the threshold (every row of it is a candidate), then x16 per chunk (PGEMB_SCAN_TC_GROWTH)
 	size_t c0 = ((2 * k > 256 ? 2 * k : 256) + 255) / 256 * 256;
 	{
 		const int lg = env_int("PGEMB_SCAN_TC_CHUNK0_LOG2", 0);
@@ -1248,6 +1284,11 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 	if (rf != dim) CU_TRY(cudaMemsetAsync(d_q, 0, qb, s));
 	CU_TRY(cudaMemcpy2DAsync(d_q, rf * 4, queries, dim * 4, dim * 4, nq, cudaMemcpyHostToDevice, s));
 	CU_TRY(cudaMemsetAsync(d_tn, 0, nb, s));
+	if (timing)
+	{
+		cudaStreamSynchronize(s);
+		t_staged = since();
+	}
 	// tiled distance step (scan_tile_kernel.cuh): same bits as scan_dist_kernel, rows read once per query tile
 	const bool tiled = env_int("PGEMB_SCAN_TILED", 1) != 0;
 	if (tc || (tiled && metric == DIST_COSINE))
@@ -1267,6 +1308,8 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 		else PGEMB_LAUNCH(scan_qconst_init_kernel<M_COS>, (uint32_t) ((nq + 127) / 128), 128, 0, s, d_qn, (uint32_t) nq, rel, d_qc, d_cn);
 		g_launches++;
 		size_t csize = c0;
+		size_t growth = (size_t) env_int("PGEMB_SCAN_TC_GROWTH", 16);
+		if (growth < 2) growth = 2;
 		for (size_t r0 = 0; r0 < N;)
 		{
 			size_t nr = N - r0 < csize ? N - r0 : csize;
@@ -1274,7 +1317,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 			st = launch_scan_filter(idx, metric, d_q, d_qn, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, rel, d_qc, d_cr, d_cs, d_cn, (uint32_t) cap, nullptr, s);
 			if (st) return st;
 #define SCAN_RESCORE(MM)                                                                                                                          \
-	PGEMB_LAUNCH(scan_rescore_kernel<MM>, (uint32_t) ((nq + 3) / 4), 128, 0, s, idx->d_vectors, idx->row_f, (uint32_t) dim, idx->d_norms, d_q, (uint32_t) rf, d_qn,  \
+	PGEMB_LAUNCH(scan_rescore_kernel<MM>, (uint32_t) nq, 128, 0, s, idx->d_vectors, idx->row_f, (uint32_t) dim, idx->d_norms, d_q, (uint32_t) rf, d_qn,  \
 				 idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k, rel, d_cr, d_cs, d_cn, (uint32_t) cap, d_td, d_tl, d_tn, d_sd, d_sl, d_qc, d_cnt)
 			if (metric == DIST_L2) SCAN_RESCORE(M_L2);
 			else SCAN_RESCORE(M_COS);
@@ -1282,7 +1325,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 			g_launches++;
 			CU_TRY(cudaGetLastError());
 			r0 += nr;
-			csize *= 8;
+			csize *= growth;
 		}
 		g_scan_tc++;
 		g_scan_pairs += (uint64_t) nq * N;
@@ -1330,6 +1373,12 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 		cudaStreamSynchronize(s);
 		return fail(PGEMB_ERR_NOMEM, "out of host memory");  // no C++ exception crosses the C ABI
 	}
+	if (timing)
+	{
+		t_enqueued = since();
+		cudaStreamSynchronize(s);
+		t_synced = since();
+	}
 	CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
 	CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
@@ -1352,6 +1401,9 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 			if (dists_out) dists_out[q * k + i] = ok ? o2f(hd[q * k + i]) : INFINITY;
 		}
 	}
+	if (timing)
+		fprintf(stderr, "pgemb_scan_topk timing (ms): queries staged %.3f | kernels enqueued %.3f | kernels done %.3f | results copied + unpacked %.3f  (nq %zu, N %zu, %s)\n",
+				t_staged, t_enqueued, t_synced, since(), nq, N, tc ? "tensor-core filter" : "exact kernels");
 	return PGEMB_OK;
 }
 
@@ -1661,13 +1713,25 @@ static pgemb_status launch_connect(pgemb_index *idx, const uint32_t *d_new_ids, 
 	GraphView	   g = graph_view(idx);
 	const size_t   M = idx->meta.M ? idx->meta.M : 1;
 	const size_t   maxM1 = idx->meta.maxM + 1;
-	const size_t   sel_smem = ef * 8 + M * 8 + ef * 4;
+	// a handful of inserts (hnsw_bind_point: one): the heuristic with its operands staged in shared memory -- the kept rows
+	// must fit next to the key arrays (M = 32 at 768-d: 100 KB); batches keep the small-footprint kernel (many CTAs per SM)
+	const size_t   sel_staged_bytes = select_smem_bytes(ef, M, idx->row_f, true);
+	const bool	   staged = count <= 8 && M <= 256 && sel_staged_bytes <= 200 * 1024 && env_int("PGEMB_SELECT_STAGED", 1) != 0;
+	const size_t   sel_smem = staged ? sel_staged_bytes : select_smem_bytes(ef, M, idx->row_f, false);
 	const size_t   bl_smem = maxM1 * 8 * 2 + (idx->meta.maxM ? idx->meta.maxM : 1) * 8 + maxM1 * 4;
 	const int	   metric = (int) idx->meta.dist_func;
 #define LAUNCH_SELECT(MM)                                                                                                        \
 	do {                                                                                                                         \
-		if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
-		PGEMB_LAUNCH(select_kernel<MM>, (uint32_t) count, kBindThreads, sel_smem, s, g, d_new_ids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) ef, w.d_pairs); \
+		if (staged)                                                                                                              \
+		{                                                                                                                        \
+			if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
+			PGEMB_LAUNCH((select_kernel<MM, true>), (uint32_t) count, kBindThreads, sel_smem, s, g, d_new_ids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) ef, w.d_pairs); \
+		}                                                                                                                        \
+		else                                                                                                                     \
+		{                                                                                                                        \
+			if (sel_smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(select_kernel<MM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sel_smem)); \
+			PGEMB_LAUNCH(select_kernel<MM>, (uint32_t) count, kBindThreads, sel_smem, s, g, d_new_ids, w.d_cand_ids, w.d_cand_d, w.d_cand_n, (uint32_t) ef, w.d_pairs); \
+		}                                                                                                                        \
 	} while (0)
 	if (metric == DIST_L2) LAUNCH_SELECT(M_L2);
 	else if (metric == DIST_COSINE) LAUNCH_SELECT(M_COS);

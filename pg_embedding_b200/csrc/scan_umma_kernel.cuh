@@ -15,11 +15,11 @@
 //                             a (query,row) pair survives only if a RIGOROUS lower bound of its distance -- from S, the
 //                             exact squared norms and the TF32 error bound |S - q.v| <= rel |q||v| -- does not exceed the
 //                             query's current k-th best exact distance; survivors go to a per-query candidate list.
-//   scan_rescore_kernel       one warp per query: candidates are re-scored with the reference-exact arithmetic
-//                             (dist_exact.cuh) and folded into the running top-k by (dist,label), exactly like
-//                             scan_select_kernel; then the query's filter constants are refreshed for the next chunk.
+//   scan_rescore_kernel       one CTA per query: candidates are re-scored with the reference-exact arithmetic
+//                             (dist_exact.cuh, one lane per candidate) and folded into the running top-k by (dist,label),
+//                             exactly like scan_select_kernel; then the query's filter constants are refreshed for the next chunk.
 //
-// The host (capi.cu, scan_topk_impl) walks the table in geometrically growing chunks (256, 2K, 16K, ... rows): the first
+// The host (capi.cu, scan_topk_impl) walks the table in geometrically growing chunks (256, 4K, 64K, ... rows): the first
 // chunk establishes the threshold, every later chunk is filtered with the exact threshold of everything before it, so
 // ~k ln(N/k) + (rows inside the error band) candidates per query are re-scored in total.  Result = the exact path's: same
 // labels, same order, bit-identical distances (tests/test_gpu_parity.py::test_scan_umma_*).  Every re-scored candidate
@@ -360,43 +360,83 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
 #endif	// PGEMB_HOST_EMULATION
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Re-scoring + selection.  One warp per query (4 per CTA).  Input: the query's candidate list of this chunk (or, when it
-// overflowed, the whole chunk); output: the running k smallest (dist,label) pairs, the refreshed filter constants.
+// Re-scoring + selection.  One CTA (4 warps) per query.
+//   phase A  all 4 warps: every listed candidate is re-scored with the reference-exact arithmetic, ONE lane per candidate
+//            (the lane owns all accumulator chains of its pair and reads the row with 16-byte loads: 128 rows in flight per
+//            query -- the loop is a chain of dependent L2/HBM round trips, so rows in flight is what counts).  Candidates that the
+//            chunk-start threshold already excludes, and deleted rows, are skipped.  The exact distance replaces the product in
+//            the candidate list (cand_s), a dead entry gets bit 31 of its row id.  Every re-scored pair CHECKS the assumed
+//            error bound (tripwire).
+//   phase B  warp 0 folds the (dist,label) pairs into the running k smallest exactly like scan_select_kernel and refreshes the
+//            query's filter constants for the next chunk.
+// A query whose list overflowed is handled by warp 0 alone: every row of the chunk is re-scored (exact, slow, still correct).
 // counters: [0] candidates re-scored, [1] error-bound violations (tripwire), [2] queries whose list overflowed.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int METRIC>
-__global__ void scan_rescore_kernel(const float *__restrict__ vectors, uint32_t row_f, uint32_t dim, const float *__restrict__ vnorm2,
-									const float *__restrict__ queries, uint32_t q_stride, const float *__restrict__ qnorm2,
-									const uint64_t *__restrict__ labels, uint32_t nq, uint32_t r0, uint32_t nr, uint32_t k, float rel,
-									const uint32_t *__restrict__ cand_rows, const float *__restrict__ cand_s, uint32_t *__restrict__ cand_n, uint32_t cap,
-									uint32_t *__restrict__ top_d, uint64_t *__restrict__ top_l, uint32_t *__restrict__ top_n,
-									uint32_t *__restrict__ tmp_d, uint64_t *__restrict__ tmp_l, float2 *__restrict__ qconst,
-									uint32_t *__restrict__ counters)
+__global__ void __launch_bounds__(128) scan_rescore_kernel(const float *__restrict__ vectors, uint32_t row_f, uint32_t dim, const float *__restrict__ vnorm2,
+														   const float *__restrict__ queries, uint32_t q_stride, const float *__restrict__ qnorm2,
+														   const uint64_t *__restrict__ labels, uint32_t nq, uint32_t r0, uint32_t nr, uint32_t k, float rel,
+														   uint32_t *__restrict__ cand_rows, float *__restrict__ cand_s, uint32_t *__restrict__ cand_n, uint32_t cap,
+														   uint32_t *__restrict__ top_d, uint64_t *__restrict__ top_l, uint32_t *__restrict__ top_n,
+														   uint32_t *__restrict__ tmp_d, uint64_t *__restrict__ tmp_l, float2 *__restrict__ qconst,
+														   uint32_t *__restrict__ counters)
 {
 	static_assert(METRIC == M_L2 || METRIC == M_COS, "the filter needs a bilinear form");
-	// ONE lane per exact pair: the lane owns all 4 (cosine) / 8 (L2) accumulator chains of its candidate and reads the row with
-	// 16-byte loads, so a warp re-scores 32 candidates at once -- the loop is a chain of dependent L2/HBM round trips (24 batches of
-	// 8 loads per 768-d row), and what matters is how many rows are in flight per warp, not lanes per row.  Same chains, same
-	// order as any other TPR (dist_exact.cuh): same bits.
-	constexpr int TPR = 1;
-	constexpr int G = 32 / TPR;						 // candidates re-scored concurrently by one warp
-	__shared__ uint32_t cd[4][kScanCand];
-	__shared__ uint64_t cl[4][kScanCand];
+	__shared__ uint32_t cd[kScanCand];
+	__shared__ uint64_t cl[kScanCand];
 	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t q = blockIdx.x * 4 + w;
+	const uint32_t q = blockIdx.x;
 	if (q >= nq) return;
 	uint32_t *td = top_d + (size_t) q * k, *sd = tmp_d + (size_t) q * k;
 	uint64_t *tl = top_l + (size_t) q * k, *sl = tmp_l + (size_t) q * k;
 	uint32_t  n = top_n[q];
-	uint32_t  nc = 0, n_resc = 0;
-	const uint32_t lt = (1u << lane) - 1u;
-	const int	   grp = (int) lane / TPR, sub = (int) lane % TPR;
 	const float	  *qp = queries + (size_t) q * q_stride;
 	const float	   qn = qnorm2[q];
 	const uint32_t listed = cand_n[q];
 	const bool	   overflow = listed > cap;
-	const uint32_t total_in = overflow ? nr : listed;
 	float2		   qc = filter_qconst<METRIC>(qn, n < k ? INFINITY : o2f(td[k - 1]), rel);
+	uint32_t	  *crow = cand_rows + (size_t) q * cap;
+	float		  *cs = cand_s + (size_t) q * cap;
+	uint32_t	   n_resc = 0;
+
+	if (!overflow)
+	{
+		// ---- phase A ------------------------------------------------------------------------------------------------
+		for (uint32_t base = 0; base < listed; base += 128)
+		{
+			const uint32_t e = base + threadIdx.x;
+			const bool	   have = e < listed;
+			const uint32_t row = crow[have ? e : 0] & 0x7fffffffu;	// (entry 0 may already carry its dead mark; idle lanes only shadow it)
+			const float	   s = cs[have ? e : 0];
+			const float	   vn = vnorm2[row];
+			bool		   alive = have && ((labels[row] >> 48) & 1ull) == 0;
+			if (alive) alive = filter_pass<METRIC>(s, qc, filter_rconst<METRIC>(vn));
+			if (__any_sync(0xffffffffu, alive))
+			{
+				// all lanes run the same code (full-mask shuffles inside); lanes without a live candidate compute and drop
+				const float dex = distance_exact<METRIC, 1>(qp, vectors + (size_t) row * row_f, (int) dim, qn, vn, 0);
+				if (alive)
+				{
+					float approx, slack;
+					filter_approx<METRIC>(s, qn, vn, rel, &approx, &slack);
+					const float ex = (METRIC == M_COS) ? dex : dex * dex;
+					if (fabsf(ex - approx) > slack * 1.5f + 1e-6f * fabsf(ex)) atomicAdd(&counters[1], 1u);
+					cs[e] = __uint_as_float(f2o(dex));
+					n_resc++;
+				}
+			}
+			if (have && !alive) crow[e] = row | 0x80000000u;
+		}
+		__syncthreads();
+	}
+	if (w != 0)
+	{
+		if (n_resc) atomicAdd(&counters[0], n_resc);
+		return;
+	}
+	// ---- phase B (warp 0) -----------------------------------------------------------------------------------------------
+	uint32_t	   nc = 0;
+	const uint32_t lt = (1u << lane) - 1u;
 	auto less = [](uint32_t d1, uint64_t l1, uint32_t d2, uint64_t l2) { return d1 < d2 || (d1 == d2 && l1 < l2); };
 	auto merge = [&]() {
 		// rank every element of top (n) and cand (nc) in their union; keep ranks < k  (as scan_select_kernel)
@@ -405,14 +445,14 @@ __global__ void scan_rescore_kernel(const float *__restrict__ vectors, uint32_t 
 		for (uint32_t i = lane; i < total; i += 32)
 		{
 			const bool	   from_top = i < n;
-			const uint32_t d = from_top ? td[i] : cd[w][i - n];
-			const uint64_t l = from_top ? tl[i] : cl[w][i - n];
+			const uint32_t d = from_top ? td[i] : cd[i - n];
+			const uint64_t l = from_top ? tl[i] : cl[i - n];
 			uint32_t	   rank = 0;
 			for (uint32_t j = 0; j < n; j++) rank += (j != i && (less(td[j], tl[j], d, l) || (!less(d, l, td[j], tl[j]) && j < i))) ? 1u : 0u;
 			for (uint32_t j = 0; j < nc; j++)
 			{
 				const uint32_t jj = n + j;
-				rank += (jj != i && (less(cd[w][j], cl[w][j], d, l) || (!less(d, l, cd[w][j], cl[w][j]) && jj < i))) ? 1u : 0u;
+				rank += (jj != i && (less(cd[j], cl[j], d, l) || (!less(d, l, cd[j], cl[j]) && jj < i))) ? 1u : 0u;
 			}
 			if (rank < k) { sd[rank] = d; sl[rank] = l; }
 		}
@@ -421,70 +461,9 @@ __global__ void scan_rescore_kernel(const float *__restrict__ vectors, uint32_t 
 		for (uint32_t i = lane; i < n; i += 32) { td[i] = sd[i]; tl[i] = sl[i]; }
 		nc = 0;
 		__syncwarp();
-		qc = filter_qconst<METRIC>(qn, n < k ? INFINITY : o2f(td[k - 1]), rel);	 // the threshold only tightens
 	};
-	for (uint32_t base = 0; base < total_in; base += 32)
-	{
-		const uint32_t e = base + lane;
-		bool		   maybe = false;
-		uint64_t	   l = 0;
-		uint32_t	   row = 0;
-		float		   s = 0.f, vn = 0.f;
-		if (e < total_in)
-		{
-			row = overflow ? r0 + e : cand_rows[(size_t) q * cap + e];
-			l = labels[row];
-			vn = vnorm2[row];
-			if (((l >> 48) & 1ull) == 0)
-			{
-				maybe = true;
-				if (!overflow)
-				{
-					// the threshold may have tightened since the tensor-core pass: test again before paying for the exact distance
-					s = cand_s[(size_t) q * cap + e];
-					maybe = filter_pass<METRIC>(s, qc, filter_rconst<METRIC>(vn));
-				}
-			}
-		}
-		uint32_t mm = __ballot_sync(0xffffffffu, maybe);
-		if (mm == 0u) continue;
-		// ---- exact re-scoring of the candidates, G at a time, by groups of TPR lanes ---------------------------------
-		const uint32_t my_rank = __popc(mm & lt);  // rank of this lane's row among the candidates of this step
-		float		   dex = 0.f;
-		uint32_t	   done = 0;
-		n_resc += (uint32_t) __popc(mm);
-		while (mm)
-		{
-			uint32_t t = mm;
-			for (int i = 0; i < grp; i++) t &= t - 1u;	// group g takes the g-th remaining candidate
-			const bool	   have = t != 0u;
-			const int	   src_lane = have ? __ffs(t) - 1 : __ffs(mm) - 1;	// idle groups shadow the first one
-			const uint32_t prow = __shfl_sync(0xffffffffu, row, src_lane);
-			const float	   pvn = __shfl_sync(0xffffffffu, vn, src_lane);
-			const float	  *vp = vectors + (size_t) prow * row_f;
-			const float	   d = distance_exact<METRIC, TPR>(qp, vp, (int) dim, qn, pvn, sub);
-			// deliver: the lane whose row has rank r among the candidates reads group (r - done)'s result
-			const int	src = ((int) my_rank - (int) done) * TPR;
-			const float got = __shfl_sync(0xffffffffu, d, (src >= 0 && src < 32) ? src : 0);
-			if (maybe && my_rank >= done && my_rank < done + (uint32_t) G) dex = got;
-			done += (uint32_t) G;
-			for (int i = 0; i < G && mm; i++) mm &= mm - 1u;
-		}
-		bool	 take = false;
-		uint32_t d = 0;
-		if (maybe)
-		{
-			if (!overflow)
-			{
-				// tripwire: the exact value must lie within the assumed error bound of the approximation
-				float approx, slack;
-				filter_approx<METRIC>(s, qn, vn, rel, &approx, &slack);
-				const float ex = (METRIC == M_COS) ? dex : dex * dex;
-				if (fabsf(ex - approx) > slack * 1.5f + 1e-6f * fabsf(ex)) atomicAdd(&counters[1], 1u);
-			}
-			d = f2o(dex);
-			take = (n < k) || less(d, l, td[k - 1], tl[k - 1]);
-		}
+	auto offer = [&](bool have, uint32_t d, uint64_t l) {
+		const bool	   take = have && ((n < k) || less(d, l, td[k - 1], tl[k - 1]));
 		const uint32_t m = __ballot_sync(0xffffffffu, take);
 		if (m)
 		{
@@ -492,12 +471,47 @@ __global__ void scan_rescore_kernel(const float *__restrict__ vectors, uint32_t 
 			if (take)
 			{
 				const uint32_t at = nc + __popc(m & lt);
-				cd[w][at] = d;
-				cl[w][at] = l;
+				cd[at] = d;
+				cl[at] = l;
 			}
 			nc += __popc(m);
-			// the first k candidates establish the threshold: merge them at once so that the filter starts to discard
+			// the first k candidates establish the threshold: merge them at once
 			if (n < k && nc >= k) merge();
+		}
+	};
+	if (!overflow)
+	{
+		for (uint32_t base = 0; base < listed; base += 32)
+		{
+			const uint32_t e = base + lane;
+			bool		   have = e < listed;
+			uint32_t	   row = 0, d = 0;
+			uint64_t	   l = 0;
+			if (have)
+			{
+				row = crow[e];
+				have = (row & 0x80000000u) == 0u;
+				if (have)
+				{
+					d = __float_as_uint(cs[e]);
+					l = labels[row];
+				}
+			}
+			offer(have, d, l);
+		}
+	}
+	else
+	{
+		// the list overflowed: every row of the chunk, 32 at a time, one lane per row
+		for (uint32_t base = 0; base < nr; base += 32)
+		{
+			const uint32_t e = base + lane;
+			const uint32_t row = r0 + (e < nr ? e : nr - 1);
+			const uint64_t l = labels[row];
+			const bool	   have = e < nr && ((l >> 48) & 1ull) == 0;
+			const float	   dex = distance_exact<METRIC, 1>(qp, vectors + (size_t) row * row_f, (int) dim, qn, vnorm2[row], 0);
+			if (have) n_resc++;
+			offer(have, f2o(dex), l);
 		}
 	}
 	if (nc) merge();
@@ -505,10 +519,10 @@ __global__ void scan_rescore_kernel(const float *__restrict__ vectors, uint32_t 
 	{
 		top_n[q] = n;
 		cand_n[q] = 0;
-		qconst[q] = qc;
-		if (n_resc) atomicAdd(&counters[0], n_resc);
+		qconst[q] = filter_qconst<METRIC>(qn, n < k ? INFINITY : o2f(td[k - 1]), rel);
 		if (overflow) atomicAdd(&counters[2], 1u);
 	}
+	if (n_resc) atomicAdd(&counters[0], n_resc);
 }
 
 // initial filter constants (nothing selected yet: T = +inf, nothing is discarded) and empty candidate lists

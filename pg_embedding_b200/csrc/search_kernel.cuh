@@ -80,7 +80,6 @@ struct SearchParams
 	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
 	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
 	uint32_t prefetch_links;
-	uint32_t ring2;			 // throughput mode, 1: a multi-group hop takes a second ring when one is free (double-buffered gather)
 	uint32_t visited_pairs;	 // latency mode, 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
 	uint32_t off_qt, off_qtail, off_res, off_hopkey, off_acckey, off_evict, off_hopid, off_pf, off_pfbar;  // inside a slot's private block
@@ -561,55 +560,34 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				{
 				const uint32_t G = (n + kRows - 1) / kRows;
 				// ---- take a ring from the CTA's pool (held for this hop's gather only) ----------------
-				// rb: low byte = ring index, bit 8 = its barrier's phase parity; kNone = none taken (non-blocking attempt only)
-				auto take_ring = [&](bool block) -> uint32_t {
-					uint32_t got = kNone;
-					if (lane == 0)
+				uint32_t rb = 0;  // low byte: ring index, bit 8: its barrier's phase parity
+				if (lane == 0)
+				{
+					for (;;)
 					{
-						for (;;)
+						const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&pool->state);
+						if ((m & 0xffffu) != 0u)
 						{
-							const uint32_t m = *reinterpret_cast<volatile uint32_t *>(&pool->state);
-							if ((m & 0xffffu) != 0u)
+							const uint32_t b = (uint32_t) __ffs(m & 0xffffu) - 1u;
+							if (atomicCAS(&pool->state, m, m & ~(1u << b)) == m)
 							{
-								const uint32_t b = (uint32_t) __ffs(m & 0xffffu) - 1u;
-								if (atomicCAS(&pool->state, m, m & ~(1u << b)) == m)
-								{
-									got = b | (((m >> (16u + b)) & 1u) << 8);
-									break;
-								}
-							}
-							else if (!block)
+								rb = b | (((m >> (16u + b)) & 1u) << 8);
 								break;
-							else
-								__nanosleep(100);
+							}
 						}
-						__threadfence_block();
+						else
+							__nanosleep(100);
 					}
-					return __shfl_sync(kFull, got, 0);
-				};
-				auto give_ring = [&](uint32_t ring_i, uint32_t par_now, uint32_t par_taken) {
-					if (lane == 0)
-					{
-						__threadfence_block();
-						if (par_now != par_taken) atomicXor(&pool->state, 1u << (16u + ring_i));  // hand the new parity on ...
-						atomicOr(&pool->state, 1u << ring_i);									   // ... then free the ring
-					}
-				};
-				const uint32_t rbA = take_ring(true);
-				// A hop of several row groups takes a SECOND ring when one happens to be free (never waits for it): group g + 1 is
-				// then in flight while group g is scored, so the hop costs one DRAM round trip + G scorings instead of G round trips.
-				const uint32_t rbB = (p.ring2 != 0u && G > 1u) ? take_ring(false) : kNone;
-				const bool	   two = rbB != kNone;
-				// (scalars selected by `w`, not 2-element arrays: a dynamically indexed array would live in local memory)
-				uint32_t	   parA = (rbA >> 8) & 1u, parB = two ? (rbB >> 8) & 1u : 0u;
-				const uint32_t parA0 = parA, parB0 = parB;
-				const uint32_t riA = rbA & 0xffu, riB = two ? (rbB & 0xffu) : riA;
-				unsigned char *ringA = ring_base + (size_t) riA * p.ring_bytes, *ringB = ring_base + (size_t) riB * p.ring_bytes;
-				uint64_t	  *barA = &pool->bar[riA], *barB = &pool->bar[riB];
-				auto		   issue = [&](uint32_t g, bool w) {
+					__threadfence_block();
+				}
+				rb = __shfl_sync(kFull, rb, 0);
+				uint32_t rpar = (rb >> 8) & 1u;
+				rb &= 0xffu;
+				const uint32_t rpar0 = rpar;
+				unsigned char *ring = ring_base + (size_t) rb * p.ring_bytes;
+				uint64_t	  *rbar = &pool->bar[rb];
+				auto		   issue = [&](uint32_t g) {
 					  const uint32_t rows = min((uint32_t) kRows, n - g * kRows);
-					  unsigned char *ring = w ? ringB : ringA;
-					  uint64_t		*rbar = w ? barB : barA;
 					  if (lane == 0) mbar_arrive_expect_tx(rbar, rows * p.row_bytes);
 					  __syncwarp();
 					  if (lane < rows)
@@ -618,37 +596,30 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 						  tma_load_1d(ring + (size_t) lane * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, rbar, pol_stream);
 					  }
 				};
-				issue(0, false);
-				if (two) issue(1, true);
+				issue(0);
 				const float *qts = qT + sub * p.qt_stride;
 				for (uint32_t g = 0; g < G; g++)
 				{
-					const bool	   w = two && (g & 1u);
 					const uint32_t k = g * kRows + row_in_stage;
 					const uint32_t kk = min(k, n - 1);
 					const uint32_t my_id = hop_id[kk];
 					float		   vn = 1.0f;
 					if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
-					if (w)
-					{
-						mbar_wait(barB, parB);
-						parB ^= 1u;
-					}
-					else
-					{
-						mbar_wait(barA, parA);
-						parA ^= 1u;
-					}
-					const float *rowp = reinterpret_cast<const float *>((w ? ringB : ringA) + (size_t) row_in_stage * p.row_smem);
+					mbar_wait(rbar, rpar);
+					rpar ^= 1u;
+					const float *rowp = reinterpret_cast<const float *>(ring + (size_t) row_in_stage * p.row_smem);
 					const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
 					if (sub == 0 && k < n) hop_key[k] = make_key(d, my_id);
 					__syncwarp();
-					const uint32_t nxt = two ? g + 2u : g + 1u;  // the ring just scored takes the next group it is due
-					if (nxt < G) issue(nxt, w);
+					if (g + 1 < G) issue(g + 1);
 				}
-				// ---- give the ring(s) back -------------------------------------------------------------
-				give_ring(riA, parA, parA0);
-				if (two) give_ring(riB, parB, parB0);
+				// ---- give the ring back ---------------------------------------------------------------
+				if (lane == 0)
+				{
+					__threadfence_block();
+					if (rpar != rpar0) atomicXor(&pool->state, 1u << (16u + rb));  // hand the new parity on ...
+					atomicOr(&pool->state, 1u << rb);								 // ... then free the ring
+				}
 				}  // !COOP
 
 				const uint64_t *Rb = res + (size_t) cur * ef;

@@ -50,8 +50,7 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;		  // bit 31: 8 lanes per L2 row
 	const bool res_global = (smem_visited & 0x20000000u) != 0u;  // bit 29: result buffers in global memory (the huge-ef variant)
 	sh.res_global = res_global;
-	const uint32_t ring2 = (smem_visited >> 28) & 1u;  // bit 28: multi-group hops take a second ring when one is free
-	smem_visited &= 0x0fffffffu;
+	smem_visited &= 0x1fffffffu;
 	tu.smem_visited = (int) smem_visited;
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);
@@ -106,7 +105,6 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	p.error_flag = &err;
 	p.prefetch_links = 1;
 	p.visited_pairs = visited_pairs;  // used by the latency-mode kernel only
-	p.ring2 = ring2;
 	apply_config(p, cfg, row_f);
 	unsigned g = nq < grid ? nq : grid;
 	if (g == 0) g = 1;

@@ -67,7 +67,7 @@ def emu_proto(emu):
     return emu
 
 
-def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0, tpr8=False, resg=False, ring2=False):
+def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid, vh, pairs=0, smem_visited=0, tpr8=False, resg=False):
     n, dim = x.shape
     row_f = (dim + 3) & ~3
     ls = (maxm + 1 + 3) & ~3
@@ -81,7 +81,7 @@ def run_emu(lib, metric, coop, x, links, labels, q, ef, maxm, warps, rings, grid
     rc = lib.emu_search_ex(METRIC_ID[metric], coop, _p(xv, C.c_float), _p(lk, C.c_uint32), _p(labels, C.c_uint64), _p(norms, C.c_float),
                         C.c_uint32(n), C.c_uint32(dim), C.c_uint32(row_f), C.c_uint32(ls), C.c_uint32(maxm), _p(np.ascontiguousarray(q), C.c_float),
                         C.c_uint32(nq), C.c_uint32(ef), 0, _p(lab, C.c_uint64), _p(dd, C.c_float), _p(ids, C.c_uint32), _p(nn, C.c_int32),
-                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited | (0x80000000 if tpr8 else 0) | (0x20000000 if resg else 0) | (0x10000000 if ring2 else 0)), C.byref(err))
+                        _p(st, C.c_uint32), C.c_uint32(warps), C.c_uint32(rings), C.c_uint32(grid), C.c_uint32(vh), C.c_uint32(pairs), C.c_uint32(smem_visited | (0x80000000 if tpr8 else 0) | (0x20000000 if resg else 0)), C.byref(err))
     assert rc == 0, rc
     assert err.value == 0, hex(err.value)
     assert lib.emu_tma_unwaited() == 0, "a bulk copy was still in flight when its CTA exited"
@@ -145,32 +145,6 @@ def test_search_kernel_emulated_very_large_ef(emu, oracle_mod, coop):
         assert got["n"].tolist() == want["n"].tolist()
         assert got["labels"].tobytes() == want["labels"].tobytes()
         assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
-
-
-@pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-d{c[1]}m{c[2]}" for c in CASES])
-def test_double_buffered_gather_with_a_second_ring(emu, oracle_mod, case, monkeypatch):
-    """PGEMB_RING2: a hop of several row groups takes a second ring when one is free (3 slots share 3 rings here, so both the
-    two-ring and the one-ring path run, depending on what the other slots hold) -- same labels, distances and counters."""
-    monkeypatch.setenv("PGEMB_EMU_JITTER", "1")
-    metric, dims, m, efc, n, levels, ef, nq = case
-    rng = np.random.default_rng(99 + dims)
-    if levels:
-        x = rng.integers(0, levels, (n, dims)).astype(np.float32); q = rng.integers(0, levels, (2 * nq, dims)).astype(np.float32)
-    else:
-        x = rng.standard_normal((n, dims)).astype(np.float32); q = rng.standard_normal((2 * nq, dims)).astype(np.float32)
-    if metric == "cosine":
-        x, q = x + 1.0, q + 1.0
-    orc = oracle_mod.FlatIndex("port", dims, m, efc, 64, metric, capacity=n)
-    orc.build(x)
-    want = orc.search_many(q, ef, want_counters=True)
-    for warps, rings in ((3, 3), (2, 1), (3, 2)):
-        got = run_emu(emu, metric, 0, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=2, vh=64, ring2=True,
-                      tpr8=(metric == "l2" and rings == 3))
-        assert got["n"].tolist() == want["n"].tolist() and got["labels"].tobytes() == want["labels"].tobytes(), (warps, rings)
-        assert got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist()
-        for qi in range(q.shape[0]):
-            k = int(got["n"][qi])
-            assert got["dists"][qi, :k].tobytes() == oracle_mod.dist_many("port", metric, q[qi], x[got["ids"][qi, :k]]).tobytes()
 
 
 @pytest.mark.parametrize("case", CASES, ids=[f"{c[0]}-d{c[1]}m{c[2]}" for c in CASES])

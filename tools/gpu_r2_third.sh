@@ -7,11 +7,7 @@ L=gpurun_out/r2_third.log; : > $L
 say() { echo "== $*" | tee -a $L; }
 say "K6 tests (products + scans)"
 timeout 600 python -m pytest tests/test_gpu_scan_umma.py -m gpu -q --timeout=500 -p no:cacheprovider 2>&1 | tail -6 | tee -a $L
-say "search parity with PGEMB_RING2=1"
-PGEMB_RING2=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout=500 -p no:cacheprovider -k "search_identical or config1 or config2 or ef_beyond" 2>&1 | tail -4 | tee -a $L
-say "bench headline: default, RING2=1 (no cpu leg, no extra legs)"
 timeout 600 python bench.py --no-cpu --no-legs --steps 20 > gpurun_out/r3_bench_a.json 2>> gpurun_out/r3_bench.err; echo "exit $?" | tee -a $L
-PGEMB_RING2=1 timeout 600 python bench.py --no-cpu --no-legs --steps 20 > gpurun_out/r3_bench_b.json 2>> gpurun_out/r3_bench.err; echo "exit $?" | tee -a $L
 timeout 600 python bench.py --no-cpu --steps 20 > gpurun_out/r3_bench_c.json 2>> gpurun_out/r3_bench.err; echo "exit $?" | tee -a $L
 python - <<'PY' | tee -a $L
 import json
@@ -22,8 +18,6 @@ for f in ("a", "b", "c"):
     except Exception as e:
         print(f, "FAILED", e)
 PY
-say "1536-d L2 shape with RING2=1"
-PGEMB_RING2=1 timeout 600 python tools/bench_shapes.py --dims 1536 --n 500000 --metric l2 --m 32 2>&1 | tail -1 | cut -c340-520 | tee -a $L
 say "ncu launch list of one pgemb_scan_topk call (1024 queries x 1M rows): who takes the time"
 PGEMB_PROF_SCAN=1024 PGEMB_BENCH_N=1000000 timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r3_scan_launches.csv python tools/prof_scan.py > gpurun_out/r3_prof_scan_list.log 2>&1
 python - <<'PY' | tee -a $L
@@ -47,3 +41,6 @@ for r in r3_scan_filter r3_scan_rescore r3_latency r3_l2_1536 r3_scan_tile r3_in
   [ -f gpurun_out/$r.ncu-rep ] && python tools/ncu_summary.py gpurun_out/$r.ncu-rep gpurun_out/$r 2>&1 | tail -1 | tee -a $L
 done
 ls -la gpurun_out/*.ncu-rep 2>/dev/null | tee -a $L
+# gpurun brings back at most 64 MiB: the summaries above are what profiles/ keeps; two reports travel for the source page
+rm -f gpurun_out/r3_l2_1536.ncu-rep gpurun_out/r3_scan_tile.ncu-rep gpurun_out/r3_insert.ncu-rep gpurun_out/r3_scan_rescore.ncu-rep
+du -sh gpurun_out | tee -a $L
