@@ -117,6 +117,7 @@ struct pgemb_index
 	uint32_t	 *d_visited = nullptr, *d_vlog = nullptr, *d_vhash = nullptr;
 	uint32_t	  ws_vh = 0;  // allocated hash entries per slot
 	size_t		  l2_persist_max = 0, l2_window_max = 0;
+	bool		  l2_limit_dropped = false;	 // the scan path gave the persisting-L2 set-aside back (scan_topk_impl)
 	// link lists that came from the caller have not been checked for repeated ids yet / result of the last check
 	bool links_checked = true, links_distinct = true;
 	uint64_t	 *d_ovf = nullptr;
@@ -752,6 +753,12 @@ pgemb_status launch_search(pgemb_index *idx, size_t nq, const float *d_queries, 
 
 	if (vh && idx->l2_window_max > 0 && env_int("PGEMB_L2_PERSIST", 1))
 	{
+		if (idx->l2_limit_dropped)
+		{
+			if (idx->l2_persist_max > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, idx->l2_persist_max * 3 / 4);
+			cudaGetLastError();
+			idx->l2_limit_dropped = false;
+		}
 		// keep the per-slot visited sets (hit on every hop by L2 atomics) resident while rows stream through L2
 		cudaStreamAttrValue av;
 		memset(&av, 0, sizeof(av));
@@ -1300,6 +1307,22 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 	if (tc)
 	{
 		// ---- K6: tensor-core filter + exact re-scoring, geometric chunks -----------------------------------------------
+		// The filter lives on L2 reuse (the table streams from HBM once, the other query tiles re-read it from L2).  A traversal
+		// on this index leaves an L2 persistence window behind (the per-slot visited sets, launch_search): give those lines and
+		// the set-aside back before scanning.  PGEMB_SCAN_L2RESET: 0 = leave as is, 1 = reset lines + window, 2 (default) = also
+		// drop the set-aside limit until the next traversal configures it again.
+		const int l2reset = env_int("PGEMB_SCAN_L2RESET", 2);
+		if (l2reset > 0 && idx->last_l2_base != nullptr)
+		{
+			cudaStreamAttrValue av;
+			memset(&av, 0, sizeof(av));
+			av.accessPolicyWindow.num_bytes = 0;
+			if (cudaStreamSetAttribute(idx->last_l2_stream ? idx->last_l2_stream : s, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+			if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+			if (l2reset > 1 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0) != cudaSuccess) cudaGetLastError();
+			idx->last_l2_base = nullptr;
+			idx->l2_limit_dropped = l2reset > 1;
+		}
 		st = ensure_row_norms(idx, s);
 		if (st) return st;
 		const float rel = scan_tc_rel(dim);

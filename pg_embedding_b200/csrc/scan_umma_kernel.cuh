@@ -399,44 +399,10 @@ __global__ void __launch_bounds__(128) scan_rescore_kernel(const float *__restri
 	float		  *cs = cand_s + (size_t) q * cap;
 	uint32_t	   n_resc = 0;
 
-	if (!overflow)
-	{
-		// ---- phase A ------------------------------------------------------------------------------------------------
-		for (uint32_t base = 0; base < listed; base += 128)
-		{
-			const uint32_t e = base + threadIdx.x;
-			const bool	   have = e < listed;
-			const uint32_t row = crow[have ? e : 0] & 0x7fffffffu;	// (entry 0 may already carry its dead mark; idle lanes only shadow it)
-			const float	   s = cs[have ? e : 0];
-			const float	   vn = vnorm2[row];
-			bool		   alive = have && ((labels[row] >> 48) & 1ull) == 0;
-			if (alive) alive = filter_pass<METRIC>(s, qc, filter_rconst<METRIC>(vn));
-			if (__any_sync(0xffffffffu, alive))
-			{
-				// all lanes run the same code (full-mask shuffles inside); lanes without a live candidate compute and drop
-				const float dex = distance_exact<METRIC, 1>(qp, vectors + (size_t) row * row_f, (int) dim, qn, vn, 0);
-				if (alive)
-				{
-					float approx, slack;
-					filter_approx<METRIC>(s, qn, vn, rel, &approx, &slack);
-					const float ex = (METRIC == M_COS) ? dex : dex * dex;
-					if (fabsf(ex - approx) > slack * 1.5f + 1e-6f * fabsf(ex)) atomicAdd(&counters[1], 1u);
-					cs[e] = __uint_as_float(f2o(dex));
-					n_resc++;
-				}
-			}
-			if (have && !alive) crow[e] = row | 0x80000000u;
-		}
-		__syncthreads();
-	}
-	if (w != 0)
-	{
-		if (n_resc) atomicAdd(&counters[0], n_resc);
-		return;
-	}
-	// ---- phase B (warp 0) -----------------------------------------------------------------------------------------------
-	uint32_t	   nc = 0;
-	const uint32_t lt = (1u << lane) - 1u;
+	// ---- phase B state (used by warp 0 only) ------------------------------------------------------------------------------
+	__shared__ float2 qc_s;	 // the filter constants all warps test with: refreshed by warp 0 after every slice it folds
+	uint32_t		  nc = 0;
+	const uint32_t	  lt = (1u << lane) - 1u;
 	auto less = [](uint32_t d1, uint64_t l1, uint32_t d2, uint64_t l2) { return d1 < d2 || (d1 == d2 && l1 < l2); };
 	auto merge = [&]() {
 		// rank every element of top (n) and cand (nc) in their union; keep ranks < k  (as scan_select_kernel)
@@ -481,28 +447,79 @@ __global__ void __launch_bounds__(128) scan_rescore_kernel(const float *__restri
 	};
 	if (!overflow)
 	{
-		for (uint32_t base = 0; base < listed; base += 32)
+		// The list is taken in slices of 512: all warps re-score a slice (phase A), warp 0 folds it (phase B) and publishes the
+		// tightened threshold, so later slices skip what can no longer matter -- the order inside the list is arbitrary
+		// (atomicAdd order of the filter kernel), any order gives the same top-k.
+		constexpr uint32_t kSlice = 512;
+		if (threadIdx.x == 0) qc_s = qc;
+		__syncthreads();
+		for (uint32_t s0 = 0; s0 < listed; s0 += kSlice)
 		{
-			const uint32_t e = base + lane;
-			bool		   have = e < listed;
-			uint32_t	   row = 0, d = 0;
-			uint64_t	   l = 0;
-			if (have)
+			const uint32_t s1 = min(listed, s0 + kSlice);
+			const float2   qcur = qc_s;
+			// ---- phase A: one lane per candidate --------------------------------------------------------------------------
+			for (uint32_t base = s0; base < s1; base += 128)
 			{
-				row = crow[e];
-				have = (row & 0x80000000u) == 0u;
-				if (have)
+				const uint32_t e = base + threadIdx.x;
+				const bool	   have = e < s1;
+				const uint32_t row = crow[have ? e : s0] & 0x7fffffffu;	// (entry s0 may already carry its dead mark; idle lanes only shadow it)
+				const float	   s = cs[have ? e : s0];
+				const float	   vn = vnorm2[row];
+				bool		   alive = have && ((labels[row] >> 48) & 1ull) == 0;
+				if (alive) alive = filter_pass<METRIC>(s, qcur, filter_rconst<METRIC>(vn));
+				if (__any_sync(0xffffffffu, alive))
 				{
-					d = __float_as_uint(cs[e]);
-					l = labels[row];
+					// all lanes run the same code (full-mask shuffles inside); lanes without a live candidate compute and drop
+					const float dex = distance_exact<METRIC, 1>(qp, vectors + (size_t) row * row_f, (int) dim, qn, vn, 0);
+					if (alive)
+					{
+						float approx, slack;
+						filter_approx<METRIC>(s, qn, vn, rel, &approx, &slack);
+						const float ex = (METRIC == M_COS) ? dex : dex * dex;
+						if (fabsf(ex - approx) > slack * 1.5f + 1e-6f * fabsf(ex)) atomicAdd(&counters[1], 1u);
+						cs[e] = __uint_as_float(f2o(dex));
+						n_resc++;
+					}
 				}
+				if (have && !alive) crow[e] = row | 0x80000000u;
 			}
-			offer(have, d, l);
+			__syncthreads();
+			// ---- phase B: warp 0 folds the slice ----------------------------------------------------------------------------
+			if (w == 0)
+			{
+				for (uint32_t base = s0; base < s1; base += 32)
+				{
+					const uint32_t e = base + lane;
+					bool		   have = e < s1;
+					uint32_t	   row = 0, d = 0;
+					uint64_t	   l = 0;
+					if (have)
+					{
+						row = crow[e];
+						have = (row & 0x80000000u) == 0u;
+						if (have)
+						{
+							d = __float_as_uint(cs[e]);
+							l = labels[row];
+						}
+					}
+					offer(have, d, l);
+				}
+				if (nc) merge();
+				if (lane == 0) qc_s = filter_qconst<METRIC>(qn, n < k ? INFINITY : o2f(td[k - 1]), rel);
+			}
+			__syncthreads();
+		}
+		if (w != 0)
+		{
+			if (n_resc) atomicAdd(&counters[0], n_resc);
+			return;
 		}
 	}
 	else
 	{
-		// the list overflowed: every row of the chunk, 32 at a time, one lane per row
+		if (w != 0) return;
+		// the list overflowed: every row of the chunk, 32 at a time, one lane per row (warp 0 alone)
 		for (uint32_t base = 0; base < nr; base += 32)
 		{
 			const uint32_t e = base + lane;
