@@ -553,7 +553,7 @@ def leg_sharded(args, torch, dist, pg, lib, _lib, rank, world, local):
     coll_per_step = (nccl.collectives - c0) / (K + W)
     same_exchanges = bool(torch.equal(out_peer[1], out_nccl[1]) and torch.equal(out_peer[0], out_nccl[0]) and torch.equal(out_peer[2], out_nccl[2]))
     # ---- parity of a query sample: compiled reference per shard + (dist,label) merge on the CPU ----
-    parity = None
+    parity = parity_ok = None
     if not args.no_cpu:
         ns = 1024
         qs = Q[(W + K - 1) * B:(W + K - 1) * B + ns]
@@ -589,6 +589,7 @@ def leg_sharded(args, torch, dist, pg, lib, _lib, rank, world, local):
                     ok = False
                     break
             parity = {"queries": ns, "identical_to_reference_per_shard_plus_cpu_merge": ok, "checker": kind}
+            parity_ok = ok
     err = peer.error()
     peer.close()
     idx.close()
@@ -603,7 +604,7 @@ def leg_sharded(args, torch, dist, pg, lib, _lib, rank, world, local):
             "exchange_bytes_read_per_rank_per_step": bytes_rank * (world - 1), "peer_error": err,
             "nccl_allgather": {"value": round(B / (ms_nccl * 1e-3), 1), "ms_per_step": round(ms_nccl, 3), "collectives_per_step": coll_per_step,
                                "launches_per_step": launches_nccl, "bytes_per_rank": bytes_rank, "same_results_as_peer_exchange": same_exchanges},
-            "parity": parity}
+            "parity": parity_ok, "parity_detail": parity}
 
 
 def host_graph(idx, n, which):

@@ -1259,7 +1259,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 		if (lg >= 8 && lg <= 20) chunk = (size_t) 1 << lg;
 	}
 	while (chunk > 256 && nq * chunk * 4 > ((size_t) 256 << 20)) chunk >>= 1;
-	// tensor-core path: first chunk establishes the threshold (every row of it is a candidate), then x16 per chunk (PGEMB_SCAN_TC_GROWTH)
+	// tensor-core path: first chunk establishes the threshold (every row of it is a candidate), then x2 per chunk (PGEMB_SCAN_TC_GROWTH)
 	size_t c0 = ((2 * k > 256 ? 2 * k : 256) + 255) / 256 * 256;
 	{
 		const int lg = env_int("PGEMB_SCAN_TC_CHUNK0_LOG2", 0);
@@ -1331,7 +1331,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 		else PGEMB_LAUNCH(scan_qconst_init_kernel<M_COS>, (uint32_t) ((nq + 127) / 128), 128, 0, s, d_qn, (uint32_t) nq, rel, d_qc, d_cn);
 		g_launches++;
 		size_t csize = c0;
-		size_t growth = (size_t) env_int("PGEMB_SCAN_TC_GROWTH", 16);
+		size_t growth = (size_t) env_int("PGEMB_SCAN_TC_GROWTH", 2);	// measured (profiles/r2_call10_scan_growth_sweep.log): 2 / 3 / 4 / 8 -> 6.7 / 7.7 / 8.0 / 8.6 ms per 1024 x 1M x 768 scan at k 64
 		if (growth < 2) growth = 2;
 		for (size_t r0 = 0; r0 < N;)
 		{
@@ -1342,8 +1342,8 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 #define SCAN_RESCORE(MM)                                                                                                                          \
 	PGEMB_LAUNCH(scan_rescore_kernel<MM>, (uint32_t) nq, 128, 0, s, idx->d_vectors, idx->row_f, (uint32_t) dim, idx->d_norms, d_q, (uint32_t) rf, d_qn,  \
 				 idx->d_labels, (uint32_t) nq, (uint32_t) r0, (uint32_t) nr, (uint32_t) k, rel, d_cr, d_cs, d_cn, (uint32_t) cap, d_td, d_tl, d_tn, d_sd, d_sl, d_qc, d_cnt)
-			if (metric == DIST_L2) SCAN_RESCORE(M_L2);
-			else SCAN_RESCORE(M_COS);
+			if (metric == DIST_L2) { SCAN_RESCORE(M_L2); }
+			else { SCAN_RESCORE(M_COS); }
 #undef SCAN_RESCORE
 			g_launches++;
 			CU_TRY(cudaGetLastError());

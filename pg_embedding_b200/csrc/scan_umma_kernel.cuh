@@ -19,7 +19,7 @@
 //                             (dist_exact.cuh, one lane per candidate) and folded into the running top-k by (dist,label),
 //                             exactly like scan_select_kernel; then the query's filter constants are refreshed for the next chunk.
 //
-// The host (capi.cu, scan_topk_impl) walks the table in geometrically growing chunks (256, 4K, 64K, ... rows): the first
+// The host (capi.cu, scan_topk_impl) walks the table in geometrically growing chunks (256, 512, 1K, ... rows): the first
 // chunk establishes the threshold, every later chunk is filtered with the exact threshold of everything before it, so
 // ~k ln(N/k) + (rows inside the error band) candidates per query are re-scored in total.  Result = the exact path's: same
 // labels, same order, bit-identical distances (tests/test_gpu_parity.py::test_scan_umma_*).  Every re-scored candidate
@@ -328,19 +328,25 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
 				}
 				else if (q_ok)
 				{
+					// survivors of these 32 columns: ONE slot reservation per thread (= per query) and chunk, then the entries
+					uint32_t pass = 0u;
 #pragma unroll
 					for (uint32_t j = 0; j < 32u; j++)
+						if (filter_pass<METRIC>(__uint_as_float(v[j]), qc, rc[c0 + j]) && c0 + j < valid) pass |= 1u << j;
+					if (pass != 0u)
 					{
-						const float s = __uint_as_float(v[j]);
-						if (filter_pass<METRIC>(s, qc, rc[c0 + j]) && c0 + j < valid)
-						{
-							const uint32_t slot = atomicAdd(&p.cand_n[q], 1u);
-							if (slot < p.cap)
+						const uint32_t first = atomicAdd(&p.cand_n[q], (uint32_t) __popc(pass));
+#pragma unroll
+						for (uint32_t j = 0; j < 32u; j++)
+							if (pass & (1u << j))
 							{
-								p.cand_rows[(size_t) q * p.cap + slot] = p.r0 + row_rel0 + c0 + j;
-								p.cand_s[(size_t) q * p.cap + slot] = s;
+								const uint32_t slot = first + (uint32_t) __popc(pass & ((1u << j) - 1u));
+								if (slot < p.cap)
+								{
+									p.cand_rows[(size_t) q * p.cap + slot] = p.r0 + row_rel0 + c0 + j;
+									p.cand_s[(size_t) q * p.cap + slot] = __uint_as_float(v[j]);
+								}
 							}
-						}
 					}
 				}
 			}
@@ -363,7 +369,9 @@ __global__ void __launch_bounds__(kUmmaThreads, 1)
 // Re-scoring + selection.  One CTA (4 warps) per query.
 //   phase A  all 4 warps: every listed candidate is re-scored with the reference-exact arithmetic, ONE lane per candidate
 //            (the lane owns all accumulator chains of its pair and reads the row with 16-byte loads: 128 rows in flight per
-//            query -- the loop is a chain of dependent L2/HBM round trips, so rows in flight is what counts).  Candidates that the
+//            query -- the loop is a chain of dependent L2/HBM round trips, so rows in flight is what counts).  Measured
+//            alternative, dropped: staging the rows through shared memory in column blocks with coalesced cp.async pieces
+//            (fewer LSU wavefronts) -- 7.7 instead of 6.7 ms per 1024 x 1M scan: more instructions, fewer resident CTAs.  Candidates that the
 //            chunk-start threshold already excludes, and deleted rows, are skipped.  The exact distance replaces the product in
 //            the candidate list (cand_s), a dead entry gets bit 31 of its row id.  Every re-scored pair CHECKS the assumed
 //            error bound (tripwire).
@@ -384,12 +392,29 @@ __global__ void __launch_bounds__(128) scan_rescore_kernel(const float *__restri
 	static_assert(METRIC == M_L2 || METRIC == M_COS, "the filter needs a bilinear form");
 	__shared__ uint32_t cd[kScanCand];
 	__shared__ uint64_t cl[kScanCand];
+	// the running top-k lives in shared memory while the kernel works on it (k <= kTopSmem; larger k stays in global memory): the
+	// rank-by-counting merge reads every entry (n + nc) times -- from L2 that was as long as the re-scoring itself
+	constexpr uint32_t kTopSmem = 256;
+	__shared__ uint32_t top_d_s[2 * kTopSmem];
+	__shared__ uint64_t top_l_s[2 * kTopSmem];
 	const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t q = blockIdx.x;
 	if (q >= nq) return;
-	uint32_t *td = top_d + (size_t) q * k, *sd = tmp_d + (size_t) q * k;
-	uint64_t *tl = top_l + (size_t) q * k, *sl = tmp_l + (size_t) q * k;
+	const bool top_in_smem = k <= kTopSmem;
+	uint32_t *gtd = top_d + (size_t) q * k;
+	uint64_t *gtl = top_l + (size_t) q * k;
+	uint32_t *td = top_in_smem ? top_d_s : gtd, *sd = top_in_smem ? top_d_s + kTopSmem : tmp_d + (size_t) q * k;
+	uint64_t *tl = top_in_smem ? top_l_s : gtl, *sl = top_in_smem ? top_l_s + kTopSmem : tmp_l + (size_t) q * k;
 	uint32_t  n = top_n[q];
+	if (top_in_smem)
+	{
+		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			top_d_s[i] = gtd[i];
+			top_l_s[i] = gtl[i];
+		}
+		__syncthreads();
+	}
 	const float	  *qp = queries + (size_t) q * q_stride;
 	const float	   qn = qnorm2[q];
 	const uint32_t listed = cand_n[q];
@@ -532,6 +557,15 @@ __global__ void __launch_bounds__(128) scan_rescore_kernel(const float *__restri
 		}
 	}
 	if (nc) merge();
+	if (top_in_smem)
+	{
+		__syncwarp();
+		for (uint32_t i = lane; i < n; i += 32)
+		{
+			gtd[i] = td[i];
+			gtl[i] = tl[i];
+		}
+	}
 	if (lane == 0)
 	{
 		top_n[q] = n;

@@ -376,6 +376,7 @@ static inline void cp_async_wait_all()
 	for (const emu::PendingCopy &c : pq) memcpy(c.dst, c.src, c.bytes);
 	pq.clear();
 }
+static inline void cp_async_wait_but2() { cp_async_wait_all(); }  // waiting for more than asked is a legal schedule
 static inline uint32_t lanemask_lt() { return (1u << (emu::L().tid.x & 31u)) - 1u; }
 
 // ---- the part of the CUDA runtime API capi.cu uses ---------------------------------------------------------

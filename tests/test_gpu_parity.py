@@ -425,27 +425,28 @@ def _clustered(rng, n, dim, centres):
 
 
 def test_config1_dims128_l2_vs_oracle(pg, oracle_mod):
-    """BASELINE configs[1] shape (dims=128, L2, m=16, efC=200, efS=64) at N=30K: the graph is built by the
-    reference algorithm on the CPU (sequential, exact), searched by both; 4096 queries must match exactly."""
+    """BASELINE configs[1] at its full size (dims=128, N=100K, L2, m=16, efC=200, efS=64): the graph is built by the reference
+    algorithm on the CPU (sequential, exact), searched by both; 4096 queries must match exactly (labels and traversal counters).
+    The last 300 inserts are replayed on the GPU from the CPU's state before them: link lists bit-identical."""
     rng = np.random.default_rng(128)
-    n, dims, m, efc, efs = 30_000, 128, 16, 200, 64
-    centres = rng.standard_normal((173, dims)).astype(np.float32)
+    n, dims, m, efc, efs = 100_000, 128, 16, 200, 64
+    centres = rng.standard_normal((316, dims)).astype(np.float32)
     x, q = _clustered(rng, n, dims, centres), _clustered(rng, 4096, dims, centres)
     which = "ref" if oracle_mod.available("ref") else "port"
+    cut = n - 300
     orc = oracle_mod.FlatIndex(which, dims, m, efc, efs, "l2", capacity=n)
-    orc.build(x)
+    orc.build(x[:cut])
+    before = orc.records().copy()                        # the graph as it was before the last 300 inserts
+    for i in range(cut, n):
+        orc.add(x[i], i)
     idx = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=n)
     idx.load_records(orc.records())
     out = idx.search_batch(q, efs, want_stats=True)
     want = orc.search_many(q, efs, nthreads=os.cpu_count() or 4, want_counters=True)
     assert out["labels"].tobytes() == want["labels"].tobytes()
     assert (out["stats"][:, :3].astype(np.uint64) == want["counters"]).all()
-    # exact sequential GPU binds reproduce the tail of the CPU build bit for bit: re-bind the last 300 nodes
     idx2 = pg.HnswIndex(dims, m, efc, efs, "l2", capacity=n)
-    cut = n - 300
-    orc2 = oracle_mod.FlatIndex(which, dims, m, efc, efs, "l2", capacity=n)
-    orc2.build(x[:cut])
-    idx2.load_records(orc2.records())
+    idx2.load_records(before)
     idx2.insert_many(x[cut:])
     assert idx2.links().tobytes() == orc.links().tobytes()
     idx.close(); idx2.close()

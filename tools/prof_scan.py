@@ -11,13 +11,14 @@ from pg_embedding_b200 import _lib
 import bench
 n = int(os.environ.get("PGEMB_BENCH_N", 200_000))
 nq = int(os.environ.get("PGEMB_PROF_SCAN", 64))
+k = int(os.environ.get("PGEMB_PROF_SCAN_K", 10))
 lib = _lib.load()
 X, Q = bench.make_data(torch, n, nq)
 idx = pg.HnswIndex(bench.DIMS, bench.M, bench.EFC, bench.EFS, bench.METRIC, capacity=n)
 _lib.check(lib.pgemb_index_append_device(idx.dev, n, X.data_ptr(), None, None, torch.cuda.current_stream().cuda_stream)); torch.cuda.synchronize()
 q = Q.cpu().numpy()
-idx.scan_topk(q[:2], 10)
+idx.scan_topk(q[:2], k)
 torch.cuda.profiler.start()
-out = idx.scan_topk(q, 10)
+out = idx.scan_topk(q, k)
 torch.cuda.profiler.stop()
 print("done", out["n"][:4].tolist())
