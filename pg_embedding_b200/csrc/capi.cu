@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -1006,6 +1007,18 @@ static pgemb_status launch_pairs(int metric, const float *d_a, const float *d_b,
 	return PGEMB_OK;
 }
 
+// hnsw_dist_func has no handle to hang a buffer on (distfunc.c:171: two pointers and a length), so the staging area of the
+// pair-distance entry points is process-wide: one device buffer on the current device, grown on demand, reused by every call
+// (round 1 paid three cudaMalloc + three cudaFree per pair).  One caller at a time (a Postgres backend is single-threaded;
+// other hosts serialise on the mutex).
+static struct
+{
+	std::mutex mu;
+	void	  *d = nullptr;
+	size_t	   bytes = 0;
+	int		   device = -1;
+} g_pair_stage;
+
 extern "C" pgemb_status pgemb_dist_batch(dist_func_t dist, size_t dim, size_t n, const coord_t *a, int broadcast_a, const coord_t *b,
 										 dist_t *out)
 {
@@ -1013,24 +1026,46 @@ extern "C" pgemb_status pgemb_dist_batch(dist_func_t dist, size_t dim, size_t n,
 	if (dim == 0 || dim > 65535) return fail(PGEMB_ERR_ARG, "dims out of range");
 	if (n == 0) return PGEMB_OK;
 	if (n >= (1ull << 28)) return fail(PGEMB_ERR_ARG, "batch too large");
-	float		*d_a = nullptr, *d_b = nullptr, *d_o = nullptr;
-	const size_t ab = (broadcast_a ? 1 : n) * dim * sizeof(float), bb = n * dim * sizeof(float);
-	cudaError_t	 e = cudaMalloc((void **) &d_a, ab);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_b, bb);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_o, n * sizeof(float));
-	if (e == cudaSuccess) e = cudaMemcpy(d_a, a, ab, cudaMemcpyHostToDevice);
-	if (e == cudaSuccess) e = cudaMemcpy(d_b, b, bb, cudaMemcpyHostToDevice);
-	pgemb_status st = PGEMB_OK;
-	if (e == cudaSuccess)
+	int dev = 0;
+	CU_TRY(cudaGetDevice(&dev));
+	auto		 up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+	const size_t ab = (broadcast_a ? 1 : n) * dim * sizeof(float), bb = n * dim * sizeof(float), ob = n * sizeof(float);
+	const size_t total = up(ab) + up(bb) + up(ob);
+	std::lock_guard<std::mutex> lock(g_pair_stage.mu);
+	if (g_pair_stage.device != dev || g_pair_stage.bytes < total)
 	{
-		st = launch_pairs((int) dist, d_a, d_b, (uint32_t) dim, (uint32_t) n, broadcast_a, d_o, 0);
-		if (st == PGEMB_OK) e = cudaMemcpy(out, d_o, n * sizeof(float), cudaMemcpyDeviceToHost);
+		if (g_pair_stage.d)
+		{
+			if (g_pair_stage.device >= 0 && g_pair_stage.device != dev)
+			{
+				cudaSetDevice(g_pair_stage.device);
+				cudaFree(g_pair_stage.d);
+				cudaSetDevice(dev);
+			}
+			else
+				cudaFree(g_pair_stage.d);
+		}
+		g_pair_stage.d = nullptr;
+		g_pair_stage.bytes = 0;
+		const size_t want = total + total / 2 + 65536;
+		if (cudaMalloc(&g_pair_stage.d, want) != cudaSuccess)
+		{
+			cudaGetLastError();
+			g_pair_stage.d = nullptr;
+			return fail(PGEMB_ERR_NOMEM, "out of device memory for the distance batch");
+		}
+		g_pair_stage.bytes = want;
+		g_pair_stage.device = dev;
 	}
-	cudaFree(d_a);
-	cudaFree(d_b);
-	cudaFree(d_o);
-	if (e != cudaSuccess) return fail(PGEMB_ERR_CUDA, std::string("pgemb_dist_batch: ") + cudaGetErrorString(e));
-	return st;
+	char  *base = (char *) g_pair_stage.d;
+	float *d_a = (float *) base, *d_b = (float *) (base + up(ab)), *d_o = (float *) (base + up(ab) + up(bb));
+	CU_TRY(cudaMemcpyAsync(d_a, a, ab, cudaMemcpyHostToDevice, 0));
+	CU_TRY(cudaMemcpyAsync(d_b, b, bb, cudaMemcpyHostToDevice, 0));
+	pgemb_status st = launch_pairs((int) dist, d_a, d_b, (uint32_t) dim, (uint32_t) n, broadcast_a, d_o, 0);
+	if (st) return st;
+	CU_TRY(cudaMemcpyAsync(out, d_o, ob, cudaMemcpyDeviceToHost, 0));
+	CU_TRY(cudaStreamSynchronize(0));
+	return PGEMB_OK;
 }
 
 extern "C" pgemb_status pgemb_dist_gather(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, const idx_t *ids, dist_t *out)

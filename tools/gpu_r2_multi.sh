@@ -6,6 +6,8 @@ mkdir -p gpurun_out
 L=gpurun_out/r2_multi$N.log; : > $L
 say() { echo "== $*" | tee -a $L; }
 say "nvidia-smi topo"; nvidia-smi topo -m 2>&1 | head -12 | tee -a $L
+say "K6 tests (one GPU of the box)"
+timeout 600 python -m pytest tests/test_gpu_scan_umma.py -m gpu -q --timeout=500 -p no:cacheprovider 2>&1 | tail -4 | tee -a $L
 say "pytest tests/test_gpu_sharded.py (world 2..$N)"
 timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout=800 -p no:cacheprovider 2>&1 | tail -12 | tee -a $L
 say "bench.py --gpus $N (torchrun): replicas headline + sharded leg"
