@@ -393,3 +393,39 @@ def test_ef_beyond_shared_memory(pg, G, oracle_mod, monkeypatch):
     G.check_ef_beyond_shared_memory(pg, oracle_mod, 12, 300, (20000, 64))
     monkeypatch.setenv("PGEMB_RES_GLOBAL", "1")
     G.test_search_identical_to_oracle(pg, oracle_mod, "manhattan", G.SEARCH_CFGS[3])
+
+
+def test_new_entry_points_argument_checks(pg):
+    """Round-2 entry points fail loudly on bad arguments (status + message), never crash."""
+    from pg_embedding_b200 import _lib
+    lib = _lib.load()
+    idx = pg.HnswIndex(4, 3, 8, 4, "l2", capacity=16)
+    idx.append(np.eye(4, dtype=np.float32))
+    assert lib.pgemb_index_poll_error(idx.dev, None) == 0                       # nothing raised
+    assert lib.pgemb_index_poll_error(None, None) == 2
+    sc = C.c_void_p()
+    q = np.ones(4, np.float32)
+    assert lib.pgemb_index_scan_begin(idx.dev, q.ctypes.data_as(C.POINTER(C.c_float)), 0, C.byref(sc)) == 2   # efsearch >= 1
+    assert lib.pgemb_index_scan_begin(None, q.ctypes.data_as(C.POINTER(C.c_float)), 4, C.byref(sc)) == 2
+    t = C.c_uint64(0)
+    assert lib.pgemb_index_scan_next(None, C.byref(t)) == -2
+    ex = C.c_void_p()
+    assert lib.pgemb_exchange_create(0, 3, 2, 8, 4, C.byref(ex)) == 2           # rank >= world
+    assert lib.pgemb_exchange_create(0, 0, 17, 8, 4, C.byref(ex)) == 2          # more than 16 shards
+    _lib.check(lib.pgemb_exchange_create(0, 0, 2, 8, 4, C.byref(ex)))
+    dq = np.ones((2, 4), np.float32)
+    assert lib.pgemb_sharded_search_device(idx.dev, ex, 2, dq.ctypes.data_as(C.c_void_p), 4, None) == 4      # not attached yet
+    assert b"attach" in lib.pgemb_last_error()
+    handles = (C.c_char * 128)()
+    assert lib.pgemb_exchange_attach(ex, handles, 1) == 2                        # null peer buffer
+    lib.pgemb_exchange_destroy(ex)
+    # one rank is its own world: search + merge degenerate to the local result
+    _lib.check(lib.pgemb_exchange_create(0, 0, 1, 8, 4, C.byref(ex)))
+    assert lib.pgemb_sharded_search_device(idx.dev, ex, 2, dq.ctypes.data_as(C.c_void_p), 5, None) == 2      # ef != k
+    _lib.check(lib.pgemb_sharded_search_device(idx.dev, ex, 2, dq.ctypes.data_as(C.c_void_p), 4, None))
+    ol = np.zeros((2, 4), np.uint64); od = np.zeros((2, 4), np.float32); on = np.zeros(2, np.int32)
+    _lib.check(lib.pgemb_sharded_merge_device(ex, 2, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p), None))
+    want = idx.search_batch(dq, 4)
+    assert ol.tobytes() == want["labels"].tobytes() and on.tolist() == want["n"].tolist()
+    lib.pgemb_exchange_destroy(ex)
+    idx.close()
