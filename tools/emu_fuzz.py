@@ -194,12 +194,63 @@ def fuzz_lib_proto(a, oracle):
     return 0
 
 
+def fuzz_scan(a, oracle):
+    """pgemb_scan_topk on the emulated library: the tensor-core path (filter predicate, chunk orchestration, candidate lists,
+    re-scoring kernel; the product itself is the host stand-in, pushed by a random fraction <= 90 % of the assumed error bound)
+    against the exact kernels, under random k / chunk / capacity / growth settings, deleted labels and duplicate rows."""
+    import ctypes as C
+    from emu_build import build_emulated
+    from pg_embedding_b200 import _lib
+    import pg_embedding_b200 as pg
+    os.environ["PGEMB_EMU_SMS"] = "2"
+    _lib._lib = _lib._bind(C.CDLL(build_emulated(tempfile.mkdtemp(prefix="emu_fuzz_scan_"))))
+    t_end = time.time() + 60.0 * a.minutes
+    seed, done = a.seed0, 0
+    while time.time() < t_end:
+        rng = np.random.default_rng(seed)
+        metric = ["l2", "cosine"][rng.integers(0, 2)]
+        dims = int(rng.integers(1, 80))
+        n = int(rng.choice([1, 5, 40, 300, 700, 1500]))
+        k = int(rng.choice([1, 3, 10, 64, 300]))
+        nq = int(rng.choice([1, 3, 9, 33]))
+        levels = int(rng.choice([0, 0, 3, 5]))
+        shift = 1.0 if metric == "cosine" else 0.0
+        if levels:
+            x = rng.integers(0, levels, (n, dims)).astype(np.float32) + shift; q = rng.integers(0, levels, (nq, dims)).astype(np.float32) + shift
+        else:
+            c = rng.standard_normal((6, dims)).astype(np.float32)
+            x = (c[rng.integers(0, 6, n)] + 0.2 * rng.standard_normal((n, dims))).astype(np.float32) + shift
+            q = (c[rng.integers(0, 6, nq)] + 0.2 * rng.standard_normal((nq, dims))).astype(np.float32) + shift
+        labels = rng.permutation(n).astype(np.uint64) + np.uint64(5)
+        if n > 3:
+            labels[:: int(rng.integers(2, 9))] |= np.uint64(1 << 48)
+        env = {"PGEMB_SCAN_TC_GROWTH": str(rng.choice([2, 3, 8, 16])), "PGEMB_SCAN_TC_CHUNK0_LOG2": str(rng.choice([0, 5, 6, 8])),
+               "PGEMB_SCAN_TC_CAP": str(rng.choice([0, 8, 64, 300])), "PGEMB_SCAN_TILED": str(rng.integers(0, 2)),
+               "PGEMB_EMU_GEMM_ERR_PPM": str(float(rng.uniform(0, 0.9)) * 1e6 * (2.0 / 1024.0 + dims / 2097152.0))}
+        os.environ.update(env)
+        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
+        idx.append(x, labels)
+        os.environ["PGEMB_SCAN_TC"] = "0"
+        want = idx.scan_topk(q, k)
+        os.environ["PGEMB_SCAN_TC"] = "2"
+        got = idx.scan_topk(q, k)
+        idx.close()
+        if not (got["labels"].tobytes() == want["labels"].tobytes() and got["dists"].tobytes() == want["dists"].tobytes() and got["n"].tolist() == want["n"].tolist()):
+            print("MISMATCH", dict(seed=seed, metric=metric, dims=dims, n=n, k=k, nq=nq, levels=levels, **env), flush=True)
+            return 1
+        seed += 1
+        done += 1
+    print(f"emu_fuzz --scan: {done} configurations, no mismatch (seeds {a.seed0}..{seed - 1})")
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--minutes", type=float, default=20.0)
     ap.add_argument("--seed0", type=int, default=100000)
     ap.add_argument("--bind", action="store_true", help="fuzz the insert path (link lists) instead of the search")
     ap.add_argument("--build", action="store_true", help="fuzz pgemb_build_exact / pgemb_build_bulk through the emulated library")
+    ap.add_argument("--scan", action="store_true", help="fuzz pgemb_scan_topk: tensor-core path (emulated product) against the exact kernels")
     ap.add_argument("--lib-proto", action="store_true", help="fuzz the prototype library under random combinations of its opt-in flags")
     a = ap.parse_args()
     from oracle import oracle
@@ -208,6 +259,8 @@ def main():
         return fuzz_build(a, oracle)
     if a.lib_proto:
         return fuzz_lib_proto(a, oracle)
+    if a.scan:
+        return fuzz_scan(a, oracle)
     import test_search_emulated as T
     tf = _TmpFactory()
     emu = emu_proto = T._build_emu(tf)
