@@ -363,6 +363,12 @@ def main():
             except Exception as e:
                 legs["sharded"] = {"error": repr(e)[:300]}
                 log(f"[rank {rank}] sharded leg failed: {e!r}")
+        if world > 1 or os.environ.get("PGEMB_BENCH_C4", "1") != "0":
+            try:
+                legs["configs4"] = leg_configs4(args, torch, dist, pg, lib, _lib, rank, world, local)
+            except Exception as e:
+                legs["configs4"] = {"error": repr(e)[:300]}
+                log(f"[rank {rank}] configs4 leg failed: {e!r}")
     if rank == 0:
         out = {
             "metric": "QPS @ recall@10, dims=768 N=1M efSearch=64", "value": round(value, 1), "unit": "queries/s",
@@ -605,6 +611,129 @@ def leg_sharded(args, torch, dist, pg, lib, _lib, rank, world, local):
             "nccl_allgather": {"value": round(B / (ms_nccl * 1e-3), 1), "ms_per_step": round(ms_nccl, 3), "collectives_per_step": coll_per_step,
                                "launches_per_step": launches_nccl, "bytes_per_rank": bytes_rank, "same_results_as_peer_exchange": same_exchanges},
             "parity": parity_ok, "parity_detail": parity}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# leg: BASELINE configs[4] shape -- dims 768, cosine, 1024-query batches against a table sharded by id range, every rank scans
+# its rows on the tensor-core path (K6), per-shard top-k exchanged and merged (K5).  12.5M rows per GPU: 100M at 8 GPUs.
+# ---------------------------------------------------------------------------------------------------------------------
+def leg_configs4(args, torch, dist, pg, lib, _lib, rank, world, local):
+    from pg_embedding_b200 import sharded
+    dims, k, nq = 768, 10, 1024
+    rows = int(os.environ.get("PGEMB_BENCH_C4_ROWS", 12_500_000))
+    K, W = min(args.steps, 5), 2
+    n_total = rows * world
+    lo, hi = sharded.shard_bounds(n_total, world)[rank]
+    g = torch.Generator(device="cuda"); g.manual_seed(99)
+    centres = torch.randn((max(4, int(round(n_total ** 0.5))), dims), generator=g, device="cuda")
+    idx = pg.HnswIndex(dims, 2, 4, 16, "cosine", capacity=hi - lo, device=local)   # no graph is built: the operator path scans the table
+    stream = torch.cuda.current_stream().cuda_stream
+    t0 = time.time()
+    chunk = 1 << 20
+    for s0 in range(lo, hi, chunk):                                                 # generated and appended chunk by chunk (38 GB per shard)
+        e = min(hi, s0 + chunk)
+        x = gen_points(torch, e - s0, 1234 + 7919 * (s0 // chunk), centres)
+        labels = torch.arange(s0, e, dtype=torch.int64, device="cuda")              # labels = global ids
+        _lib.check(lib.pgemb_index_append_device(idx.dev, e - s0, x.data_ptr(), labels.data_ptr(), None, stream)); torch.cuda.synchronize()
+        del x, labels
+    Q = gen_points(torch, nq * (K + W), 5678, centres)                              # the same queries on every rank
+    log(f"[rank {rank}] configs4 leg: shard [{lo},{hi}) generated in {time.time() - t0:.1f}s")
+    os.environ.pop("PGEMB_SCAN_TC", None)
+    peer = nccl = None
+    if world > 1:
+        peer = sharded.PeerExchange(idx, nq, k)
+        nccl = sharded.ShardedSearch(sharded.gpu_local_scan_packed(idx), sharded.gpu_merge_packed())
+
+    def scan_local(q):
+        od = torch.empty((q.shape[0], k), dtype=torch.float32, device="cuda"); ol = torch.empty((q.shape[0], k), dtype=torch.int64, device="cuda")
+        on = torch.empty((q.shape[0],), dtype=torch.int32, device="cuda")
+        _lib.check(lib.pgemb_scan_topk_device(idx.dev, q.shape[0], q.data_ptr(), k, ol.data_ptr(), od.data_ptr(), on.data_ptr(), stream))
+        return od, ol, on
+
+    def timed(run):
+        for s in range(W):
+            run(Q[s * nq:(s + 1) * nq])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = int(lib.pgemb_launch_count())
+        e0.record()
+        for s in range(W, W + K):
+            out = run(Q[s * nq:(s + 1) * nq])
+        e1.record(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / K, out, (int(lib.pgemb_launch_count()) - l0) / K
+
+    c0 = scan_counters(lib)
+    ms, out, launches = timed((lambda q: peer.scan(q, k)) if world > 1 else scan_local)
+    c1 = scan_counters(lib)
+    nccl_part = None
+    if world > 1:
+        ms_n, out_n, launches_n = timed(lambda q: nccl.search(q, k))
+        nccl_part = {"value": round(nq / (ms_n * 1e-3), 1), "ms_per_step": round(ms_n, 3), "collectives_per_step": 1, "launches_per_step": launches_n,
+                     "bytes_per_rank": sharded.packed_bytes(nq, k),
+                     "same_results_as_peer_exchange": bool(torch.equal(out[1], out_n[1]) and torch.equal(out[0], out_n[0]) and torch.equal(out[2], out_n[2]))}
+    # ---- parity of a query sample: the exact kernels (no filter; themselves pinned to the oracle by the tests) per shard,
+    #      merged on the CPU by (dist,label)
+    ns = 16
+    qs = Q[(W + K - 1) * nq:(W + K - 1) * nq + ns].contiguous()
+    os.environ["PGEMB_SCAN_TC"] = "0"
+    t0 = time.perf_counter()
+    ed, el, en = scan_local(qs)
+    torch.cuda.synchronize()
+    t_exact = time.perf_counter() - t0
+    os.environ.pop("PGEMB_SCAN_TC", None)
+    if world > 1:
+        gl = [torch.empty_like(el) for _ in range(world)]; gd = [torch.empty_like(ed) for _ in range(world)]; gn = [torch.empty_like(en) for _ in range(world)]
+        dist.all_gather(gl, el); dist.all_gather(gd, ed); dist.all_gather(gn, en)      # parity plumbing, untimed
+    else:
+        gl, gd, gn = [el], [ed], [en]
+    parity_ok = None
+    if rank == 0:
+        L = torch.stack(gl).cpu().numpy(); D = torch.stack(gd).cpu().numpy(); Nn = torch.stack(gn).cpu().numpy()
+        gpu_l = out[1][:ns].cpu().numpy(); gpu_d = out[0][:ns].cpu().numpy(); gpu_n = out[2][:ns].cpu().numpy()
+        parity_ok = True
+        for i in range(ns):
+            pairs = sorted((float(D[s, i, j]), int(L[s, i, j])) for s in range(world) for j in range(int(Nn[s, i])))[:k]
+            if gpu_n[i] != len(pairs) or gpu_l[i, :len(pairs)].tolist() != [p_[1] for p_ in pairs] or \
+                    gpu_d[i, :len(pairs)].tobytes() != np.array([p_[0] for p_ in pairs], np.float32).tobytes():
+                parity_ok = False
+                break
+    err = peer.error() if peer else 0
+    merge_ms = peer.merge_ms() if peer else 0.0
+    if peer:
+        peer.close()
+    idx.close()
+    del Q
+    torch.cuda.empty_cache()
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        bf16 = 1590.0
+    hbm, _ = measured_peak_gbs()
+    t = ms * 1e-3
+    flops_gpu = 2.0 * nq * rows * dims
+    qtiles = (nq + 127) // 128
+    return {"workload": f"dims={dims} N={n_total} ({rows} rows per shard) cosine, {nq}-query batches, k={k} (BASELINE configs[4] shape: {world} of its 8 shards), "
+                        f"every rank scans its id range on the tensor-core path (K6), per-shard top-k exchanged and merged (K5); no graph",
+            "value": round(nq / t, 1), "unit": "queries/s", "ms_per_step": round(ms, 3), "steps": K, "warmup": W, "scaling": "weak (shard size fixed, table grows with N)",
+            "pairs_per_s": round(nq * n_total / t, 0),
+            "tensor": {"bound": "tensor", "achieved_per_gpu": round(flops_gpu / t / 1e12, 1), "peak": round(bf16 / 2.0, 1), "unit": "TFLOP/s",
+                       "frac": round(flops_gpu / t / 1e12 / (bf16 / 2.0), 4), "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"},
+            "hbm_bound_one_table_pass_per_query_tile_s": round(qtiles * rows * dims * 4 / (hbm * 1e9), 5),
+            "x_of_that_bound": round(t / (qtiles * rows * dims * 4 / (hbm * 1e9)), 2),
+            "rescored_fraction": round((c1["rescored"] - c0["rescored"]) / max(1, c1["pairs"] - c0["pairs"]), 8),
+            "tripwire_fallbacks": int(c1["fallbacks"] - c0["fallbacks"]), "overflowed_queries": int(c1["overflow"] - c0["overflow"]),
+            "through_tensor_path": bool(c1["tc"] - c0["tc"] == K + W),
+            "exchange": ("peer memory: per-shard top-k read over NVLink by the wait+merge kernel (CUDA IPC); no collective" if world > 1 else "none (one shard)"),
+            "launches_per_step": launches, "collectives_per_step": 0, "merge_kernel_ms_incl_peer_wait": round(merge_ms, 3),
+            "exchange_bytes_read_per_rank_per_step": sharded.packed_bytes(nq, k) * (world - 1), "peer_error": err,
+            "nccl_allgather": nccl_part,
+            "exact_kernels_same_sample": {"queries": ns, "seconds": round(t_exact, 4), "pairs_per_s": round(ns * rows / t_exact, 0)},
+            "parity": parity_ok, "parity_detail": {"queries": ns, "identical_to_exact_kernels_per_shard_plus_cpu_merge_labels_order_bits": parity_ok}}
 
 
 def host_graph(idx, n, which):

@@ -201,6 +201,10 @@ pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries
  *   out[3] scans repeated on the exact kernels because the error-bound tripwire fired
  *   out[4] queries whose candidate list overflowed (re-scored against the whole chunk)   out[5] exact-kernel scans */
 void pgemb_scan_counters(uint64_t out[6]);
+/* pgemb_scan_topk with DEVICE pointers in and out (queries [nq*dim], labels [nq*k], dists [nq*k] optional, n [nq]); `stream` is
+ * synchronised with on entry, the scan has finished when the call returns.  Same results, byte for byte. */
+pgemb_status pgemb_scan_topk_device(pgemb_index *idx, size_t nq, const coord_t *d_queries, size_t k, label_t *d_labels_out,
+                                    dist_t *d_dists_out, int32_t *d_n_out, void *stream);
 /* Test entry: the raw tensor-core products S[q][j] = q . row(r0 + j) (TF32 operands, fp32 accumulate) of the K6 kernel,
  * out[nq * nr], host pointers -- lets a test check descriptors / swizzle / TMEM read-back against a float64 product. */
 pgemb_status pgemb_debug_umma_product(pgemb_index *idx, size_t nq, const coord_t *queries, size_t r0, size_t nr, float *out);
@@ -278,6 +282,9 @@ void        *pgemb_exchange_buffer(pgemb_exchange *ex);
  * device pointer from pgemb_exchange_buffer instead of an IPC handle. */
 pgemb_status pgemb_exchange_attach(pgemb_exchange *ex, const void *handles, int same_process);
 pgemb_status pgemb_sharded_search_device(pgemb_index *idx, pgemb_exchange *ex, size_t nq, const coord_t *d_queries, size_t ef, void *stream);
+/* the brute-force scan (pgemb_scan_topk_device) as the local step instead of the traversal: BASELINE configs[4], every rank scans
+ * its id range for the whole query batch; k must equal the exchange's k */
+pgemb_status pgemb_sharded_scan_device(pgemb_index *idx, pgemb_exchange *ex, size_t nq, const coord_t *d_queries, size_t k, void *stream);
 pgemb_status pgemb_sharded_merge_device(pgemb_exchange *ex, size_t nq, label_t *d_labels_out, dist_t *d_dists_out, int32_t *d_n_out, void *stream);
 float        pgemb_exchange_last_merge_ms(pgemb_exchange *ex);
 int          pgemb_exchange_error(pgemb_exchange *ex);

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "pgemb_index_set_links", "pgemb_index_get_labels", "pgemb_index_set_labels",
     "pgemb_index_truncate", "pgemb_index_reserve", "pgemb_search_batch", "pgemb_search_batch_device",
     "pgemb_index_poll_error", "pgemb_last_kernel_ms", "pgemb_launch_count", "pgemb_dist_batch", "pgemb_dist_gather", "pgemb_scan_topk",
-    "pgemb_scan_counters", "pgemb_debug_umma_product",
+    "pgemb_scan_counters", "pgemb_scan_topk_device", "pgemb_sharded_scan_device", "pgemb_debug_umma_product",
     "pgemb_index_scan_begin", "pgemb_index_scan_next", "pgemb_index_scan_next_batch", "pgemb_index_scan_ef", "pgemb_index_scan_searches",
     "pgemb_index_scan_end",
     "pgemb_bind_point", "pgemb_insert_batch", "pgemb_merge_topk_device", "pgemb_packed_topk_bytes", "pgemb_merge_topk_packed_device",
@@ -131,6 +131,8 @@ def _bind(lib: C.CDLL) -> C.CDLL:
     lib.pgemb_exchange_buffer.restype = vp
     lib.pgemb_exchange_attach.argtypes = [vp, vp, C.c_int]
     lib.pgemb_sharded_search_device.argtypes = [vp, vp, sz, vp, sz, vp]
+    lib.pgemb_sharded_scan_device.argtypes = [vp, vp, sz, vp, sz, vp]
+    lib.pgemb_scan_topk_device.argtypes = [vp, sz, vp, sz, vp, vp, vp, vp]
     lib.pgemb_sharded_merge_device.argtypes = [vp, sz, vp, vp, vp, vp]
     lib.pgemb_exchange_last_merge_ms.argtypes = [vp]
     lib.pgemb_exchange_last_merge_ms.restype = C.c_float

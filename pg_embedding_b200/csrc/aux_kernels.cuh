@@ -122,6 +122,21 @@ __global__ void scan_dist_kernel(const float *__restrict__ vectors, const float 
 	if (pair < total && sub == 0) out[pair] = d;
 }
 
+// Device-pointer epilogue of the brute-force scan (pgemb_scan_topk_device): the running top-k (order keys, labels, counts) in
+// the caller's layout -- distances as floats, unused tail = (~0, +inf) -- exactly what the host epilogue of pgemb_scan_topk writes.
+__global__ void scan_finish_kernel(const uint32_t *__restrict__ top_d, const uint64_t *__restrict__ top_l, const uint32_t *__restrict__ top_n, uint32_t nq,
+								   uint32_t k, uint64_t *__restrict__ labels_out, float *__restrict__ dists_out, int32_t *__restrict__ n_out)
+{
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (size_t) nq * k) return;
+	const uint32_t q = (uint32_t) (i / k), j = (uint32_t) (i % k);
+	const uint32_t n = top_n[q];
+	const bool	   ok = j < n;
+	labels_out[i] = ok ? top_l[i] : ~(uint64_t) 0;
+	if (dists_out) dists_out[i] = ok ? o2f(top_d[i]) : INFINITY;
+	if (j == 0) n_out[q] = (int32_t) n;
+}
+
 // Step 2: fold a chunk of distances into the running k smallest (dist,label) pairs of every query.
 // One warp per query.  top_d holds f2o(dist); candidates better than the current worst pair are gathered in shared
 // memory and merged by rank whenever the buffer fills (the threshold only tightens, so gathering with a stale

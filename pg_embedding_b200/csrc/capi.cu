@@ -1229,10 +1229,32 @@ static pgemb_status launch_scan_filter(pgemb_index *idx, int metric, const float
 }
 
 static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
-								   int32_t *n_out, bool allow_tc, bool *tc_violation);
+								   int32_t *n_out, bool allow_tc, bool *tc_violation, bool device_io);
+static pgemb_status scan_topk_groups(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out, int32_t *n_out,
+									 bool device_io);
 
 extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
 										int32_t *n_out)
+{
+	return scan_topk_groups(idx, nq, queries, k, labels_out, dists_out, n_out, false);
+}
+
+// The same scan with DEVICE pointers in and out (the caller's stream is only synchronised with: the scan runs on the index's own
+// stream and has finished when the call returns).  For callers whose queries and results live in HBM already: the sharded scan.
+extern "C" pgemb_status pgemb_scan_topk_device(pgemb_index *idx, size_t nq, const coord_t *d_queries, size_t k, label_t *d_labels_out, dist_t *d_dists_out,
+											   int32_t *d_n_out, void *stream)
+{
+	if (idx && stream)
+	{
+		pgemb_status st = set_device(idx);
+		if (st) return st;
+		CU_TRY(cudaStreamSynchronize((cudaStream_t) stream));  // the queries may have been produced on it
+	}
+	return scan_topk_groups(idx, nq, d_queries, k, d_labels_out, d_dists_out, d_n_out, true);
+}
+
+static pgemb_status scan_topk_groups(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out, int32_t *n_out,
+									 bool device_io)
 {
 	if (!idx || ((!queries || !labels_out || !n_out) && nq)) return fail(PGEMB_ERR_ARG, "null argument");
 	if (nq == 0) return PGEMB_OK;
@@ -1245,13 +1267,14 @@ extern "C" pgemb_status pgemb_scan_topk(pgemb_index *idx, size_t nq, const coord
 		const size_t gq = nq - q0 < group ? nq - q0 : group;
 		bool		 viol = false;
 		pgemb_status st = scan_topk_impl(idx, gq, queries + q0 * idx->meta.dim, k, labels_out + q0 * k, dists_out ? dists_out + q0 * k : nullptr, n_out + q0,
-										 true, &viol);
+										 true, &viol, device_io);
 		if (st == PGEMB_OK && viol)
 		{
 			// the tensor-core filter saw a product outside its assumed error bound: its result is not trusted
 			g_scan_fallbacks++;
 			fprintf(stderr, "pgemb_scan_topk: tensor-core error bound exceeded, repeating the scan on the exact kernels\n");
-			st = scan_topk_impl(idx, gq, queries + q0 * idx->meta.dim, k, labels_out + q0 * k, dists_out ? dists_out + q0 * k : nullptr, n_out + q0, false, &viol);
+			st = scan_topk_impl(idx, gq, queries + q0 * idx->meta.dim, k, labels_out + q0 * k, dists_out ? dists_out + q0 * k : nullptr, n_out + q0, false, &viol,
+								device_io);
 		}
 		if (st) return st;
 	}
@@ -1270,7 +1293,7 @@ static bool scan_use_tc(const pgemb_index *idx, bool allow_tc)
 }
 
 static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *queries, size_t k, label_t *labels_out, dist_t *dists_out,
-								   int32_t *n_out, bool allow_tc, bool *tc_violation)
+								   int32_t *n_out, bool allow_tc, bool *tc_violation, bool device_io)
 {
 	*tc_violation = false;
 	pgemb_status st = set_device(idx);
@@ -1324,7 +1347,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 	float	 *d_cs = (float *) base;		base += up(cb);		// candidate products
 	uint32_t *d_cnt = (uint32_t *) base;						// [0] re-scored, [1] tripwire, [2] overflowed queries
 	if (rf != dim) CU_TRY(cudaMemsetAsync(d_q, 0, qb, s));
-	CU_TRY(cudaMemcpy2DAsync(d_q, rf * 4, queries, dim * 4, dim * 4, nq, cudaMemcpyHostToDevice, s));
+	CU_TRY(cudaMemcpy2DAsync(d_q, rf * 4, queries, dim * 4, dim * 4, nq, device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
 	CU_TRY(cudaMemsetAsync(d_tn, 0, nb, s));
 	if (timing)
 	{
@@ -1368,6 +1391,13 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 		size_t csize = c0;
 		size_t growth = (size_t) env_int("PGEMB_SCAN_TC_GROWTH", 2);	// measured (profiles/r2_call10_scan_growth_sweep.log): 2 / 3 / 4 / 8 -> 6.7 / 7.7 / 8.0 / 8.6 ms per 1024 x 1M x 768 scan at k 64
 		if (growth < 2) growth = 2;
+		// chunks stop growing at 2^20 rows (PGEMB_SCAN_TC_CHUNK_MAX_LOG2): the candidate lists are sized for what passes the filter in
+		// one chunk, and a table of tens of millions of rows must not end in one chunk of half the table
+		size_t cmax = (size_t) 1 << 20;
+		{
+			const int lg = env_int("PGEMB_SCAN_TC_CHUNK_MAX_LOG2", 0);
+			if (lg >= 8 && lg <= 30) cmax = (size_t) 1 << lg;
+		}
 		for (size_t r0 = 0; r0 < N;)
 		{
 			size_t nr = N - r0 < csize ? N - r0 : csize;
@@ -1384,6 +1414,7 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 			CU_TRY(cudaGetLastError());
 			r0 += nr;
 			csize *= growth;
+			if (csize > cmax) csize = cmax > c0 ? cmax : c0;
 		}
 		g_scan_tc++;
 		g_scan_pairs += (uint64_t) nq * N;
@@ -1420,44 +1451,57 @@ static pgemb_status scan_topk_impl(pgemb_index *idx, size_t nq, const coord_t *q
 			CU_TRY(cudaGetLastError());
 		}
 	}
-	std::vector<uint32_t> hd, hn;
-	try
-	{
-		hd.resize(nq * k);
-		hn.resize(nq);
-	}
-	catch (const std::bad_alloc &)
-	{
-		cudaStreamSynchronize(s);
-		return fail(PGEMB_ERR_NOMEM, "out of host memory");  // no C++ exception crosses the C ABI
-	}
-	if (timing)
-	{
-		t_enqueued = since();
-		cudaStreamSynchronize(s);
-		t_synced = since();
-	}
-	CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
-	CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
-	CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
 	uint32_t cnt[4] = {0, 0, 0, 0};
-	if (tc) CU_TRY(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
-	CU_TRY(cudaStreamSynchronize(s));
+	if (device_io)
+	{
+		PGEMB_LAUNCH(scan_finish_kernel, (uint32_t) ((nq * k + 255) / 256), 256, 0, s, d_td, d_tl, d_tn, (uint32_t) nq, (uint32_t) k, labels_out, dists_out, n_out);
+		g_launches++;
+		CU_TRY(cudaGetLastError());
+		if (timing) t_enqueued = since();
+		if (tc) CU_TRY(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
+		CU_TRY(cudaStreamSynchronize(s));
+		if (timing) t_synced = since();
+	}
+	else
+	{
+		std::vector<uint32_t> hd, hn;
+		try
+		{
+			hd.resize(nq * k);
+			hn.resize(nq);
+		}
+		catch (const std::bad_alloc &)
+		{
+			cudaStreamSynchronize(s);
+			return fail(PGEMB_ERR_NOMEM, "out of host memory");  // no C++ exception crosses the C ABI
+		}
+		if (timing)
+		{
+			t_enqueued = since();
+			cudaStreamSynchronize(s);
+			t_synced = since();
+		}
+		CU_TRY(cudaMemcpyAsync(hd.data(), d_td, kd, cudaMemcpyDeviceToHost, s));
+		CU_TRY(cudaMemcpyAsync(labels_out, d_tl, kl, cudaMemcpyDeviceToHost, s));
+		CU_TRY(cudaMemcpyAsync(hn.data(), d_tn, nb, cudaMemcpyDeviceToHost, s));
+		if (tc) CU_TRY(cudaMemcpyAsync(cnt, d_cnt, 16, cudaMemcpyDeviceToHost, s));
+		CU_TRY(cudaStreamSynchronize(s));
+		for (size_t q = 0; q < nq; q++)
+		{
+			n_out[q] = (int32_t) hn[q];
+			for (size_t i = 0; i < k; i++)
+			{
+				const bool ok = i < hn[q];
+				if (!ok) labels_out[q * k + i] = ~(label_t) 0;
+				if (dists_out) dists_out[q * k + i] = ok ? o2f(hd[q * k + i]) : INFINITY;
+			}
+		}
+	}
 	if (tc)
 	{
 		g_scan_rescored += cnt[0];
 		g_scan_overflow += cnt[2];
 		if (cnt[1]) *tc_violation = true;
-	}
-	for (size_t q = 0; q < nq; q++)
-	{
-		n_out[q] = (int32_t) hn[q];
-		for (size_t i = 0; i < k; i++)
-		{
-			const bool ok = i < hn[q];
-			if (!ok) labels_out[q * k + i] = ~(label_t) 0;
-			if (dists_out) dists_out[q * k + i] = ok ? o2f(hd[q * k + i]) : INFINITY;
-		}
 	}
 	if (timing)
 		fprintf(stderr, "pgemb_scan_topk timing (ms): queries staged %.3f | kernels enqueued %.3f | kernels done %.3f | results copied + unpacked %.3f  (nq %zu, N %zu, %s)\n",
@@ -1932,6 +1976,10 @@ extern "C" pgemb_status pgemb_build_bulk(pgemb_index *idx, size_t first, size_t 
 // longest prefix whose searches provably equal the sequential ones (validate_kernel) is connected -- own lists
 // + back-links per target in source-id order, which is the sequential order -- and the batch restarts at the
 // first conflicting insert.  The first insert of a batch is always valid, so the build always progresses.
+// Measured and dropped (profiles/r2_call16_exact_repair.log): redoing each conflicting insert alone and re-validating the rest of
+// the batch against its true back-link targets -- bit-identical too (446 fuzzed configurations), but every repair costs a whole
+// search latency, which is what a fresh speculative round costs while accepting ~37 inserts: 207-795 us per insert at N ~ 1M
+// against 172 us for this restart scheme.
 extern "C" pgemb_status pgemb_build_exact(pgemb_index *idx, size_t first, size_t n, size_t batch_max, double *seconds_out,
 										  uint64_t *stats_out /* [3]: batches, searches run, inserts */)
 {
@@ -2278,6 +2326,31 @@ extern "C" pgemb_status pgemb_sharded_search_device(pgemb_index *idx, pgemb_exch
 	pgemb_status st = launch_search(idx, nq, d_queries, (uint32_t) idx->meta.dim, nullptr, (uint32_t) idx->n, ef, 0, d_l, d_d, nullptr, d_n, nullptr, s, true);
 	if (st) return st;
 	// publish: my sequence number into every peer's flag array, after the search in stream order
+	uint32_t *src = &ex->h_seq[ex->seq & 63u];
+	*src = ex->seq;
+	for (int r = 0; r < ex->world; r++)
+	{
+		if (r == ex->rank) continue;
+		CU_TRY(cudaMemcpyAsync(ex->peer[r] + ex->off_flags + (size_t) ex->rank * 4, src, 4, cudaMemcpyHostToDevice, s));
+	}
+	return PGEMB_OK;
+}
+
+// The brute-force scan as the local step of a sharded exchange (BASELINE configs[4]: every rank scans its id range for the whole
+// query batch): results land in this rank's result area, then the step is published to the peers exactly as a traversal's is.
+extern "C" pgemb_status pgemb_sharded_scan_device(pgemb_index *idx, pgemb_exchange *ex, size_t nq, const coord_t *d_queries, size_t k, void *stream)
+{
+	if (!idx || !ex) return fail(PGEMB_ERR_ARG, "null argument");
+	if (ex->world > 1 && !ex->attached) return fail(PGEMB_ERR_STATE, "pgemb_exchange_attach has not been called");
+	if (k != ex->k) return fail(PGEMB_ERR_ARG, "k differs from the exchange's k");
+	if (nq == 0 || nq > ex->max_nq) return fail(PGEMB_ERR_ARG, "nq out of range for this exchange");
+	if (idx->device != ex->device) return fail(PGEMB_ERR_ARG, "index and exchange live on different devices");
+	cudaStream_t s = (cudaStream_t) stream;
+	const uint32_t seq = ex->seq + 1;
+	char		  *area = ex->d_buf + (size_t) (seq & 1u) * ex->area_bytes;
+	pgemb_status   st = pgemb_scan_topk_device(idx, nq, d_queries, k, (label_t *) area, (dist_t *) (area + nq * ex->k * 8), (int32_t *) (area + nq * ex->k * 12), stream);
+	if (st) return st;
+	ex->seq = seq;
 	uint32_t *src = &ex->h_seq[ex->seq & 63u];
 	*src = ex->seq;
 	for (int r = 0; r < ex->world; r++)

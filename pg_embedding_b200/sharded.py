@@ -110,6 +110,25 @@ def gpu_local_search_packed(index):
     return run
 
 
+def gpu_local_scan_packed(index):
+    """local_search for the brute-force scan (BASELINE configs[4]): `run(queries, k)` scans this rank's rows (pgemb_scan_topk_device,
+    the tensor-core filter + exact re-scoring) straight into one packed buffer."""
+    import torch
+    from . import _lib
+
+    lib = _lib.load()
+
+    def run(queries, k):
+        nq = queries.shape[0]
+        buf = torch.zeros(packed_bytes(nq, k), dtype=torch.uint8, device=queries.device)
+        base = buf.data_ptr()
+        _lib.check(lib.pgemb_scan_topk_device(index.dev, nq, queries.data_ptr(), k, base, base + nq * k * 8, base + nq * k * 12,
+                                               torch.cuda.current_stream().cuda_stream))
+        return buf
+
+    return run
+
+
 def gpu_merge_packed():
     import torch
     from . import _lib
@@ -159,6 +178,20 @@ class PeerExchange:
         ol = torch.empty((nq, ef), dtype=torch.int64, device=queries.device)
         on = torch.empty((nq,), dtype=torch.int32, device=queries.device)
         _lib.check(self.lib.pgemb_sharded_search_device(self.index.dev, self.ex, nq, queries.data_ptr(), ef, st))
+        _lib.check(self.lib.pgemb_sharded_merge_device(self.ex, nq, ol.data_ptr(), od.data_ptr(), on.data_ptr(), st))
+        return od, ol, on
+
+    def scan(self, queries, k: int):
+        """The same exchange with the brute-force scan as the local step."""
+        import torch
+        from . import _lib
+        assert k == self.k
+        nq = queries.shape[0]
+        st = torch.cuda.current_stream().cuda_stream
+        od = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        ol = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+        on = torch.empty((nq,), dtype=torch.int32, device=queries.device)
+        _lib.check(self.lib.pgemb_sharded_scan_device(self.index.dev, self.ex, nq, queries.data_ptr(), k, st))
         _lib.check(self.lib.pgemb_sharded_merge_device(self.ex, nq, ol.data_ptr(), od.data_ptr(), on.data_ptr(), st))
         return od, ol, on
 

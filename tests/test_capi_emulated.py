@@ -387,6 +387,56 @@ def test_peer_memory_exchange_two_shards(pg, oracle_mod):
         lib.pgemb_exchange_destroy(exs[r]); idxs[r].close(); orcs[r].close()
 
 
+@pytest.mark.parametrize("metric,tc", [("cosine", "2"), ("l2", "2"), ("manhattan", "0")])
+def test_sharded_scan_two_shards(pg, oracle_mod, monkeypatch, metric, tc):
+    """BASELINE configs[4]'s step on two id-range shards in one process: pgemb_scan_topk_device == pgemb_scan_topk byte for byte, and
+    pgemb_sharded_scan_device + the wait+merge kernel == the oracle's distances over the WHOLE table sorted by (dist,label)."""
+    from pg_embedding_b200 import _lib, sharded
+    lib = _lib.load()
+    monkeypatch.setenv("PGEMB_SCAN_TC", tc)
+    rng = np.random.default_rng(31)
+    n, dims, k, nq, world = 900, 20, 12, 9, 2
+    x = rng.integers(0, 3, (n, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)   # ties across the shards
+    labels_all = rng.permutation(n).astype(np.uint64) + np.uint64(5)
+    labels_all[::13] |= np.uint64(1 << 48)                                                         # deleted rows
+    bounds = sharded.shard_bounds(n, world)
+    idxs, exs = [], []
+    for r, (lo, hi) in enumerate(bounds):
+        idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=hi - lo)
+        idx.append(x[lo:hi], labels_all[lo:hi])
+        ex = C.c_void_p()
+        _lib.check(lib.pgemb_exchange_create(0, r, world, 32, k, C.byref(ex)))
+        idxs.append(idx); exs.append(ex)
+    handles = (C.c_char * (64 * world))()
+    for r in range(world):
+        C.memmove(C.addressof(handles) + 64 * r, C.byref(C.c_void_p(lib.pgemb_exchange_buffer(exs[r]))), 8)
+    for r in range(world):
+        _lib.check(lib.pgemb_exchange_attach(exs[r], handles, 1))
+    live = [j for j in range(n) if not (int(labels_all[j]) >> 48) & 1]
+    for step in range(2):
+        q = rng.integers(0, 3, (nq - step, dims)).astype(np.float32) + (1.0 if metric == "cosine" else 0.0)
+        nqs = q.shape[0]
+        for r in range(world):
+            host = idxs[r].scan_topk(q, k)
+            ol = np.zeros((nqs, k), np.uint64); od = np.zeros((nqs, k), np.float32); on = np.zeros(nqs, np.int32)
+            _lib.check(lib.pgemb_scan_topk_device(idxs[r].dev, nqs, q.ctypes.data_as(C.c_void_p), k, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p),
+                                                  on.ctypes.data_as(C.c_void_p), None))
+            assert ol.tobytes() == host["labels"].tobytes() and od.tobytes() == host["dists"].tobytes() and on.tolist() == host["n"].tolist()
+            _lib.check(lib.pgemb_sharded_scan_device(idxs[r].dev, exs[r], nqs, q.ctypes.data_as(C.c_void_p), k, None))
+        for r in range(world):
+            ol = np.zeros((nqs, k), np.uint64); od = np.zeros((nqs, k), np.float32); on = np.zeros(nqs, np.int32)
+            _lib.check(lib.pgemb_sharded_merge_device(exs[r], nqs, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p), None))
+            assert lib.pgemb_exchange_error(exs[r]) == 0
+            for i in range(nqs):
+                d = oracle_mod.dist_many("port", metric, q[i], x)
+                want = sorted((float(d[j]), int(labels_all[j])) for j in live)[:k]
+                assert on[i] == len(want) and ol[i, :on[i]].tolist() == [w[1] for w in want], (metric, step, r, i)
+                assert od[i, :on[i]].tobytes() == np.array([w[0] for w in want], np.float32).tobytes()
+    assert lib.pgemb_sharded_scan_device(idxs[0].dev, exs[0], nq, q.ctypes.data_as(C.c_void_p), k + 1, None) == 2     # k differs from the exchange's
+    for r in range(world):
+        lib.pgemb_exchange_destroy(exs[r]); idxs[r].close()
+
+
 def test_ef_beyond_shared_memory(pg, G, oracle_mod, monkeypatch):
     """ef = 20000 through the library on the host: launch_search must fall back to the global-memory result queues by itself;
     PGEMB_RES_GLOBAL=1 forces that variant for ordinary searches too."""

@@ -94,3 +94,71 @@ def test_sharded_search_both_exchanges(tmp_path, oracle_mod, world):
             assert res[0][s]["on"][i] == len(want)
             assert res[0][s]["ol"][i, :len(want)].tolist() == [w[1] for w in want]
             assert np.array([w[0] for w in want], np.float32).tobytes() == res[0][s]["od"][i, :len(want)].tobytes()
+
+
+SCAN = dict(n=40000, dims=96, k=10, nq=200)
+
+
+def _scan_inputs():
+    rng = np.random.default_rng(17)
+    c = rng.standard_normal((16, SCAN["dims"])).astype(np.float32)
+    x = (c[rng.integers(0, 16, SCAN["n"])] + 0.2 * rng.standard_normal((SCAN["n"], SCAN["dims"]))).astype(np.float32) + np.float32(1.0)
+    x[300:340] = x[30000:30040]                                 # duplicates across shards
+    labels = rng.permutation(SCAN["n"]).astype(np.uint64)
+    labels[::17] |= np.uint64(1 << 48)                          # deleted rows
+    q = (c[rng.integers(0, 16, SCAN["nq"])] + 0.2 * rng.standard_normal((SCAN["nq"], SCAN["dims"]))).astype(np.float32) + np.float32(1.0)
+    return x, labels, q
+
+
+def _scan_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["PGEMB_SCAN_TC"] = "2"
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    sys.path.insert(0, ROOT)
+    import pg_embedding_b200 as pg
+    from pg_embedding_b200 import sharded
+    x, labels, q = _scan_inputs()
+    lo, hi = sharded.shard_bounds(SCAN["n"], world)[rank]
+    idx = pg.HnswIndex(SCAN["dims"], 4, 8, 16, "cosine", capacity=hi - lo, device=rank)
+    idx.append(x[lo:hi], labels[lo:hi])
+    nccl = sharded.ShardedSearch(sharded.gpu_local_scan_packed(idx), sharded.gpu_merge_packed())
+    peer = sharded.PeerExchange(idx, SCAN["nq"], SCAN["k"])
+    qd = torch.from_numpy(q).cuda()
+    res = {}
+    for s in range(2):
+        od, ol, on = nccl.search(qd[s:], SCAN["k"])
+        pd, pl, pn = peer.scan(qd[s:], SCAN["k"])
+        torch.cuda.synchronize()
+        assert peer.error() == 0
+        res[s] = {"ol": ol.cpu().numpy(), "on": on.cpu().numpy(), "od": od.cpu().numpy(), "pl": pl.cpu().numpy(), "pn": pn.cpu().numpy(), "pd": pd.cpu().numpy()}
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), res, allow_pickle=True)
+    dist.barrier(); peer.close(); dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_scan_both_exchanges(tmp_path, oracle_mod, world):
+    """BASELINE configs[4]'s step (every rank scans its id range on the tensor-core path, top-k exchanged and merged) ==
+    the oracle's distances over the whole table sorted by (dist,label), on every rank, through both exchanges."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_scan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"s{r}.npy", allow_pickle=True).item() for r in range(world)]
+    x, labels, q = _scan_inputs()
+    k = SCAN["k"]
+    live = np.array([j for j in range(SCAN["n"]) if not (int(labels[j]) >> 48) & 1])
+    for s in range(2):
+        for rk in range(world):
+            a = res[rk][s]
+            assert a["ol"].tobytes() == res[0][s]["ol"].tobytes() and a["pl"].tobytes() == a["ol"].tobytes()
+            assert a["pd"].tobytes() == a["od"].tobytes() and a["pn"].tolist() == a["on"].tolist()
+        for i in range(0, SCAN["nq"] - s, 5):
+            d = oracle_mod.dist_many("port", "cosine", q[s + i], x)
+            want = sorted((float(d[j]), int(labels[j])) for j in live)[:k]
+            assert res[0][s]["on"][i] == len(want)
+            assert res[0][s]["ol"][i, :k].astype(np.uint64).tolist() == [w[1] for w in want]
+            assert np.array([w[0] for w in want], np.float32).tobytes() == res[0][s]["od"][i, :k].tobytes()

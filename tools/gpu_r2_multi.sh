@@ -6,8 +6,10 @@ mkdir -p gpurun_out
 L=gpurun_out/r2_multi$N.log; : > $L
 say() { echo "== $*" | tee -a $L; }
 say "nvidia-smi topo"; nvidia-smi topo -m 2>&1 | head -12 | tee -a $L
+if [ -z "$SKIP_K6" ]; then
 say "K6 tests (one GPU of the box)"
 timeout 600 python -m pytest tests/test_gpu_scan_umma.py -m gpu -q --timeout=500 -p no:cacheprovider 2>&1 | tail -4 | tee -a $L
+fi
 say "pytest tests/test_gpu_sharded.py (world 2..$N)"
 timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -q --timeout=800 -p no:cacheprovider 2>&1 | tail -12 | tee -a $L
 say "bench.py --gpus $N (torchrun): replicas headline + sharded leg"
@@ -19,6 +21,7 @@ try:
     d = json.load(open("gpurun_out/r2_bench_n$N.json"))
     print("value", d["value"], "e2e", d["e2e"]["value"], "n_gpus", d["n_gpus"])
     print("sharded", json.dumps(d.get("sharded")))
+    print("configs4", json.dumps(d.get("configs4")))
 except Exception as e:
     print("bench FAILED", e)
 PY
