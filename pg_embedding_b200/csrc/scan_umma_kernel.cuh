@@ -406,18 +406,19 @@ __global__ void __launch_bounds__(128) scan_rescore_kernel(const float *__restri
 	uint32_t *td = top_in_smem ? top_d_s : gtd, *sd = top_in_smem ? top_d_s + kTopSmem : tmp_d + (size_t) q * k;
 	uint64_t *tl = top_in_smem ? top_l_s : gtl, *sl = top_in_smem ? top_l_s + kTopSmem : tmp_l + (size_t) q * k;
 	uint32_t  n = top_n[q];
+	// Read by every warp BEFORE the barrier below: warp 0 resets cand_n[q] (and rewrites top_n[q]) when it is done, and on the
+	// overflow path it gets there without another barrier -- a warp that read the list length after that would take the other
+	// branch and wait at a barrier nobody else reaches (found by the emulator's fuzz campaign on a loaded host).
+	const uint32_t listed = cand_n[q];
 	if (top_in_smem)
-	{
 		for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
 		{
 			top_d_s[i] = gtd[i];
 			top_l_s[i] = gtl[i];
 		}
-		__syncthreads();
-	}
+	__syncthreads();
 	const float	  *qp = queries + (size_t) q * q_stride;
 	const float	   qn = qnorm2[q];
-	const uint32_t listed = cand_n[q];
 	const bool	   overflow = listed > cap;
 	float2		   qc = filter_qconst<METRIC>(qn, n < k ? INFINITY : o2f(td[k - 1]), rel);
 	uint32_t	  *crow = cand_rows + (size_t) q * cap;

@@ -79,6 +79,8 @@ struct SearchParams
 	// gathers+scores (about half of a hop), so rings -- the shared-memory-hungry resource that bounds
 	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
 	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
+	uint32_t row_pool;	// throughput mode, 1: the ring region is a pool of `rings` single-row slots (search_config.h), off_gbar = the slot's gather barrier
+	uint32_t off_gbar;
 	uint32_t prefetch_links;
 	uint32_t visited_pairs;	 // latency mode, 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
@@ -109,6 +111,8 @@ inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_
 	p.off_acckey = cfg.off_acckey;
 	p.off_evict = cfg.off_evict;
 	p.off_hopid = cfg.off_hopid;
+	p.row_pool = cfg.row_pool ? 1u : 0u;
+	p.off_gbar = cfg.off_gbar;
 }
 
 constexpr uint32_t kNone = 0xffffffffu;
@@ -379,6 +383,9 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(priv + p.off_hopid);
 	uint32_t	  *pf_links = reinterpret_cast<uint32_t *>(priv + p.off_pf);
 	uint64_t	  *pf_bar = reinterpret_cast<uint64_t *>(priv + p.off_pfbar);
+	uint64_t	  *g_bar = reinterpret_cast<uint64_t *>(priv + p.off_gbar);	// row pool: this slot's gather barrier
+	uint32_t	   g_par = 0;
+	unsigned long long *pool_mask = reinterpret_cast<unsigned long long *>(pool);	// row pool: free mask = (state, pad) as one word
 
 	const uint32_t lt = lanemask_lt();
 	const int	   row_in_stage = lane / TPR;
@@ -401,12 +408,18 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 
 	if (threadIdx.x == 0)
 	{
-		pool->state = (1u << p.rings) - 1u;	// all free, all parities 0
-		for (uint32_t b = 0; b < p.rings; b++)
+		if (!COOP && p.row_pool)
+			*pool_mask = p.rings >= 64u ? ~0ull : ((1ull << p.rings) - 1ull);	// every row slot free
+		else
 		{
-			mbar_init(&pool->bar[b], 1);
+			pool->state = (1u << p.rings) - 1u;	// all free, all parities 0
+			for (uint32_t b = 0; b < p.rings; b++)
+			{
+				mbar_init(&pool->bar[b], 1);
+			}
 		}
 	}
+	if (!COOP && p.row_pool && lane == 0) mbar_init(g_bar, 1);
 	if (vh_shared)
 		for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) vh[i] = 0xffffffffu;
 	if (lane == 0 && (!COOP || warp == 0)) mbar_init(pf_bar, 1);
@@ -555,6 +568,91 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					coop_bar(1, blockDim.x);
 					coop_gather<METRIC, TPR>(p, ring_base, &pool->bar[0], coop_par, 0, blockDim.x >> 5, n, hop_id, hop_key, qT, q_tail, qn, main_n, pol_stream);
 					coop_bar(2, blockDim.x);
+				}
+				else if (p.row_pool)
+				{
+					// ---- row pool: the hop's rows go into single-row slots of the CTA's pool, ALL in flight at once (one DRAM
+					// round trip per hop instead of one per 8-row group), each slot given back as soon as its row is scored ----
+					const float *qts = qT + sub * p.qt_stride;
+					uint32_t	 done = 0;
+					while (done < n)
+					{
+						const uint32_t want = n - done;
+						unsigned long long take = 0ull;
+						if (lane == 0)
+						{
+							const uint32_t least = want < (uint32_t) kRows ? want : (uint32_t) kRows;  // not worth a round trip for less
+							for (;;)
+							{
+								const unsigned long long m = *reinterpret_cast<volatile unsigned long long *>(pool_mask);
+								if ((uint32_t) __popcll(m) >= least)
+								{
+									unsigned long long t = m;
+									if ((uint32_t) __popcll(m) > want)
+									{
+										// the `want` lowest free slots
+										t = 0ull;
+										unsigned long long f = m;
+										for (uint32_t i = 0; i < want; i++)
+										{
+											t |= f & (0ull - f);
+											f &= f - 1ull;
+										}
+									}
+									if (atomicCAS(pool_mask, m, m & ~t) == m)
+									{
+										take = t;
+										break;
+									}
+								}
+								else
+									__nanosleep(100);
+							}
+							__threadfence_block();
+						}
+						take = __shfl_sync(kFull, take, 0);
+						const uint32_t cnt = (uint32_t) __popcll(take);
+						if (lane == 0) mbar_arrive_expect_tx(g_bar, cnt * p.row_bytes);
+						__syncwarp();
+#pragma unroll
+						for (uint32_t h = 0; h < 2u; h++)
+						{
+							const uint32_t bit = lane + 32u * h;
+							if ((take >> bit) & 1ull)
+							{
+								const uint32_t k = done + (uint32_t) __popcll(take & ((1ull << bit) - 1ull));
+								const uint32_t id = hop_id[k];
+								hop_key[k] = (uint64_t) bit;  // where row k lands (replaced by its key once scored)
+								tma_load_1d(ring_base + (size_t) bit * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, g_bar, pol_stream);
+							}
+						}
+						__syncwarp();
+						for (uint32_t g0 = 0; g0 < cnt; g0 += kRows)
+						{
+							const bool	   valid = g0 + row_in_stage < cnt;
+							const uint32_t k = done + (valid ? g0 + row_in_stage : g0);
+							const uint32_t pos = (uint32_t) hop_key[k];
+							const uint32_t my_id = hop_id[k];
+							float		   vn = 1.0f;
+							if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
+							if (g0 == 0)
+							{
+								mbar_wait(g_bar, g_par);
+								g_par ^= 1u;
+							}
+							const float *rowp = reinterpret_cast<const float *>(ring_base + (size_t) pos * p.row_smem);
+							const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
+							__syncwarp();  // every lane has read its row and its hop_key[] position
+							if (sub == 0 && valid)
+							{
+								hop_key[k] = make_key(d, my_id);
+								__threadfence_block();
+								atomicOr(pool_mask, 1ull << pos);  // the row slot is free again
+							}
+						}
+						__syncwarp();
+						done += cnt;
+					}
 				}
 				else
 				{

@@ -1,5 +1,6 @@
 // Scheduler and launcher of the host SIMT emulator (see fake_cuda/cuda_runtime.h).  Test infrastructure.
 #include <cuda_runtime.h>
+#include <signal.h>
 
 namespace emu {
 
@@ -9,6 +10,22 @@ pthread_mutex_t	   g_mbar_mu = PTHREAD_MUTEX_INITIALIZER;
 int				   g_tma_late = 0;
 int				   g_jitter = 0;
 int				   g_tma_unwaited = 0;
+
+// SIGUSR1 (e.g. `timeout -s USR1`): where every warp of the CTA in flight stands -- for hangs under the emulator
+static Warp *volatile g_live[64];
+static volatile unsigned g_live_n = 0;
+static void dump_state(int)
+{
+	fprintf(stderr, "emu: state of the CTA in flight (%u warps)\n", g_live_n);
+	for (unsigned wi = 0; wi < g_live_n && wi < 64; wi++)
+	{
+		Warp *w = g_live[wi];
+		if (!w) continue;
+		fprintf(stderr, "  warp %u kind %d bar %d cur %d:", wi, w->kind, w->bar_id, w->cur);
+		for (int i = 0; i < 32; i++) fprintf(stderr, " %c%d", w->lane[i].st == DONE ? 'D' : w->lane[i].st == AT_COLL ? 'C' : 'R', w->lane[i].st == AT_COLL ? w->lane[i].site : 0);
+		fprintf(stderr, "\n");
+	}
+}
 
 static void lane_trampoline()
 {
@@ -114,6 +131,12 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 		g_jitter = (j && *j && atoi(j) != 0) ? 1 : 0;
 	}
 	const unsigned nwarps = (block_threads + 31) / 32;
+	static bool handler = false;
+	if (!handler)
+	{
+		handler = true;
+		signal(SIGUSR1, dump_state);
+	}
 	for (unsigned by = 0; by < grid.y; by++)
 		for (unsigned bx = 0; bx < grid.x; bx++)
 		{
@@ -136,9 +159,12 @@ void launch(dim3 grid, unsigned block_threads, size_t dyn_smem_bytes, const std:
 				w->cta = &cta;
 				w->body = fn;
 				for (int l = 0; l < 32; l++) w->lane[l].tid = dim3(wi * 32 + l);
+				if (wi < 64) g_live[wi] = w;
+				g_live_n = wi + 1;
 				th.emplace_back([w]() { run_warp(*w); });
 			}
 			for (auto &t : th) t.join();
+			g_live_n = 0;
 			for (auto *w : warps)
 			{
 				for (int l = 0; l < 32; l++)

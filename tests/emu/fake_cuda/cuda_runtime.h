@@ -205,6 +205,7 @@ static inline void coop_bar(int id, uint32_t, int site = __builtin_LINE()) { emu
 // ---- bit tricks, conversions, arithmetic ------------------------------------------------------------
 static inline int	   __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int	   __ffs(unsigned v) { return __builtin_ffs((int) v); }
+static inline int	   __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int	   __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float	   __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
@@ -241,6 +242,15 @@ static inline unsigned atomicMin(unsigned *p, unsigned v)
 static inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
 {
 	unsigned e = cmp;
+	emu::jitter();
+	__atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+	emu::jitter();
+	return e;
+}
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { emu::jitter(); return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned long long atomicCAS(unsigned long long *p, unsigned long long cmp, unsigned long long val)
+{
+	unsigned long long e = cmp;
 	emu::jitter();
 	__atomic_compare_exchange_n(p, &e, val, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
 	emu::jitter();
