@@ -572,9 +572,15 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 				else if (p.row_pool)
 				{
 					// ---- row pool: the hop's rows go into single-row slots of the CTA's pool, ALL in flight at once (one DRAM
-					// round trip per hop instead of one per 8-row group), each slot given back as soon as its row is scored ----
-					const float *qts = qT + sub * p.qt_stride;
-					uint32_t	 done = 0;
+					// round trip per hop instead of one per 8-row group), each slot given back as soon as its row is scored.
+					// Slot b has bank residue b % kRows (the row pitch is conflict-free for kRows CONSECUTIVE slots), so the rows
+					// that are scored together are chosen AFTER the allocation: scoring group j = the j-th allocated slot of
+					// every residue (a table in the slot's scratch maps (j, residue) -> hop row).  Any free slots will do, no
+					// group reads two rows of one residue; the price is max_r(count_r) groups instead of ceil(cnt / kRows).
+					constexpr unsigned long long kCol = (kRows == 8) ? 0x0101010101010101ull : 0x1111111111111111ull;
+					unsigned char *gmap = reinterpret_cast<unsigned char *>(acc_key);	// [j * kRows + r] -> row of this round (acc_key is free until the queue update)
+					const float	  *qts = qT + sub * p.qt_stride;
+					uint32_t	   done = 0;
 					while (done < n)
 					{
 						const uint32_t want = n - done;
@@ -590,8 +596,7 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 									unsigned long long t = m;
 									if ((uint32_t) __popcll(m) > want)
 									{
-										// the `want` lowest free slots
-										t = 0ull;
+										t = 0ull;  // the `want` lowest free slots
 										unsigned long long f = m;
 										for (uint32_t i = 0; i < want; i++)
 										{
@@ -620,29 +625,42 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 							const uint32_t bit = lane + 32u * h;
 							if ((take >> bit) & 1ull)
 							{
-								const uint32_t k = done + (uint32_t) __popcll(take & ((1ull << bit) - 1ull));
-								const uint32_t id = hop_id[k];
-								hop_key[k] = (uint64_t) bit;  // where row k lands (replaced by its key once scored)
+								const unsigned long long below = take & ((1ull << bit) - 1ull);
+								const uint32_t			 r = bit % (uint32_t) kRows;
+								const uint32_t			 j = (uint32_t) __popcll(below & (kCol << r));
+								const uint32_t			 i = (uint32_t) __popcll(below);
+								const uint32_t			 k = done + i;
+								const uint32_t			 id = hop_id[k];
 								tma_load_1d(ring_base + (size_t) bit * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, g_bar, pol_stream);
+								gmap[j * (uint32_t) kRows + r] = (unsigned char) i;
+								// where row k lands and (cosine) its norm, fetched while the row is in flight; replaced by the key once scored
+								float vn = 1.0f;
+								if (METRIC == M_COS) vn = p.norms[id];
+								hop_key[k] = (uint64_t) bit | ((uint64_t) __float_as_uint(vn) << 32);
 							}
 						}
+						const uint32_t mine = (uint32_t) __popcll(take & (kCol << (uint32_t) row_in_stage));	// slots of my residue
+						uint32_t	   J = mine;
+#pragma unroll
+						for (int off = TPR; off < 32; off <<= 1) J = max(J, __shfl_xor_sync(kFull, J, off));
 						__syncwarp();
-						for (uint32_t g0 = 0; g0 < cnt; g0 += kRows)
+						mbar_wait(g_bar, g_par);
+						g_par ^= 1u;
+						for (uint32_t j = 0; j < J; j++)
 						{
-							const bool	   valid = g0 + row_in_stage < cnt;
-							const uint32_t k = done + (valid ? g0 + row_in_stage : g0);
-							const uint32_t pos = (uint32_t) hop_key[k];
+							const bool	   valid = j < mine;
+							// lanes without a row in this group shadow the group's first row (same address: a broadcast, and its
+							// hop_key[] entry is still a slot position -- it turns into a key only after this group is scored)
+							const uint32_t vm = __ballot_sync(kFull, valid);
+							const uint32_t rr = valid ? (uint32_t) row_in_stage : (uint32_t) (__ffs(vm) - 1) / (uint32_t) TPR;
+							const uint32_t k = done + (uint32_t) gmap[j * (uint32_t) kRows + rr];
+							const uint64_t hk = hop_key[k];
+							const uint32_t pos = (uint32_t) hk;
+							const float	   vn = __uint_as_float((uint32_t) (hk >> 32));
 							const uint32_t my_id = hop_id[k];
-							float		   vn = 1.0f;
-							if (METRIC == M_COS) vn = p.norms[my_id];  // in flight while the rows land
-							if (g0 == 0)
-							{
-								mbar_wait(g_bar, g_par);
-								g_par ^= 1u;
-							}
-							const float *rowp = reinterpret_cast<const float *>(ring_base + (size_t) pos * p.row_smem);
-							const float	 d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
-							__syncwarp();  // every lane has read its row and its hop_key[] position
+							const float	  *rowp = reinterpret_cast<const float *>(ring_base + (size_t) pos * p.row_smem);
+							const float	   d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
+							__syncwarp();  // every lane has read its row and its hop_key[] entry
 							if (sub == 0 && valid)
 							{
 								hop_key[k] = make_key(d, my_id);
@@ -650,7 +668,6 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 								atomicOr(pool_mask, 1ull << pos);  // the row slot is free again
 							}
 						}
-						__syncwarp();
 						done += cnt;
 					}
 				}
