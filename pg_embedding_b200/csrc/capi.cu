@@ -517,8 +517,6 @@ static pgemb_status make_config(const pgemb_index *idx, uint32_t ef, SearchConfi
 	// long L2 rows (>= 4 KB, e.g. 1536-d): 8 lanes per row, rings of 4 rows -> twice as many rings per SM (measured on the
 	// configs[3] row shape: 0.67 -> 0.80 of the HBM roofline, profiles/README.md round 2); PGEMB_L2_TPR8=0 disables
 	sh.tpr = (!res_global && sh.metric == DIST_L2 && env_int("PGEMB_L2_TPR8", 1) != 0 && idx->row_f * 4u >= (uint32_t) env_int("PGEMB_L2_TPR8_MIN_BYTES", 4096)) ? 8u : 4u;
-	// throughput mode: per-row pool instead of rings (search_config.h; PGEMB_ROW_POOL)
-	sh.row_pool = !coop && !res_global && env_int("PGEMB_ROW_POOL", 0) != 0;
 	SearchTuning tu;
 	tu.duty = env_int("PGEMB_RING_DUTY_PCT", 50) / 100.0;
 	tu.want_warps = env_int("PGEMB_WARPS", 0);

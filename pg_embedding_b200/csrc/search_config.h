@@ -30,10 +30,6 @@ struct SearchConfig
 	uint32_t tpr = 4;
 	uint32_t off_vhs = 0, vhs_entries = 0;	// latency mode: visited hash set in shared memory
 	bool	 res_global = false;
-	// throughput mode, row pool: the ring region is ONE pool of `rings` single-row slots (ring_bytes = row_smem) handed out per
-	// row by a 64-bit free mask; a slot waits for its rows on its own mbarrier (off_gbar)
-	bool	 row_pool = false;
-	uint32_t off_gbar = 0;
 };
 
 struct SearchShape
@@ -44,7 +40,6 @@ struct SearchShape
 	// the two result buffers (2 x ef keys) live in global memory instead of the slot's private shared-memory block: for ef so
 	// large that they no longer fit (the reference doubles efSearch without bound, embedding.c:334)
 	bool res_global = false;
-	bool row_pool = false;	// throughput mode: per-row pool instead of 8-row (4-row) rings
 };
 
 struct SearchTuning
@@ -98,7 +93,6 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 	t.off_hopid = off;		off = cfg_align_up(off + hopcap * 4u, 16);
 	t.off_pf = off;			off = cfg_align_up(off + sh.link_stride * 4u, 8);
 	t.off_pfbar = off;		off += 8u;
-	t.off_gbar = off;		off += 8u;
 	t.priv_bytes = cfg_align_up(off, 128);
 	t.ring_bytes = cfg_align_up(rows_per_ring * row_smem, 128);
 	const uint32_t pool_bytes = cfg_align_up((uint32_t) sizeof(RingPool), 128);
@@ -158,41 +152,6 @@ inline int make_search_config(const SearchShape &sh, const SearchTuning &tu, boo
 		return 0;
 	}
 	const int wantW = tu.want_warps, wantR = tu.want_rings;
-	if (sh.row_pool)
-	{
-		// row pool: W slots, everything else of the CTA's shared memory is row slots (at most 64: one free-mask word).  A hop's
-		// gather is ONE round trip whatever its row count, so fewer slots than the ring layout needs keep the pool busy.
-		uint32_t W = (wantW > 0 && wantW <= 32) ? (uint32_t) wantW : 10u;
-		while (W > 1 && pool_bytes + W * t.priv_bytes + 2u * rows_per_ring * row_smem > max_cta) W--;
-		if (pool_bytes + W * t.priv_bytes + 2u * rows_per_ring * row_smem <= max_cta)
-		{
-			uint32_t R = (max_cta - pool_bytes - W * t.priv_bytes) / row_smem;
-			if (R > 64u) R = 64u;
-			if (wantR > 0 && (uint32_t) wantR < R && (uint32_t) wantR >= 2u * rows_per_ring) R = (uint32_t) wantR;
-			t.row_pool = true;
-			t.warps = W;
-			t.rings = R;
-			t.ring_bytes = row_smem;
-			t.off_pool = 0;
-			t.off_ring = pool_bytes;
-			t.off_priv = cfg_align_up(pool_bytes + R * row_smem, 128);
-			t.smem = t.off_priv + W * t.priv_bytes;
-			if (t.smem > max_cta)
-			{
-				R--;
-				t.rings = R;
-				t.off_priv = cfg_align_up(pool_bytes + R * row_smem, 128);
-				t.smem = t.off_priv + W * t.priv_bytes;
-			}
-			t.row_smem = row_smem;
-			t.qt_stride = qt_stride;
-			t.ef = ef;
-			t.slots = W * sh.sm_count;
-			*c = t;
-			return 0;
-		}
-		// does not fit: the ring layout below
-	}
 	if (wantW > 0 && wantW <= 32) bestW = (uint32_t) wantW;
 	if (wantR > 0 && wantR <= (int) kMaxRings) bestR = (uint32_t) wantR;
 	if (bestR > bestW) bestR = bestW;

@@ -79,8 +79,6 @@ struct SearchParams
 	// gathers+scores (about half of a hop), so rings -- the shared-memory-hungry resource that bounds
 	// bytes in flight -- are time-multiplexed between more slots than would fit with one ring each.
 	uint32_t rings, ring_bytes, row_smem, row_bytes, qt_stride;
-	uint32_t row_pool;	// throughput mode, 1: the ring region is a pool of `rings` single-row slots (search_config.h), off_gbar = the slot's gather barrier
-	uint32_t off_gbar;
 	uint32_t prefetch_links;
 	uint32_t visited_pairs;	 // latency mode, 1: the ids of every link list are distinct -> both halves of a list are test-and-set concurrently
 	uint32_t off_pool, off_ring, off_priv, priv_bytes;	 // CTA-level
@@ -111,8 +109,6 @@ inline void apply_config(SearchParams &p, const SearchConfig &cfg, uint32_t row_
 	p.off_acckey = cfg.off_acckey;
 	p.off_evict = cfg.off_evict;
 	p.off_hopid = cfg.off_hopid;
-	p.row_pool = cfg.row_pool ? 1u : 0u;
-	p.off_gbar = cfg.off_gbar;
 }
 
 constexpr uint32_t kNone = 0xffffffffu;
@@ -383,9 +379,6 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 	uint32_t	  *hop_id = reinterpret_cast<uint32_t *>(priv + p.off_hopid);
 	uint32_t	  *pf_links = reinterpret_cast<uint32_t *>(priv + p.off_pf);
 	uint64_t	  *pf_bar = reinterpret_cast<uint64_t *>(priv + p.off_pfbar);
-	uint64_t	  *g_bar = reinterpret_cast<uint64_t *>(priv + p.off_gbar);	// row pool: this slot's gather barrier
-	uint32_t	   g_par = 0;
-	unsigned long long *pool_mask = reinterpret_cast<unsigned long long *>(pool);	// row pool: free mask = (state, pad) as one word
 
 	const uint32_t lt = lanemask_lt();
 	const int	   row_in_stage = lane / TPR;
@@ -408,18 +401,12 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 
 	if (threadIdx.x == 0)
 	{
-		if (!COOP && p.row_pool)
-			*pool_mask = p.rings >= 64u ? ~0ull : ((1ull << p.rings) - 1ull);	// every row slot free
-		else
+		pool->state = (1u << p.rings) - 1u;	// all free, all parities 0
+		for (uint32_t b = 0; b < p.rings; b++)
 		{
-			pool->state = (1u << p.rings) - 1u;	// all free, all parities 0
-			for (uint32_t b = 0; b < p.rings; b++)
-			{
-				mbar_init(&pool->bar[b], 1);
-			}
+			mbar_init(&pool->bar[b], 1);
 		}
 	}
-	if (!COOP && p.row_pool && lane == 0) mbar_init(g_bar, 1);
 	if (vh_shared)
 		for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) vh[i] = 0xffffffffu;
 	if (lane == 0 && (!COOP || warp == 0)) mbar_init(pf_bar, 1);
@@ -568,108 +555,6 @@ __global__ void __launch_bounds__(1024) search_kernel(const SearchParams p)
 					coop_bar(1, blockDim.x);
 					coop_gather<METRIC, TPR>(p, ring_base, &pool->bar[0], coop_par, 0, blockDim.x >> 5, n, hop_id, hop_key, qT, q_tail, qn, main_n, pol_stream);
 					coop_bar(2, blockDim.x);
-				}
-				else if (p.row_pool)
-				{
-					// ---- row pool: the hop's rows go into single-row slots of the CTA's pool, ALL in flight at once (one DRAM
-					// round trip per hop instead of one per 8-row group), each slot given back as soon as its row is scored.
-					// Slot b has bank residue b % kRows (the row pitch is conflict-free for kRows CONSECUTIVE slots), so the rows
-					// that are scored together are chosen AFTER the allocation: scoring group j = the j-th allocated slot of
-					// every residue (a table in the slot's scratch maps (j, residue) -> hop row).  Any free slots will do, no
-					// group reads two rows of one residue; the price is max_r(count_r) groups instead of ceil(cnt / kRows).
-					constexpr unsigned long long kCol = (kRows == 8) ? 0x0101010101010101ull : 0x1111111111111111ull;
-					unsigned char *gmap = reinterpret_cast<unsigned char *>(acc_key);	// [j * kRows + r] -> row of this round (acc_key is free until the queue update)
-					const float	  *qts = qT + sub * p.qt_stride;
-					uint32_t	   done = 0;
-					while (done < n)
-					{
-						const uint32_t want = n - done;
-						unsigned long long take = 0ull;
-						if (lane == 0)
-						{
-							const uint32_t least = want < (uint32_t) kRows ? want : (uint32_t) kRows;  // not worth a round trip for less
-							for (;;)
-							{
-								const unsigned long long m = *reinterpret_cast<volatile unsigned long long *>(pool_mask);
-								if ((uint32_t) __popcll(m) >= least)
-								{
-									unsigned long long t = m;
-									if ((uint32_t) __popcll(m) > want)
-									{
-										t = 0ull;  // the `want` lowest free slots
-										unsigned long long f = m;
-										for (uint32_t i = 0; i < want; i++)
-										{
-											t |= f & (0ull - f);
-											f &= f - 1ull;
-										}
-									}
-									if (atomicCAS(pool_mask, m, m & ~t) == m)
-									{
-										take = t;
-										break;
-									}
-								}
-								else
-									__nanosleep(100);
-							}
-							__threadfence_block();
-						}
-						take = __shfl_sync(kFull, take, 0);
-						const uint32_t cnt = (uint32_t) __popcll(take);
-						if (lane == 0) mbar_arrive_expect_tx(g_bar, cnt * p.row_bytes);
-						__syncwarp();
-#pragma unroll
-						for (uint32_t h = 0; h < 2u; h++)
-						{
-							const uint32_t bit = lane + 32u * h;
-							if ((take >> bit) & 1ull)
-							{
-								const unsigned long long below = take & ((1ull << bit) - 1ull);
-								const uint32_t			 r = bit % (uint32_t) kRows;
-								const uint32_t			 j = (uint32_t) __popcll(below & (kCol << r));
-								const uint32_t			 i = (uint32_t) __popcll(below);
-								const uint32_t			 k = done + i;
-								const uint32_t			 id = hop_id[k];
-								tma_load_1d(ring_base + (size_t) bit * p.row_smem, p.vectors + (size_t) id * p.row_f, p.row_bytes, g_bar, pol_stream);
-								gmap[j * (uint32_t) kRows + r] = (unsigned char) i;
-								// where row k lands and (cosine) its norm, fetched while the row is in flight; replaced by the key once scored
-								float vn = 1.0f;
-								if (METRIC == M_COS) vn = p.norms[id];
-								hop_key[k] = (uint64_t) bit | ((uint64_t) __float_as_uint(vn) << 32);
-							}
-						}
-						const uint32_t mine = (uint32_t) __popcll(take & (kCol << (uint32_t) row_in_stage));	// slots of my residue
-						uint32_t	   J = mine;
-#pragma unroll
-						for (int off = TPR; off < 32; off <<= 1) J = max(J, __shfl_xor_sync(kFull, J, off));
-						__syncwarp();
-						mbar_wait(g_bar, g_par);
-						g_par ^= 1u;
-						for (uint32_t j = 0; j < J; j++)
-						{
-							const bool	   valid = j < mine;
-							// lanes without a row in this group shadow the group's first row (same address: a broadcast, and its
-							// hop_key[] entry is still a slot position -- it turns into a key only after this group is scored)
-							const uint32_t vm = __ballot_sync(kFull, valid);
-							const uint32_t rr = valid ? (uint32_t) row_in_stage : (uint32_t) (__ffs(vm) - 1) / (uint32_t) TPR;
-							const uint32_t k = done + (uint32_t) gmap[j * (uint32_t) kRows + rr];
-							const uint64_t hk = hop_key[k];
-							const uint32_t pos = (uint32_t) hk;
-							const float	   vn = __uint_as_float((uint32_t) (hk >> 32));
-							const uint32_t my_id = hop_id[k];
-							const float	  *rowp = reinterpret_cast<const float *>(ring_base + (size_t) pos * p.row_smem);
-							const float	   d = score_row<METRIC, TPR>(qts, rowp, sub, main_n, q_tail, dim, qn, vn);
-							__syncwarp();  // every lane has read its row and its hop_key[] entry
-							if (sub == 0 && valid)
-							{
-								hop_key[k] = make_key(d, my_id);
-								__threadfence_block();
-								atomicOr(pool_mask, 1ull << pos);  // the row slot is free again
-							}
-						}
-						done += cnt;
-					}
 				}
 				else
 				{

@@ -50,8 +50,7 @@ extern "C" int emu_search_ex(int metric, int coop, const float *vectors, const u
 	sh.tpr = (smem_visited & 0x80000000u) ? 8u : 4u;		  // bit 31: 8 lanes per L2 row
 	const bool res_global = (smem_visited & 0x20000000u) != 0u;  // bit 29: result buffers in global memory (the huge-ef variant)
 	sh.res_global = res_global;
-	sh.row_pool = (smem_visited & 0x10000000u) != 0u && !coop;	  // bit 28: per-row pool instead of rings (throughput mode)
-	smem_visited &= 0x0fffffffu;
+	smem_visited &= 0x1fffffffu;
 	tu.smem_visited = (int) smem_visited;
 	SearchConfig cfg;
 	const int rc = make_search_config(sh, tu, coop != 0, &cfg);

@@ -311,17 +311,6 @@ def test_tensor_core_filter_scan(pg, G, U, oracle_mod, metric, monkeypatch):
         U.test_scan_umma_default_policy(pg, monkeypatch)
 
 
-def test_row_pool_through_the_library(pg, G, oracle_mod, monkeypatch):
-    """PGEMB_ROW_POOL=1 through launch_search (configuration, workspace, kernel parameters) on the emulated library."""
-    monkeypatch.setenv("PGEMB_ROW_POOL", "1")
-    monkeypatch.setenv("PGEMB_COOP", "0")
-    for metric in ("l2", "cosine"):
-        G.test_search_identical_to_oracle(pg, oracle_mod, metric, G.SEARCH_CFGS[3])
-    monkeypatch.setenv("PGEMB_WARPS", "3")
-    monkeypatch.setenv("PGEMB_RINGS", "16")
-    G.test_search_identical_to_oracle(pg, oracle_mod, "manhattan", G.SEARCH_CFGS[1])
-
-
 def test_prototype_l2_eight_lanes(pg_proto, G, oracle_mod, monkeypatch):
     pg = pg_proto
     monkeypatch.setenv("PGEMB_L2_TPR8", "1")

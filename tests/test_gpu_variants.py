@@ -67,21 +67,6 @@ def test_l2_eight_lanes_per_row(pg, oracle_mod, monkeypatch):
 
 
 @pytest.mark.parametrize("metric", METRICS)
-def test_row_pool_gather(pg, oracle_mod, metric, monkeypatch):
-    """PGEMB_ROW_POOL=1: throughput-mode hops gather their rows into single-row slots of a per-CTA pool, all in flight at once."""
-    monkeypatch.setenv("PGEMB_ROW_POOL", "1")
-    monkeypatch.setenv("PGEMB_COOP", "0")                  # small batches too go through the throughput kernel
-    for cfg in (SEARCH_CFGS[1], SEARCH_CFGS[3], SEARCH_CFGS[4], SEARCH_CFGS[6], SEARCH_CFGS[7]):   # [6]: hops of up to 200 rows > the 64-row pool
-        G.test_search_identical_to_oracle(pg, oracle_mod, metric, cfg)
-    if metric == "l2":
-        monkeypatch.setenv("PGEMB_L2_TPR8_MIN_BYTES", "0")  # 8 lanes per row, 4-row scoring groups
-        G.test_search_identical_to_oracle(pg, oracle_mod, metric, SEARCH_CFGS[4])
-    monkeypatch.setenv("PGEMB_WARPS", "3")
-    monkeypatch.setenv("PGEMB_RINGS", "16")                # a 16-row pool for hops of up to 2m rows: several rounds per hop
-    G.test_search_identical_to_oracle(pg, oracle_mod, metric, SEARCH_CFGS[7])
-
-
-@pytest.mark.parametrize("metric", METRICS)
 def test_scan_topk_tiled(pg, oracle_mod, metric, monkeypatch):
     """The exact scan's distance step through scan_tile_kernel (rows staged once per query tile), tensor-core filter off."""
     monkeypatch.setenv("PGEMB_SCAN_TILED", "1")

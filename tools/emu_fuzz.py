@@ -285,7 +285,7 @@ def main():
         pairs = int(rng.integers(0, 2)) if proto else 0
         sv = int(rng.choice([0, 1024, 4096])) if (proto and coop) else 0
         tpr8 = bool(proto and metric == "l2" and rng.integers(0, 2))
-        rowpool = bool(rng.integers(0, 2)) and not coop   # throughput mode: per-row pool instead of rings (the draw once chose the removed LDGSTS gather)
+        rng.integers(0, 2)   # (this draw once chose the removed LDGSTS gather; kept so that old seeds reproduce)
         os.environ["PGEMB_EMU_TMA"] = "late" if rng.integers(0, 2) else "issue"
         os.environ["PGEMB_EMU_JITTER"] = str(int(rng.integers(0, 2)))
         if levels:
@@ -307,10 +307,10 @@ def main():
                 orc.mark_deleted(i)
         want = orc.search_many(q, ef, want_counters=True)
         what = dict(seed=seed, metric=metric, dims=dims, m=m, efc=efc, n=n, levels=levels, ef=ef, nq=nq, coop=coop, warps=warps, rings=rings, grid=grid,
-                    vh=vh, proto=proto, pairs=pairs, sv=sv, tpr8=tpr8, rowpool=rowpool, tma=os.environ["PGEMB_EMU_TMA"], jitter=os.environ["PGEMB_EMU_JITTER"])
+                    vh=vh, proto=proto, pairs=pairs, sv=sv, tpr8=tpr8, tma=os.environ["PGEMB_EMU_TMA"], jitter=os.environ["PGEMB_EMU_JITTER"])
         try:
-            got = T.run_emu(emu_proto if proto else emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=(16 * rings if rowpool else rings), grid=grid, vh=vh,
-                            pairs=pairs, smem_visited=sv, tpr8=tpr8, rowpool=rowpool)
+            got = T.run_emu(emu_proto if proto else emu, metric, coop, x, orc.links(), orc.labels(), q, ef, 2 * m, warps=warps, rings=rings, grid=grid, vh=vh,
+                            pairs=pairs, smem_visited=sv, tpr8=tpr8)
             ok = (got["n"].tolist() == want["n"].tolist() and got["labels"].tobytes() == want["labels"].tobytes()
                   and got["stats"][:, :3].tolist() == want["counters"][:, :3].tolist())
         except AssertionError as e:
