@@ -14,6 +14,7 @@ try:
     d = json.load(open("gpurun_out/r2_bench_n8.json"))
     print("value", d["value"], "e2e", d["e2e"]["value"], "n_gpus", d["n_gpus"])
     print("sharded", json.dumps(d.get("sharded")))
+    print("configs4", json.dumps(d.get("configs4")))
 except Exception as e:
     print("bench FAILED", e)
 PY
