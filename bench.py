@@ -157,21 +157,26 @@ class ClockSampler:
 
 
 def ncu_traffic_bytes(batch):
-    """DRAM read+write bytes of one traversal launch from the committed ncu --set full capture (profiles/), valid for
-    the default 32768-query launch of this workload only; None otherwise."""
-    p = os.path.join(ROOT, "profiles", "r1_search_kernel_cosine768_metrics.csv")
-    if batch != 32768 or not os.path.isfile(p):
-        return None
+    """DRAM read+write bytes of one traversal launch from the committed ncu --set full capture (profiles/; the newest round's),
+    valid for the default 32768-query launch of this workload only; (None, None) otherwise."""
+    if batch != 32768:
+        return None, None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-    tot = 0.0
-    try:
-        for line in open(p):
-            f = line.strip().split(",")
-            if len(f) >= 4 and f[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(f[-1]) * scale.get(f[-2], 1.0)
-    except Exception:
-        return None
-    return int(tot) if tot > 0 else None
+    for name in ("r2_search_kernel_cosine768_metrics.csv", "r1_search_kernel_cosine768_metrics.csv"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.isfile(p):
+            continue
+        tot = 0.0
+        try:
+            for line in open(p):
+                f = line.strip().split(",")
+                if len(f) >= 4 and f[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(f[-1]) * scale.get(f[-2], 1.0)
+        except Exception:
+            continue
+        if tot > 0:
+            return int(tot), name
+    return None, None
 
 
 def measured_peak_gbs():
@@ -290,11 +295,11 @@ def main():
     kms = ms / K                                                                       # this rank's launches (CUDA events on the launching stream)
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (kms * 1e-3) / 1e9
-    traffic = ncu_traffic_bytes(B) if n == 1_000_000 else None
+    traffic, traffic_file = ncu_traffic_bytes(B) if n == 1_000_000 else (None, None)
     roofline = {"bound": "hbm", "kernel": "search_kernel<cosine> (K3: TMA row gather + exact distance + queue update)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": peak_src, "traffic": traffic,
-                "traffic_source": "static: profiles/r1_search_kernel_cosine768_metrics.csv (ncu --set full capture of this launch shape; not re-measured in this run)" if traffic else None,
+                "traffic_source": f"static: profiles/{traffic_file} (ncu --set full capture of this launch shape; not re-measured in this run)" if traffic else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": round(kms, 3), "kernel_ms_source": "timed region / steps (one launch per step)",
                 "per_query": {"dist_evals": float(st[:, 0].mean()), "expansions": float(st[:, 1].mean()),
                               "bytes": float(alg_bytes / B)}}

@@ -69,9 +69,27 @@ def _worker(rank, world, port, out_dir):
     s = sharded.ShardedSearch(local_search, merge)
     od, ol, on = s.search(torch.from_numpy(q), ef)
     assert s.collectives == 1                                     # one all-gather per step, nothing else
+    # the sharded brute-force scan (BASELINE configs[4]'s host logic): every rank scans ITS rows for the whole batch -- here
+    # the oracle's distances, ordered by (dist,label) -- and the same exchange + merge yields the top-k over the whole table
+    kscan = 7
+    lab_all = (np.arange(n, dtype=np.uint64) * np.uint64(3)) + np.uint64(1)
+
+    def local_scan(queries, k):
+        qn = queries.numpy()
+        d = np.full((qn.shape[0], k), np.inf, np.float32); lab = np.full((qn.shape[0], k), -1, np.int64); cnt = np.zeros(qn.shape[0], np.int32)
+        for i in range(qn.shape[0]):
+            dd = oracle.dist_many("port", "l2", qn[i], x[lo:hi])
+            order = sorted((float(dd[j]), int(lab_all[lo + j])) for j in range(hi - lo))[:k]
+            cnt[i] = len(order)
+            d[i, :len(order)] = [o[0] for o in order]; lab[i, :len(order)] = [o[1] for o in order]
+        return torch.from_numpy(d), torch.from_numpy(lab), torch.from_numpy(cnt)
+
+    s2 = sharded.ShardedSearch(local_scan, merge)
+    sd, sl, sn = s2.search(torch.from_numpy(q[:9]), kscan)
+    assert s2.collectives == 1
     # replica mode: query split covers the batch exactly once
     a, b = sharded.split_queries(nq, world, rank)
-    np.save(os.path.join(out_dir, f"r{rank}.npy"), {"od": od, "ol": ol, "on": on, "split": (a, b)}, allow_pickle=True)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), {"od": od, "ol": ol, "on": on, "split": (a, b), "sd": sd, "sl": sl, "sn": sn}, allow_pickle=True)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,6 +102,16 @@ def test_sharded_exchange_world2(tmp_path, oracle_mod):
     # every rank ends with the same merged answer
     assert (res[0]["ol"] == res[1]["ol"]).all() and (res[0]["on"] == res[1]["on"]).all()
     assert res[0]["split"] == (0, 20) and res[1]["split"] == (20, 40)
+    # the sharded scan: identical on both ranks and equal to a brute force over the whole table in (dist,label) order
+    assert (res[0]["sl"] == res[1]["sl"]).all() and (res[0]["sd"] == res[1]["sd"]).all() and (res[0]["sn"] == res[1]["sn"]).all()
+    rng0 = np.random.default_rng(3)
+    x0 = rng0.standard_normal((1201, 12)).astype(np.float32); q0 = rng0.standard_normal((40, 12)).astype(np.float32)
+    lab0 = (np.arange(1201, dtype=np.uint64) * np.uint64(3)) + np.uint64(1)
+    for i in range(9):
+        dd = oracle_mod.dist_many("port", "l2", q0[i], x0)
+        want = sorted((float(dd[j]), int(lab0[j])) for j in range(1201))[:7]
+        assert res[0]["sn"][i] == 7 and res[0]["sl"][i].tolist() == [w[1] for w in want]
+        assert np.array([w[0] for w in want], np.float32).tobytes() == np.asarray(res[0]["sd"][i], np.float32).tobytes()
     # and it equals the oracle run per shard + merged on one process
     from pg_embedding_b200 import sharded
     rng = np.random.default_rng(3)
