@@ -24,7 +24,7 @@ except Exception as e:
     print("bench FAILED", e)
 PY
 say "ncu launch list of the bench command (headline only)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-legs --no-cpu > gpurun_out/rf2_list.log 2>&1; echo "exit $?" | tee -a $L
+PGEMB_PROFILE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 5 --warmup 3 --no-legs --no-cpu > gpurun_out/rf2_list.log 2>&1; echo "exit $?" | tee -a $L   # PGEMB_PROFILE: cudaProfilerStart/Stop bracket exactly the timed region
 grep -c search_kernel gpurun_out/r2_launches.csv | tee -a $L
 say "ncu --set full of the headline traversal launch"
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -f -k regex:search_kernel -c 1 -o gpurun_out/r2_search_kernel_cosine768 python tools/prof_shape.py > gpurun_out/rf2_prof.log 2>&1; echo "exit $?" | tee -a $L
