@@ -477,5 +477,17 @@ def test_new_entry_points_argument_checks(pg):
     _lib.check(lib.pgemb_sharded_merge_device(ex, 2, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p), None))
     want = idx.search_batch(dq, 4)
     assert ol.tobytes() == want["labels"].tobytes() and on.tolist() == want["n"].tolist()
+    # the scan as the local step: same degenerate world, equals the host-pointer scan; argument errors
+    assert lib.pgemb_sharded_scan_device(idx.dev, ex, 2, dq.ctypes.data_as(C.c_void_p), 3, None) == 2        # k != the exchange's
+    assert lib.pgemb_sharded_scan_device(idx.dev, ex, 9, dq.ctypes.data_as(C.c_void_p), 4, None) == 2        # nq > max_nq
+    assert lib.pgemb_sharded_scan_device(None, ex, 2, dq.ctypes.data_as(C.c_void_p), 4, None) == 2
+    _lib.check(lib.pgemb_sharded_scan_device(idx.dev, ex, 2, dq.ctypes.data_as(C.c_void_p), 4, None))
+    _lib.check(lib.pgemb_sharded_merge_device(ex, 2, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p), None))
+    want = idx.scan_topk(dq, 4)
+    assert ol.tobytes() == want["labels"].tobytes() and od.tobytes() == want["dists"].tobytes() and on.tolist() == want["n"].tolist()
+    assert lib.pgemb_scan_topk_device(idx.dev, 2, None, 4, ol.ctypes.data_as(C.c_void_p), None, on.ctypes.data_as(C.c_void_p), None) == 2   # null queries
+    assert lib.pgemb_scan_topk_device(idx.dev, 2, dq.ctypes.data_as(C.c_void_p), 0, ol.ctypes.data_as(C.c_void_p), None, on.ctypes.data_as(C.c_void_p), None) == 2   # k = 0
+    _lib.check(lib.pgemb_scan_topk_device(idx.dev, 2, dq.ctypes.data_as(C.c_void_p), 4, ol.ctypes.data_as(C.c_void_p), None, on.ctypes.data_as(C.c_void_p), None))    # distances optional
+    assert ol.tobytes() == want["labels"].tobytes()
     lib.pgemb_exchange_destroy(ex)
     idx.close()
