@@ -513,8 +513,10 @@ def leg_configs1(args, torch, pg, lib, _lib, local):
             "value": round(B / (ms * 1e-3), 1), "unit": "queries/s", "ms_per_step": round(ms, 3), "steps": K, "warmup": W, "recall_at_10": round(recall, 4),
             "roofline": {"bound": "l2", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "algorithmic_bytes_per_launch": alg,
                          "hbm_peak": hbm, "frac_of_hbm_peak": round(alg / (ms * 1e-3) / 1e9 / hbm, 4),
-                         "note": "working set 51 MB vectors + 13 MB links < 126 MB L2: rows are served by L2, not HBM -- the HBM roof is NOT the binding one "
-                                 "here; the kernel is bound by the dependent-hop latency (7 rows x 512 B per hop) -- see profiles/README.md",
+                         "note": "working set 51 MB vectors + 13 MB links < 126 MB L2: the HBM roof is NOT the binding one here (ncu: DRAM 12 % of peak). "
+                                 "The kernel is bound by instruction issue and the dependent hop chain: 64 % of the issue slots busy with 30 warps per SM, "
+                                 "about 1400 warp instructions of queue / visited / prefetch bookkeeping per hop around 7.5 rows x 512 B of scoring "
+                                 "(profiles/r2_configs1_metrics.csv, profiles/README.md)",
                          "per_query": {"dist_evals": float(st[:, 0].mean()), "expansions": float(st[:, 1].mean())}},
             "cpu_baseline": cpu, "parity": par}
 
