@@ -437,6 +437,11 @@ def test_sharded_scan_two_shards(pg, oracle_mod, monkeypatch, metric, tc):
         lib.pgemb_exchange_destroy(exs[r]); idxs[r].close()
 
 
+def test_device_scan_edge_cases(pg, oracle_mod):
+    import test_gpu_scan_umma as U
+    U.check_device_scan_edge_cases(pg, oracle_mod)
+
+
 def test_ef_beyond_shared_memory(pg, G, oracle_mod, monkeypatch):
     """ef = 20000 through the library on the host: launch_search must fall back to the global-memory result queues by itself;
     PGEMB_RES_GLOBAL=1 forces that variant for ordinary searches too."""

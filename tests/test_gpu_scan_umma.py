@@ -189,3 +189,46 @@ def test_scan_umma_default_policy(pg, monkeypatch):
         c1 = counters()
         assert (c1["tc"] - c0["tc"] == 1) == expect_tc and (c1["exact"] - c0["exact"] == 1) == (not expect_tc), (metric, n)
         idx.close()
+
+
+def check_device_scan_edge_cases(pg, oracle_mod):
+    """pgemb_scan_topk_device on tables smaller than k, on an empty table and with every row deleted: counts, fill values
+    (~0 / +inf) and the host-pointer call's bytes."""
+    from pg_embedding_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    k, nq, dims = 6, 4, 5
+    q = rng.standard_normal((nq, dims)).astype(np.float32)
+    for n, deleted in ((0, False), (3, False), (3, True), (40, False)):
+        idx = pg.HnswIndex(dims, 3, 8, 4, "l2", capacity=max(n, 1))
+        x = rng.standard_normal((n, dims)).astype(np.float32)
+        if n:
+            labels = np.arange(n, dtype=np.uint64) + np.uint64(7)
+            if deleted:
+                labels |= np.uint64(1 << 48)
+            idx.append(x, labels)
+        ol = np.full((nq, k), 123, np.uint64); od = np.full((nq, k), 5.0, np.float32); on = np.full(nq, -1, np.int32)
+        import torch
+        if torch.cuda.is_available():      # a real device: the entry point takes device pointers
+            tq = torch.from_numpy(q).cuda(); tl = torch.from_numpy(ol.view(np.int64)).cuda(); td = torch.from_numpy(od).cuda(); tn = torch.from_numpy(on).cuda()
+            _lib.check(lib.pgemb_scan_topk_device(idx.dev, nq, tq.data_ptr(), k, tl.data_ptr(), td.data_ptr(), tn.data_ptr(), None))
+            torch.cuda.synchronize()
+            ol, od, on = tl.cpu().numpy().view(np.uint64), td.cpu().numpy(), tn.cpu().numpy()
+        else:                              # the host-emulated library (tests/test_capi_emulated.py): all memory is host memory
+            _lib.check(lib.pgemb_scan_topk_device(idx.dev, nq, q.ctypes.data_as(C.c_void_p), k, ol.ctypes.data_as(C.c_void_p), od.ctypes.data_as(C.c_void_p),
+                                                  on.ctypes.data_as(C.c_void_p), None))
+        live = 0 if deleted else n
+        assert on.tolist() == [min(k, live)] * nq, (n, deleted)
+        assert (ol[:, min(k, live):] == np.uint64(0xFFFFFFFFFFFFFFFF)).all() and np.isinf(od[:, min(k, live):]).all()
+        host = idx.scan_topk(q, k)
+        assert ol.tobytes() == host["labels"].tobytes() and od.tobytes() == host["dists"].tobytes() and on.tolist() == host["n"].tolist()
+        if live:
+            for i in range(nq):
+                d = oracle_mod.dist_many("port", "l2", q[i], x)
+                want = sorted((float(d[j]), j + 7) for j in range(n))[:k]
+                assert ol[i, :len(want)].tolist() == [w[1] for w in want]
+        idx.close()
+
+
+def test_device_scan_edge_cases(pg, oracle_mod):
+    check_device_scan_edge_cases(pg, oracle_mod)
