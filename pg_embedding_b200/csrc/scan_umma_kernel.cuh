@@ -589,8 +589,9 @@ __global__ void scan_qconst_init_kernel(const float *__restrict__ qnorm2, uint32
 
 #ifdef PGEMB_HOST_EMULATION
 // Host stand-in for scan_filter_umma_kernel (tests/emu only): the same predicate on a product whose operands are cut to
-// TF32 (10 mantissa bits, truncation) and, with PGEMB_EMU_GEMM_ERR_PPM = x, pushed by +-x ppm of |q||v|: 90 % of the assumed
-// bound must still give exact results, 4x the bound must trip the tripwire.
+// TF32 (10 mantissa bits, truncation) and, with PGEMB_EMU_GEMM_ERR_PPM = x, pushed by +-x ppm of |q||v|: truncation + push up to
+// 90 % of the assumed bound must still give exact results, 4x the bound must trip the tripwire.  (The truncation alone can use
+// 2 * 2^-10 of the bound -- one-dimensional rows do -- so a test's push has to leave that much room.)
 template <int METRIC>
 inline void scan_filter_emulated(const float *queries, uint32_t q_stride, const float *vectors, uint32_t row_f, uint32_t dim, float rel,
 								 const float *qnorm2, const ScanFilterParams &p)

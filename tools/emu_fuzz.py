@@ -226,7 +226,10 @@ def fuzz_scan(a, oracle):
             labels[:: int(rng.integers(2, 9))] |= np.uint64(1 << 48)
         env = {"PGEMB_SCAN_TC_GROWTH": str(rng.choice([2, 3, 8, 16])), "PGEMB_SCAN_TC_CHUNK0_LOG2": str(rng.choice([0, 5, 6, 8])),
                "PGEMB_SCAN_TC_CAP": str(rng.choice([0, 8, 64, 300])), "PGEMB_SCAN_TILED": str(rng.integers(0, 2)),
-               "PGEMB_EMU_GEMM_ERR_PPM": str(float(rng.uniform(0, 0.9)) * 1e6 * (2.0 / 1024.0 + dims / 2097152.0))}
+               # the stand-in's own operand truncation already uses up to 2 * 2^-10 of the assumed bound rel = 1.5 * (2 * 2^-10 + dims * 2^-21):
+               # the extra push gets at most 90 % of what is left (a push of 0.9 * rel / 1.5 ON TOP of a worst-case truncation exceeds
+               # the bound, and the filter then rightly may drop a row: seed 3403124 of the first campaigns, dims 1)
+               "PGEMB_EMU_GEMM_ERR_PPM": str(float(rng.uniform(0, 0.9)) * 1e6 * (1.0 / 1024.0 + 1.5 * dims / 2097152.0))}
         os.environ.update(env)
         idx = pg.HnswIndex(dims, 4, 8, 16, metric, capacity=n)
         idx.append(x, labels)
